@@ -1,0 +1,204 @@
+/*
+ * nw_sm100.h — C ABI of libnw_sm100.so: the B200 (sm_100a) implementation of the
+ * Nadaraya-Watson head hot path of alanqrwang/nwhead.
+ *
+ * The reference has no FFI layer (it is pure PyTorch).  Each entry point below replaces the
+ * torch library calls of one reference function; the citation names that function
+ * (paths relative to the reference repository root).  The Python drop-in package
+ * `nwhead_b200` binds these with ctypes (nwhead_b200/_abi.py); INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it and nothing synchronises with the host;
+ *   - the library allocates no device memory: scratch is passed in by the caller and sized with
+ *     the matching *_plan / *_workspace_bytes query;
+ *   - return value: NW_OK (0) or a negative NW_ERR_* code; nw_last_error() returns a
+ *     thread-local, NUL-terminated description of the last failure on the calling thread;
+ *   - there is no CPU fallback: on a machine without an sm_100 device every compute entry point
+ *     returns NW_ERR_CUDA / NW_ERR_UNSUPPORTED.
+ */
+#ifndef NW_SM100_H_
+#define NW_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NW_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NW_API __attribute__((visibility("default")))
+#else
+#define NW_API
+#endif
+
+#define NW_OK 0
+#define NW_ERR_INVALID (-1)     /* bad argument (shape, alignment, enum) */
+#define NW_ERR_CUDA (-2)        /* a CUDA runtime / driver call failed */
+#define NW_ERR_UNSUPPORTED (-3) /* device is not sm_100, or shape outside the kernel's limits */
+#define NW_ERR_WORKSPACE (-4)   /* caller-provided scratch too small */
+
+/* similarity kernels — nwhead/kernel.py:80-97 (get_kernel) */
+#define NW_KIND_EUCLIDEAN 0   /* -cdist(x, y)                       nwhead/kernel.py:13-15 */
+#define NW_KIND_HYPERSPHERE 1 /* -cdist(normalize(x), normalize(y)) nwhead/kernel.py:17-21 */
+#define NW_KIND_COSINE 2      /* normalize(x) . normalize(y)        nwhead/kernel.py:23-28 */
+#define NW_KIND_DOT 3         /* x . y                              nwhead/kernel.py:30-33 */
+#define NW_KIND_CLIP 4        /* exp(logit_scale) * cosine          nwhead/kernel.py:35-44 */
+
+/* score epilogue of the fused tensor-core forward */
+#define NW_EPI_EUCLID 0 /* score = -sqrt(max(|q|^2 + |s|^2 - 2 q.s, 0)) */
+#define NW_EPI_LINEAR 1 /* score = scale * q.s */
+
+/* operand precision of the tensor-core path */
+#define NW_PREC_BF16 1   /* one bf16 value per feature */
+#define NW_PREC_BF16X3 3 /* hi/lo bf16 split, 3 products: ~fp32 accuracy at 3x the FLOPs */
+
+/* row layouts written by nw_rows_to_bf16 */
+#define NW_ROWS_BANK 0  /* support rows:  [hi]  or [hi | hi | lo] */
+#define NW_ROWS_QUERY 1 /* query rows:    [hi]  or [hi | lo | hi] */
+
+NW_API const char* nw_last_error(void);
+NW_API int nw_abi_version(void);
+/* 0 when the current CUDA device can run the kernels (compute capability 10.x), else NW_ERR_*. */
+NW_API int nw_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Support bank (K0) — replaces the CPU fp32 bank assembled by NWNet._compute_all_support_feats
+ * (nwhead/nw.py:213-243) and stored by SupportSetEval.build_infer_iters (nwhead/support.py:113-120),
+ * and the per-call `.to(device)` of the whole bank in NWNet.predict (nwhead/nw.py:156).
+ * ------------------------------------------------------------------------------------------ */
+
+/* bf16 elements per stored row for feature width d: precision*d rounded up to a multiple of 64. */
+NW_API int nw_row_elems(int d, int precision);
+
+/* labels_i64[perm[i]] -> int32, validating 0 <= label < C (F.one_hot would raise, nwhead/nw.py:276)
+ * and that the gathered sequence is non-decreasing.  status_out[0] = #out-of-range labels,
+ * status_out[1] = #descents (0 means class-sorted).  perm may be NULL (identity). */
+NW_API int nw_labels_to_i32(const int64_t* labels_i64, const int64_t* perm, int64_t n, int n_classes,
+                     int32_t* labels_out, int32_t* status_out, void* stream);
+
+/* offsets[c] = first row of class c in a class-sorted label vector, offsets[C] = n. */
+NW_API int nw_class_offsets(const int32_t* labels_sorted, int64_t n, int n_classes, int32_t* offsets, void* stream);
+
+/* mean over rows of a row-major fp32 matrix (used to centre euclidean banks before bf16 rounding;
+ * distances are translation invariant).  workspace: nw_column_mean_workspace_bytes(d). */
+NW_API size_t nw_column_mean_workspace_bytes(int d);
+NW_API int nw_column_mean(const float* rows, int64_t n, int d, int64_t ld, float* mean_out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* out[i, :] = bf16 layout of f(rows[perm[i], :]) with f = optional centring (x - center) followed by
+ * optional L2 normalisation x / max(|x|, 1e-12) (F.normalize, nwhead/kernel.py:19-20,25-26,41-42);
+ * sqnorm_out[i] = squared norm of the values the tensor cores will see.
+ * out has row stride row_elems = nw_row_elems(d, precision); padding columns are zero. */
+NW_API int nw_rows_to_bf16(const float* rows, int64_t n, int d, int64_t ld, const int64_t* perm, const float* center,
+                    int normalize, int layout, int precision, void* out_bf16, int row_elems,
+                    float* sqnorm_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused tensor-core forward (K1) — replaces, for a shared 2-D support with N > 25,
+ * NWHead.forward (nwhead/nw.py:266-289): one_hot (276), expand (277-279), kernel (283:
+ * nwhead/kernel.py:13-44), softmax (285), bmm with the one-hot labels (287), log(.+1e-12) (289).
+ * The (B, N) score matrix never reaches HBM.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct nw_forward_plan_t {
+  int q_tiles;         /* ceil(B / 128) */
+  int s_tiles;         /* ceil(N / 256) */
+  int chunks;          /* contiguous support chunks the bank is cut into */
+  int tiles_per_chunk; /* support tiles per chunk */
+  int grid;            /* persistent CTAs launched */
+  int64_t side_elems;  /* floats of scratch `side` required: chunks * B * 2 */
+} nw_forward_plan_t;
+
+NW_API int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t* plan_out);
+
+/* class_lse[b, c] = log sum_{j : labels[j] == c} exp(score(b, j)); -inf for classes with no support
+ * row in this bank (or bank shard).  Inputs are the bf16 layouts of nw_rows_to_bf16.
+ * labels must be class-sorted int32.  q_sqnorm / s_sqnorm are only read for NW_EPI_EUCLID.
+ * side: scratch of plan.side_elems floats. */
+NW_API int nw_forward_class_lse(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
+                         const void* bank_bf16, const float* s_sqnorm, const int32_t* labels, int64_t n_support,
+                         int row_elems, int n_classes, float* class_lse, float* side, int64_t side_elems,
+                         void* stream);
+
+/* logp[b, c] = log( exp(class_lse[b,c] - logsumexp_c class_lse[b,:]) + 1e-12 )  (nwhead/nw.py:285-289).
+ * With a sharded bank, all-reduce class_lse with MAX across ranks first (each class is owned by one
+ * rank, so the merge is exact). */
+NW_API int nw_logp_from_class_lse(const float* class_lse, int n_query, int n_classes, float* logp, void* stream);
+
+/* Exact merge of two class-LSE tables (generic row-sharded banks): a = log(exp(a) + exp(b)). */
+NW_API int nw_class_lse_merge(float* a, const float* b, int64_t n_elems, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Direct fp32 path — exact-difference scores, any shape, 2-D or per-query 3-D support, with
+ * gradients.  Replaces NWHead.forward + its autograd for episodic training (nwhead/nw.py:162-211,
+ * train.py:412-415) and the direct `kernel(x, y)` call of NWNet.get_neighbors (nwhead/nw.py:248).
+ * torch.cdist itself switches to exact differences for <= 25 rows.
+ * ------------------------------------------------------------------------------------------ */
+
+/* scores[b, j] = kernel(q[b], s[j]) (support_batched = 0, s is (N, d)) or kernel(q[b], s[b, j])
+ * (support_batched = 1, s is (B, N, d)).  scale: exp(logit_scale) for NW_KIND_CLIP, ignored otherwise. */
+NW_API int nw_direct_scores(int kind, float scale, const float* q, int n_query, int d, const float* s,
+                     int64_t n_support, int support_batched, float* scores, void* stream);
+
+/* softmax over the support axis + label aggregation + log: logp (B, C), row_lse (B) = logsumexp_j
+ * scores[b, :] (saved for backward).  labels int64 as handed to F.one_hot: (N) or (B, N). */
+NW_API int nw_direct_aggregate(const float* scores, const int64_t* labels, int labels_batched, int n_query,
+                        int64_t n_support, int n_classes, float* logp, float* row_lse, int32_t* status_out,
+                        void* stream);
+
+/* closed-form backward.  workspace: nw_direct_backward_workspace_elems(...) floats.
+ * grad_q (B, d) and grad_s ((N, d) or (B, N, d)) may each be NULL when not needed.
+ * grad_scale_rows (B) receives per-query partial sums of d/d(logit_scale) for NW_KIND_CLIP (may be
+ * NULL).  Coincident points contribute zero gradient, as torch.cdist's backward does. */
+NW_API int64_t nw_direct_backward_workspace_elems(int n_query, int64_t n_support, int support_batched);
+NW_API int nw_direct_backward(int kind, float scale, const float* q, int n_query, int d, const float* s,
+                       int64_t n_support, int support_batched, const int64_t* labels, int labels_batched,
+                       int n_classes, const float* scores, const float* row_lse, const float* logp,
+                       const float* grad_out, float* workspace, float* grad_q, float* grad_s,
+                       float* grad_scale_rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cluster mode (K3) — replaces compute_clusters(embeddings, labels, n_clusters=1)
+ * (nwhead/utils.py:218-246; sklearn KMeans with one cluster is the class mean).
+ * out[c, :] = mean of the rows of class c (zeros for an empty class); rows are addressed through
+ * perm (NULL = identity) so that offsets describe a class-sorted order.
+ * workspace: nw_class_centroids_workspace_bytes(n_classes, d).
+ * ------------------------------------------------------------------------------------------ */
+NW_API size_t nw_class_centroids_workspace_bytes(int n_classes, int d);
+NW_API int nw_class_centroids(const float* rows, int d, int64_t ld, const int64_t* perm, const int32_t* offsets,
+                       int n_classes, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * support_influence (K4) — replaces the per-query Python loop of util/metric.py:23-50.
+ * ------------------------------------------------------------------------------------------ */
+
+/* out[r] = argmax_c onehot[r, c] (first maximum, as torch.argmax) — util/metric.py:42-43. */
+NW_API int nw_onehot_argmax(const float* onehot, int64_t n_rows, int n_classes, int32_t* out, void* stream);
+
+/* out[b, g, j] = log( (p_b - p_b * w[b, j]) / (p_b - w[b, j] * [slabel[g, j] == qlabel[b]]) ),
+ * p_b = softmaxes[b, qlabel[b]]   (util/metric.py:45-47).  n_label_sets = 1 for (N, C) slabels,
+ * = B for the documented (B, N, C) slabels, whose argmax broadcasts to a (B, B, N) result. */
+NW_API int nw_support_influence(const float* softmaxes, const int32_t* qlabel, const float* sweights,
+                         const int32_t* slabel, int n_query, int n_label_sets, int64_t n_support,
+                         int n_classes, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Neighbour ranking (K5) — replaces torch.argsort(scores, descending=True) of NWNet.get_neighbors
+ * (nwhead/nw.py:248-249) and KNN.__call__ (nwhead/utils.py:187-189).
+ * idx_out (R, k) int64 column indices of the k largest scores of each row, best first; equal scores
+ * are ordered by ascending index.  k == n_cols gives the full ranking.
+ * workspace: nw_rank_rows_workspace_bytes(n_rows, n_cols).
+ * ------------------------------------------------------------------------------------------ */
+NW_API size_t nw_rank_rows_workspace_bytes(int n_rows, int64_t n_cols);
+NW_API int nw_rank_rows(const float* scores, int n_rows, int64_t n_cols, int64_t k, int64_t* idx_out, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NW_SM100_H_ */

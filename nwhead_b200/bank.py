@@ -1,0 +1,220 @@
+"""Device-resident support bank and the tensor-core forward built on it.
+
+Replaces the CPU fp32 bank of the reference (nwhead/nw.py:118-125, 213-243; nwhead/support.py:113-120)
+and the per-call whole-bank host->device copy in NWNet.predict (nwhead/nw.py:156).
+
+HBM layout (all contiguous, 16-byte aligned):
+    feats_bf16 (N, row_elems) bf16   row_elems = precision*d rounded up to 64 (one 128-B TMA row per k-block)
+    sqnorm     (N,)          fp32    squared norms of the ROUNDED rows (euclidean kinds)
+    labels     (N,)          int32   class-sorted
+    offsets    (C+1,)        int32   first row of every class
+    perm       (N,)          int64   bank row -> row of the tensor the bank was built from (None = identity)
+    center     (d,)          fp32    column mean removed before rounding (euclidean only)
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from . import _abi
+from ._abi import KIND, check, load, ptr, stream_of
+
+NORMALISED_KINDS = ("hypersphere_euclidean", "cosine", "clip")
+EUCLID_KINDS = ("euclidean", "hypersphere_euclidean")
+AUTO_X3_MAX_ELEMS = 1 << 26  # 'auto' uses the 3-product split up to 64 Mi bank elements
+
+
+def resolve_precision(precision: str, n: int, d: int) -> int:
+    precision = os.environ.get("NW_B200_PRECISION", precision)
+    if precision == "auto":
+        return _abi.PREC_BF16X3 if n * d <= AUTO_X3_MAX_ELEMS else _abi.PREC_BF16
+    if precision == "bf16":
+        return _abi.PREC_BF16
+    if precision == "bf16x3":
+        return _abi.PREC_BF16X3
+    raise ValueError(f"unknown precision {precision!r} (use 'auto', 'bf16' or 'bf16x3')")
+
+
+def rows_to_bf16(rows: torch.Tensor, *, perm, center, normalize: bool, layout: int, precision: int):
+    """nw_rows_to_bf16: fp32 (R, d) -> (bf16 (R, row_elems), sqnorm (R,))."""
+    lib = load()
+    assert rows.dim() == 2 and rows.dtype == torch.float32 and rows.stride(1) == 1
+    n, d = rows.shape
+    row_elems = lib.nw_row_elems(d, precision)
+    out = torch.empty((n, row_elems), dtype=torch.bfloat16, device=rows.device)
+    sq = torch.empty((n,), dtype=torch.float32, device=rows.device)
+    check(
+        lib.nw_rows_to_bf16(ptr(rows), n, d, rows.stride(0), ptr(perm), ptr(center), int(normalize), layout,
+                            precision, ptr(out), row_elems, ptr(sq), stream_of(rows.device)),
+        "nw_rows_to_bf16",
+    )
+    return out, sq
+
+
+class SupportBank:
+    """A class-sorted support set resident in HBM in the layout the fused forward consumes."""
+
+    def __init__(self, feats_bf16, sqnorm, labels_i32, offsets, perm, center, kind, precision, d, n_classes):
+        self.feats_bf16 = feats_bf16
+        self.sqnorm = sqnorm
+        self.labels = labels_i32
+        self.offsets = offsets
+        self.perm = perm
+        self.center = center
+        self.kind = kind
+        self.precision = precision
+        self.d = d
+        self.n_classes = n_classes
+
+    def __len__(self):
+        return self.feats_bf16.shape[0]
+
+    @property
+    def device(self):
+        return self.feats_bf16.device
+
+    @property
+    def row_elems(self):
+        return self.feats_bf16.shape[1]
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.feats_bf16, self.sqnorm, self.labels, self.offsets))
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def build(feats: torch.Tensor, labels: torch.Tensor, n_classes: int, kind: str = "euclidean",
+              precision: str = "auto", center: Optional[torch.Tensor] = None, use_center: bool = True,
+              class_range=None) -> "SupportBank":
+        """feats (N, d) fp32 CUDA, labels (N,) int64 CUDA (any order).  Raises like F.one_hot
+        (nwhead/nw.py:276) when a label is outside [0, n_classes)."""
+        if kind not in KIND:
+            raise NotImplementedError(kind)
+        dev = _abi.require_cuda(feats, labels)
+        lib = load()
+        if feats.dtype != torch.float32:
+            raise TypeError(f"support features must be float32, got {feats.dtype}")  # reference: fp64 raises
+        if labels.dtype != torch.int64:
+            raise RuntimeError("one_hot is only applicable to index tensor of type LongTensor.")
+        feats = feats.detach()
+        if feats.stride(1) != 1:
+            feats = feats.contiguous()
+        labels = labels.detach().contiguous()
+        n, d = feats.shape
+        st = stream_of(dev)
+        prec = resolve_precision(precision, n, d)
+
+        labels_i32 = torch.empty((n,), dtype=torch.int32, device=dev)
+        status = torch.empty((2,), dtype=torch.int32, device=dev)
+        check(lib.nw_labels_to_i32(ptr(labels), None, n, n_classes, ptr(labels_i32), ptr(status), st),
+              "nw_labels_to_i32")
+        bad, descents = status.tolist()
+        if bad:
+            raise RuntimeError("Class values must be smaller than num_classes.")
+        perm = None
+        if descents:  # unsorted support: class-sort it (stable).  torch.sort is plumbing, not the hot path.
+            perm = torch.sort(labels, stable=True).indices.contiguous()
+            check(lib.nw_labels_to_i32(ptr(labels), ptr(perm), n, n_classes, ptr(labels_i32), ptr(status), st),
+                  "nw_labels_to_i32")
+        offsets = torch.empty((n_classes + 1,), dtype=torch.int32, device=dev)
+        check(lib.nw_class_offsets(ptr(labels_i32), n, n_classes, ptr(offsets), st), "nw_class_offsets")
+
+        if kind == "euclidean" and use_center and center is None:
+            center = torch.empty((d,), dtype=torch.float32, device=dev)
+            ws_bytes = lib.nw_column_mean_workspace_bytes(d)
+            ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=dev)
+            check(lib.nw_column_mean(ptr(feats), n, d, feats.stride(0), ptr(center), ptr(ws), ws_bytes, st),
+                  "nw_column_mean")
+        if kind != "euclidean":
+            center = None
+        feats_bf16, sqnorm = rows_to_bf16(feats, perm=perm, center=center, normalize=kind in NORMALISED_KINDS,
+                                          layout=_abi.ROWS_BANK, precision=prec)
+        return SupportBank(feats_bf16, sqnorm, labels_i32, offsets, perm, center, kind, prec, d, n_classes)
+
+    # ------------------------------------------------------------------------------------------
+    def subset(self, bank_rows: torch.Tensor) -> "SupportBank":
+        """Bank restricted to the given bank rows (must keep the class-sorted order): used by
+        mode='random' (nwhead/support.py:126-129, 139) and by class-aligned sharding."""
+        lib = load()
+        idx = bank_rows.to(self.device, torch.int64)
+        labels = self.labels.index_select(0, idx).contiguous()
+        offsets = torch.empty((self.n_classes + 1,), dtype=torch.int32, device=self.device)
+        check(lib.nw_class_offsets(ptr(labels), labels.numel(), self.n_classes, ptr(offsets), stream_of(self.device)),
+              "nw_class_offsets")
+        perm = idx if self.perm is None else self.perm.index_select(0, idx)
+        return SupportBank(self.feats_bf16.index_select(0, idx).contiguous(), self.sqnorm.index_select(0, idx).contiguous(),
+                           labels, offsets, perm, self.center, self.kind, self.precision, self.d, self.n_classes)
+
+    def class_shard(self, rank: int, world: int) -> "SupportBank":
+        """Contiguous class-aligned shard: rank r owns classes [r*C/R, (r+1)*C/R)."""
+        c_lo = (rank * self.n_classes) // world
+        c_hi = ((rank + 1) * self.n_classes) // world
+        off = self.offsets[[c_lo, c_hi]].tolist()
+        r0, r1 = off
+        if r1 <= r0:
+            raise ValueError(f"rank {rank} owns no support rows (classes [{c_lo},{c_hi}))")
+        sl = slice(r0, r1)
+        lib = load()
+        labels = self.labels[sl].contiguous()
+        offsets = torch.empty((self.n_classes + 1,), dtype=torch.int32, device=self.device)
+        check(lib.nw_class_offsets(ptr(labels), labels.numel(), self.n_classes, ptr(offsets), stream_of(self.device)),
+              "nw_class_offsets")
+        perm = (torch.arange(r0, r1, device=self.device) if self.perm is None else self.perm[sl]).contiguous()
+        return SupportBank(self.feats_bf16[sl].contiguous(), self.sqnorm[sl].contiguous(), labels, offsets, perm,
+                           self.center, self.kind, self.precision, self.d, self.n_classes)
+
+    # ------------------------------------------------------------------------------------------
+    def prepare_queries(self, q: torch.Tensor):
+        """fp32 queries -> (bf16 rows in the query layout, squared norms), centred / normalised like the bank."""
+        if q.dtype != torch.float32:
+            raise TypeError(f"query features must be float32, got {q.dtype}")
+        q = q.detach()
+        if q.dim() != 2 or q.shape[1] != self.d:
+            raise ValueError(f"queries must be (B, {self.d}), got {tuple(q.shape)}")
+        if q.stride(1) != 1:
+            q = q.contiguous()
+        return rows_to_bf16(q, perm=None, center=self.center, normalize=self.kind in NORMALISED_KINDS,
+                            layout=_abi.ROWS_QUERY, precision=self.precision)
+
+    def class_lse(self, q: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        """(B, C) per-class log-sum-exp of the scores against this bank (−inf for absent classes)."""
+        _abi.require_cuda(q, self.feats_bf16)
+        q_bf16, q_sq = self.prepare_queries(q)
+        return self.class_lse_prepared(q_bf16, q_sq, scale)
+
+    def class_lse_prepared(self, q_bf16: torch.Tensor, q_sq: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        lib = load()
+        b = q_bf16.shape[0]
+        n = len(self)
+        plan = _abi.forward_plan(b, n)
+        dev = self.device
+        out = torch.empty((b, self.n_classes), dtype=torch.float32, device=dev)
+        side = torch.empty((max(int(plan.side_elems), 1),), dtype=torch.float32, device=dev)
+        epi = _abi.EPI_EUCLID if self.kind in EUCLID_KINDS else _abi.EPI_LINEAR
+        check(
+            lib.nw_forward_class_lse(epi, float(scale), ptr(q_bf16), ptr(q_sq), b, ptr(self.feats_bf16),
+                                     ptr(self.sqnorm), ptr(self.labels), n, self.row_elems, self.n_classes,
+                                     ptr(out), ptr(side), side.numel(), stream_of(dev)),
+            "nw_forward_class_lse",
+        )
+        return out
+
+    def forward(self, q: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        """log(softmax-weighted label aggregation + 1e-12): NWHead.forward (nwhead/nw.py:266-289)."""
+        return logp_from_class_lse(self.class_lse(q, scale))
+
+
+def logp_from_class_lse(class_lse: torch.Tensor) -> torch.Tensor:
+    lib = load()
+    b, c = class_lse.shape
+    out = torch.empty_like(class_lse)
+    check(lib.nw_logp_from_class_lse(ptr(class_lse), b, c, ptr(out), stream_of(class_lse.device)),
+          "nw_logp_from_class_lse")
+    return out
+
+
+def class_lse_merge_(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a <- log(exp(a) + exp(b)) elementwise (generic row-sharded merge)."""
+    check(load().nw_class_lse_merge(ptr(a), ptr(b), a.numel(), stream_of(a.device)), "nw_class_lse_merge")
+    return a

@@ -1,0 +1,333 @@
+// K3 class centroids, K4 support influence, K5 neighbour ranking — HBM-bound streaming kernels.
+
+#include "nw_common.cuh"
+
+namespace nw {
+namespace aux {
+
+// ---------------------------------------------------------------------------------------------
+// K3: per-class mean over a class-sorted fp32 matrix (reference compute_clusters with n_clusters=1,
+// nwhead/utils.py:218-246).  Algorithmic traffic: N*d*4 bytes read once + C*d*4 written.
+// Grid (class, column block, row split): every block streams whole 4 KB row segments (coalesced,
+// 16-B vector loads, 4 independent accumulators per thread); partials are combined in fixed order.
+// ---------------------------------------------------------------------------------------------
+constexpr int CENT_SPLITS = 8;
+constexpr int CENT_THREADS = 256;
+
+template <bool VEC>
+__global__ void __launch_bounds__(CENT_THREADS) centroid_partial_kernel(const float* __restrict__ rows, int d,
+                                                                        long long ld,
+                                                                        const int64_t* __restrict__ perm,
+                                                                        const int32_t* __restrict__ offsets,
+                                                                        float* __restrict__ partial, int n_classes) {
+  const int c = blockIdx.x;
+  const int split = blockIdx.z;
+  const int lo = offsets[c], hi = offsets[c + 1];
+  const int per = (hi - lo + CENT_SPLITS - 1) / CENT_SPLITS;
+  const int r0 = lo + split * per;
+  const int r1 = min(r0 + per, hi);
+  float* dst = partial + (size_t(split) * n_classes + c) * d;
+  if (VEC) {
+    const int col = (blockIdx.y * CENT_THREADS + threadIdx.x) * 4;
+    if (col >= d) return;
+    float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
+    int r = r0;
+    for (; r + 3 < r1; r += 4) {
+      const float4 v0 = __ldcs(reinterpret_cast<const float4*>(rows + (perm ? perm[r] : r) * ld + col));
+      const float4 v1 = __ldcs(reinterpret_cast<const float4*>(rows + (perm ? perm[r + 1] : r + 1) * ld + col));
+      const float4 v2 = __ldcs(reinterpret_cast<const float4*>(rows + (perm ? perm[r + 2] : r + 2) * ld + col));
+      const float4 v3 = __ldcs(reinterpret_cast<const float4*>(rows + (perm ? perm[r + 3] : r + 3) * ld + col));
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+      a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+      a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+      a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+    }
+    for (; r < r1; ++r) {
+      const float4 v0 = __ldcs(reinterpret_cast<const float4*>(rows + (perm ? perm[r] : r) * ld + col));
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+    float4 o;
+    o.x = (a0.x + a1.x) + (a2.x + a3.x);
+    o.y = (a0.y + a1.y) + (a2.y + a3.y);
+    o.z = (a0.z + a1.z) + (a2.z + a3.z);
+    o.w = (a0.w + a1.w) + (a2.w + a3.w);
+    *reinterpret_cast<float4*>(dst + col) = o;
+  } else {
+    const int col = blockIdx.y * CENT_THREADS + threadIdx.x;
+    if (col >= d) return;
+    float a = 0.f;
+    for (int r = r0; r < r1; ++r) a += rows[(perm ? perm[r] : r) * ld + col];
+    dst[col] = a;
+  }
+}
+
+__global__ void centroid_finish_kernel(const float* __restrict__ partial, const int32_t* __restrict__ offsets,
+                                       int n_classes, int d, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_classes * d) return;
+  const int c = int(i / d);
+  const int cnt = offsets[c + 1] - offsets[c];
+  float acc = 0.f;
+#pragma unroll
+  for (int s = 0; s < CENT_SPLITS; ++s) acc += partial[size_t(s) * n_classes * d + i];
+  out[i] = cnt > 0 ? acc / float(cnt) : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: support influence (reference util/metric.py:23-50).  8 B per (query, support) pair.
+// ---------------------------------------------------------------------------------------------
+__global__ void onehot_argmax_kernel(const float* __restrict__ onehot, long long n_rows, int n_classes,
+                                     int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const float* p = onehot + r * n_classes;
+  float best = __int_as_float(0xff800000);
+  int bi = 0x7fffffff;
+  for (int c = lane; c < n_classes; c += 32) {
+    const float v = p[c];
+    if (v > best || (v == best && c < bi)) {
+      best = v;
+      bi = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  if (lane == 0) out[r] = bi;
+}
+
+__device__ __forceinline__ float influence_one(float p, float w, bool same) {
+  // torch: log((p - p*w) / (p - w*indicator))   (util/metric.py:47), IEEE division, +inf / nan preserved
+  const float num = p - p * w;
+  const float den = p - (same ? w : 0.0f);
+  return logf(num / den);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) influence_kernel(const float* __restrict__ softmaxes,
+                                                        const int32_t* __restrict__ qlabel,
+                                                        const float* __restrict__ sweights,
+                                                        const int32_t* __restrict__ slabel, long long n_support,
+                                                        int n_classes, int n_sets, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int g = blockIdx.z;
+  const int qy = qlabel[b];
+  const float p = softmaxes[(long long)b * n_classes + qy];
+  const float* w = sweights + (long long)b * n_support;
+  const int32_t* sl = slabel + (long long)g * n_support;
+  float* o = out + ((long long)b * n_sets + g) * n_support;
+  if (VEC) {
+    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j >= n_support) return;
+    const float4 wv = __ldcs(reinterpret_cast<const float4*>(w + j));
+    const int4 lv = *reinterpret_cast<const int4*>(sl + j);
+    float4 r;
+    r.x = influence_one(p, wv.x, lv.x == qy);
+    r.y = influence_one(p, wv.y, lv.y == qy);
+    r.z = influence_one(p, wv.z, lv.z == qy);
+    r.w = influence_one(p, wv.w, lv.w == qy);
+    __stcs(reinterpret_cast<float4*>(o + j), r);
+  } else {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_support) return;
+    o[j] = influence_one(p, w[j], sl[j] == qy);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: per-row descending ranking by bitonic sort of 64-bit (score, index) keys.
+// ---------------------------------------------------------------------------------------------
+constexpr int SORT_CHUNK = 4096;  // keys sorted per block in shared memory (32 KB)
+
+__device__ __forceinline__ uint64_t make_key(float v, uint32_t idx) {
+  uint32_t u = __float_as_uint(v);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-orderable
+  return (uint64_t(~u) << 32) | idx;               // descending score, ascending index on ties
+}
+
+__global__ void rank_init_kernel(const float* __restrict__ scores, long long n_cols, long long padded,
+                                 uint64_t* __restrict__ keys) {
+  const long long r = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= padded) return;
+  keys[r * padded + i] = i < n_cols ? make_key(scores[r * n_cols + i], uint32_t(i)) : ~uint64_t(0);
+}
+
+__device__ __forceinline__ void cmp_swap(uint64_t& a, uint64_t& b, bool up) {
+  if ((a > b) == up) {
+    const uint64_t t = a;
+    a = b;
+    b = t;
+  }
+}
+
+// Runs every (size, stride) step with stride < SORT_CHUNK for size in [size_lo, size_hi] on one chunk.
+__global__ void __launch_bounds__(1024) rank_smem_kernel(uint64_t* __restrict__ keys, long long padded,
+                                                         long long size_lo, long long size_hi) {
+  __shared__ uint64_t sm[SORT_CHUNK];
+  const long long row_base = (long long)blockIdx.y * padded;
+  const long long base = (long long)blockIdx.x * SORT_CHUNK;
+  const int n = int(padded < SORT_CHUNK ? padded : SORT_CHUNK);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = keys[row_base + base + i];
+  __syncthreads();
+  for (long long size = size_lo; size <= size_hi; size <<= 1) {
+    long long stride = size >> 1;
+    if (stride >= SORT_CHUNK) stride = SORT_CHUNK >> 1;
+    for (; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+        const int i = int(2 * t - (t & (stride - 1)));
+        const bool up = ((base + i) & size) == 0;
+        cmp_swap(sm[i], sm[i + stride], up);
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) keys[row_base + base + i] = sm[i];
+}
+
+__global__ void rank_global_step_kernel(uint64_t* __restrict__ keys, long long padded, long long size,
+                                        long long stride) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= padded / 2) return;
+  uint64_t* row = keys + (long long)blockIdx.y * padded;
+  const long long i = 2 * t - (t & (stride - 1));
+  const bool up = (i & size) == 0;
+  uint64_t a = row[i], b = row[i + stride];
+  if ((a > b) == up) {
+    row[i] = b;
+    row[i + stride] = a;
+  }
+}
+
+__global__ void rank_emit_kernel(const uint64_t* __restrict__ keys, long long padded, long long k,
+                                 int64_t* __restrict__ idx_out) {
+  const long long r = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  idx_out[r * k + i] = int64_t(keys[r * padded + i] & 0xffffffffull);
+}
+
+static long long next_pow2(long long n) {
+  long long p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+}  // namespace aux
+}  // namespace nw
+
+using namespace nw;
+
+extern "C" size_t nw_class_centroids_workspace_bytes(int n_classes, int d) {
+  if (n_classes <= 0 || d <= 0) return 0;
+  return size_t(aux::CENT_SPLITS) * size_t(n_classes) * size_t(d) * sizeof(float);
+}
+
+extern "C" int nw_class_centroids(const float* rows, int d, int64_t ld, const int64_t* perm,
+                                  const int32_t* offsets, int n_classes, float* out, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(rows && offsets && out && workspace, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(d > 0 && ld >= d && n_classes > 0, NW_ERR_INVALID, "bad shape");
+  NW_REQUIRE(n_classes <= 65535 * 32, NW_ERR_UNSUPPORTED, "too many classes");
+  NW_REQUIRE(workspace_bytes >= nw_class_centroids_workspace_bytes(n_classes, d), NW_ERR_WORKSPACE,
+             "workspace too small");
+  const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(workspace) & 15) == 0);
+  float* partial = static_cast<float*>(workspace);
+  if (vec) {
+    dim3 grid(n_classes, ceil_div(d, aux::CENT_THREADS * 4), aux::CENT_SPLITS);
+    aux::centroid_partial_kernel<true><<<grid, aux::CENT_THREADS, 0, stream>>>(rows, d, ld, perm, offsets, partial,
+                                                                               n_classes);
+  } else {
+    dim3 grid(n_classes, ceil_div(d, aux::CENT_THREADS), aux::CENT_SPLITS);
+    aux::centroid_partial_kernel<false><<<grid, aux::CENT_THREADS, 0, stream>>>(rows, d, ld, perm, offsets,
+                                                                                partial, n_classes);
+  }
+  NW_CUDA_OK(cudaGetLastError());
+  const long long total = (long long)n_classes * d;
+  aux::centroid_finish_kernel<<<unsigned(ceil_div_ll(total, 256)), 256, 0, stream>>>(partial, offsets, n_classes, d,
+                                                                                    out);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_onehot_argmax(const float* onehot, int64_t n_rows, int n_classes, int32_t* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(onehot && out, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n_rows > 0 && n_classes > 0, NW_ERR_INVALID, "shapes must be positive");
+  aux::onehot_argmax_kernel<<<unsigned(ceil_div_ll(n_rows, 8)), 256, 0, stream>>>(onehot, n_rows, n_classes, out);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_support_influence(const float* softmaxes, const int32_t* qlabel, const float* sweights,
+                                    const int32_t* slabel, int n_query, int n_label_sets, int64_t n_support,
+                                    int n_classes, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(softmaxes && qlabel && sweights && slabel && out, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n_query > 0 && n_support > 0 && n_classes > 0 && n_label_sets > 0, NW_ERR_INVALID,
+             "shapes must be positive");
+  NW_REQUIRE(n_query <= 65535 && n_label_sets <= 65535, NW_ERR_UNSUPPORTED,
+             "n_query and n_label_sets are limited to 65535 per call");
+  const bool vec = (n_support % 4 == 0) && ((reinterpret_cast<uintptr_t>(sweights) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(slabel) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (vec) {
+    dim3 grid(unsigned(ceil_div_ll(n_support, 1024)), n_query, n_label_sets);
+    aux::influence_kernel<true><<<grid, 256, 0, stream>>>(softmaxes, qlabel, sweights, slabel, n_support, n_classes,
+                                                          n_label_sets, out);
+  } else {
+    dim3 grid(unsigned(ceil_div_ll(n_support, 256)), n_query, n_label_sets);
+    aux::influence_kernel<false><<<grid, 256, 0, stream>>>(softmaxes, qlabel, sweights, slabel, n_support, n_classes,
+                                                           n_label_sets, out);
+  }
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" size_t nw_rank_rows_workspace_bytes(int n_rows, int64_t n_cols) {
+  if (n_rows <= 0 || n_cols <= 0) return 0;
+  return size_t(n_rows) * size_t(aux::next_pow2(n_cols)) * sizeof(uint64_t);
+}
+
+extern "C" int nw_rank_rows(const float* scores, int n_rows, int64_t n_cols, int64_t k, int64_t* idx_out,
+                            void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(scores && idx_out && workspace, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n_rows > 0 && n_rows <= 65535 && n_cols > 0 && n_cols < (1ll << 32), NW_ERR_INVALID, "bad shape");
+  NW_REQUIRE(k > 0 && k <= n_cols, NW_ERR_INVALID, "k must be in [1, n_cols]");
+  NW_REQUIRE(workspace_bytes >= nw_rank_rows_workspace_bytes(n_rows, n_cols), NW_ERR_WORKSPACE, "workspace too small");
+  const long long padded = aux::next_pow2(n_cols);
+  uint64_t* keys = static_cast<uint64_t*>(workspace);
+  {
+    dim3 grid(unsigned(ceil_div_ll(padded, 256)), n_rows);
+    aux::rank_init_kernel<<<grid, 256, 0, stream>>>(scores, n_cols, padded, keys);
+  }
+  const long long chunk = aux::SORT_CHUNK;
+  const long long nchunks = padded > chunk ? padded / chunk : 1;
+  {
+    dim3 grid(unsigned(nchunks), n_rows);
+    aux::rank_smem_kernel<<<grid, 1024, 0, stream>>>(keys, padded, 2, padded < chunk ? padded : chunk);
+  }
+  for (long long size = chunk * 2; size <= padded; size <<= 1) {
+    for (long long stride = size >> 1; stride >= chunk; stride >>= 1) {
+      dim3 grid(unsigned(ceil_div_ll(padded / 2, 256)), n_rows);
+      aux::rank_global_step_kernel<<<grid, 256, 0, stream>>>(keys, padded, size, stride);
+    }
+    dim3 grid(unsigned(nchunks), n_rows);
+    aux::rank_smem_kernel<<<grid, 1024, 0, stream>>>(keys, padded, size, size);
+  }
+  {
+    dim3 grid(unsigned(ceil_div_ll(k, 256)), n_rows);
+    aux::rank_emit_kernel<<<grid, 256, 0, stream>>>(keys, padded, k, idx_out);
+  }
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}

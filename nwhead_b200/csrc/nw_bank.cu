@@ -1,0 +1,289 @@
+// K0 — support-bank construction and query preparation (HBM-bound streaming kernels), plus the
+// library's error plumbing.
+//
+// Replaces the CPU fp32 bank of the reference (nwhead/nw.py:213-243, nwhead/support.py:113-120) and
+// the per-call whole-bank host->device copy (nwhead/nw.py:156) by a device-resident, class-sorted
+// layout: bf16 features (row stride a multiple of 64 elements = 128 B, so every k-block is one TMA
+// swizzle row), fp32 squared norms of the ROUNDED values, int32 labels, int32 class offsets.
+
+#include <stdarg.h>
+#include <string.h>
+
+#include "nw_common.cuh"
+
+namespace nw {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d in %s", int(e), cudaGetErrorString(e), file, line, what);
+  return NW_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+namespace k0 {
+
+__global__ void labels_to_i32_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ perm,
+                                     long long n, int n_classes, int32_t* __restrict__ out,
+                                     int32_t* __restrict__ status) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  int bad = 0, desc = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long v = labels[perm ? perm[i] : i];
+    if (v < 0 || v >= n_classes) ++bad;
+    if (i > 0) {
+      const long long pv = labels[perm ? perm[i - 1] : i - 1];
+      if (v < pv) ++desc;
+    }
+    out[i] = int32_t(v);
+  }
+  if (bad) atomicAdd(status + 0, bad);
+  if (desc) atomicAdd(status + 1, desc);
+}
+
+__global__ void class_offsets_kernel(const int32_t* __restrict__ lab, long long n, int n_classes,
+                                     int32_t* __restrict__ offsets) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+    const int prev = i > 0 ? lab[i - 1] : -1;
+    const int cur = i < n ? lab[i] : n_classes;
+    for (int c = prev + 1; c <= cur; ++c) offsets[c] = int32_t(i);
+  }
+}
+
+constexpr int MEAN_SPLITS = 256;
+
+// partial[r][col] = sum over the r-th slab of rows
+__global__ void column_partial_kernel(const float* __restrict__ rows, long long n, int d, long long ld,
+                                      float* __restrict__ partial) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (n + MEAN_SPLITS - 1) / MEAN_SPLITS;
+  const long long r0 = (long long)blockIdx.y * per;
+  const long long r1 = r0 + per < n ? r0 + per : n;
+  if (col >= d) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  long long r = r0;
+  for (; r + 3 < r1; r += 4) {
+    a0 += rows[r * ld + col];
+    a1 += rows[(r + 1) * ld + col];
+    a2 += rows[(r + 2) * ld + col];
+    a3 += rows[(r + 3) * ld + col];
+  }
+  for (; r < r1; ++r) a0 += rows[r * ld + col];
+  partial[(long long)blockIdx.y * d + col] = (a0 + a1) + (a2 + a3);
+}
+
+__global__ void column_finish_kernel(const float* __restrict__ partial, long long n, int d,
+                                     float* __restrict__ mean) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= d) return;
+  double acc = 0.0;
+  for (int r = 0; r < MEAN_SPLITS; ++r) acc += double(partial[(long long)r * d + col]);
+  mean[col] = float(acc / double(n));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return uint32_t(__bfloat16_as_ushort(a)) | (uint32_t(__bfloat16_as_ushort(b)) << 16);
+}
+
+// One warp per output row.  VEC: 16-byte loads (d % 4 == 0, ld % 4 == 0, 16-B aligned base).
+template <bool VEC>
+__global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restrict__ rows, long long n, int d,
+                                                           long long ld, const int64_t* __restrict__ perm,
+                                                           const float* __restrict__ center, int normalize,
+                                                           int layout, int precision,
+                                                           __nv_bfloat16* __restrict__ out, int row_elems,
+                                                           float* __restrict__ sqnorm_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* src = rows + (perm ? perm[row] : row) * ld;
+  __nv_bfloat16* dst = out + row * (long long)row_elems;
+
+  float inv = 1.0f;
+  if (normalize) {
+    float ss = 0.f;
+    if (VEC) {
+      for (int c = lane * 4; c < d; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(src + c);
+        if (center) {
+          const float4 m = *reinterpret_cast<const float4*>(center + c);
+          v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
+        }
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+    } else {
+      for (int c = lane; c < d; c += 32) {
+        const float v = src[c] - (center ? center[c] : 0.f);
+        ss += v * v;
+      }
+    }
+    ss = warp_sum(ss);
+    inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(|x|, eps)
+  }
+
+  // segment placement: bank rows [hi | hi | lo], query rows [hi | lo | hi]
+  const int seg_hi2 = (layout == NW_ROWS_BANK) ? d : 2 * d;
+  const int seg_lo = (layout == NW_ROWS_BANK) ? 2 * d : d;
+  float sq = 0.f;
+  if (VEC) {
+    for (int c = lane * 4; c < d; c += 128) {
+      float4 v = *reinterpret_cast<const float4*>(src + c);
+      if (center) {
+        const float4 m = *reinterpret_cast<const float4*>(center + c);
+        v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
+      }
+      float x[4] = {v.x * inv, v.y * inv, v.z * inv, v.w * inv};
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        hi[i] = __float2bfloat16_rn(x[i]);
+        const float h = __bfloat162float(hi[i]);
+        if (precision == NW_PREC_BF16X3) {
+          lo[i] = __float2bfloat16_rn(x[i] - h);
+          const float l = __bfloat162float(lo[i]);
+          sq += h * h + 2.0f * h * l;  // exactly what hi.hi + lo.hi + hi.lo contracts to on the diagonal
+        } else {
+          sq += h * h;
+        }
+      }
+      const uint2 ph = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]));
+      *reinterpret_cast<uint2*>(dst + c) = ph;
+      if (precision == NW_PREC_BF16X3) {
+        *reinterpret_cast<uint2*>(dst + seg_hi2 + c) = ph;
+        *reinterpret_cast<uint2*>(dst + seg_lo + c) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+      }
+    }
+  } else {
+    for (int c = lane; c < d; c += 32) {
+      const float x = (src[c] - (center ? center[c] : 0.f)) * inv;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+      const float h = __bfloat162float(hi);
+      dst[c] = hi;
+      if (precision == NW_PREC_BF16X3) {
+        const __nv_bfloat16 lo = __float2bfloat16_rn(x - h);
+        const float l = __bfloat162float(lo);
+        dst[seg_hi2 + c] = hi;
+        dst[seg_lo + c] = lo;
+        sq += h * h + 2.0f * h * l;
+      } else {
+        sq += h * h;
+      }
+    }
+  }
+  for (int c = precision * d + lane; c < row_elems; c += 32) dst[c] = __float2bfloat16_rn(0.f);
+  sq = warp_sum(sq);
+  if (lane == 0 && sqnorm_out) sqnorm_out[row] = sq;
+}
+
+}  // namespace k0
+}  // namespace nw
+
+using namespace nw;
+
+extern "C" const char* nw_last_error(void) { return g_err; }
+extern "C" int nw_abi_version(void) { return NW_ABI_VERSION; }
+
+extern "C" int nw_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute", __FILE__, __LINE__);
+  NW_REQUIRE(major == 10, NW_ERR_UNSUPPORTED,
+             "libnw_sm100 needs a compute-capability 10.x (B200) device, found major %d; there is no fallback",
+             major);
+  return NW_OK;
+}
+
+extern "C" int nw_row_elems(int d, int precision) {
+  if (d <= 0 || (precision != NW_PREC_BF16 && precision != NW_PREC_BF16X3)) return NW_ERR_INVALID;
+  return ((precision * d + 63) / 64) * 64;
+}
+
+extern "C" int nw_labels_to_i32(const int64_t* labels_i64, const int64_t* perm, int64_t n, int n_classes,
+                                int32_t* labels_out, int32_t* status_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(labels_i64 && labels_out && status_out, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n > 0 && n_classes > 0, NW_ERR_INVALID, "n and n_classes must be positive");
+  NW_CUDA_OK(cudaMemsetAsync(status_out, 0, 2 * sizeof(int32_t), stream));
+  const int blocks = int(ceil_div_ll(n, 256) < 2048 ? ceil_div_ll(n, 256) : 2048);
+  k0::labels_to_i32_kernel<<<blocks, 256, 0, stream>>>(labels_i64, perm, n, n_classes, labels_out, status_out);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_class_offsets(const int32_t* labels_sorted, int64_t n, int n_classes, int32_t* offsets,
+                                void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(labels_sorted && offsets, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n > 0 && n_classes > 0, NW_ERR_INVALID, "n and n_classes must be positive");
+  const int blocks = int(ceil_div_ll(n + 1, 256) < 2048 ? ceil_div_ll(n + 1, 256) : 2048);
+  k0::class_offsets_kernel<<<blocks, 256, 0, stream>>>(labels_sorted, n, n_classes, offsets);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" size_t nw_column_mean_workspace_bytes(int d) {
+  return d > 0 ? size_t(k0::MEAN_SPLITS) * size_t(d) * sizeof(float) : 0;
+}
+
+extern "C" int nw_column_mean(const float* rows, int64_t n, int d, int64_t ld, float* mean_out, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(rows && mean_out && workspace, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n > 0 && d > 0 && ld >= d, NW_ERR_INVALID, "bad shape n=%lld d=%d ld=%lld", (long long)n, d, (long long)ld);
+  NW_REQUIRE(workspace_bytes >= nw_column_mean_workspace_bytes(d), NW_ERR_WORKSPACE, "workspace too small");
+  dim3 grid(ceil_div(d, 128), k0::MEAN_SPLITS);
+  k0::column_partial_kernel<<<grid, 128, 0, stream>>>(rows, n, d, ld, static_cast<float*>(workspace));
+  NW_CUDA_OK(cudaGetLastError());
+  k0::column_finish_kernel<<<ceil_div(d, 128), 128, 0, stream>>>(static_cast<const float*>(workspace), n, d, mean_out);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_rows_to_bf16(const float* rows, int64_t n, int d, int64_t ld, const int64_t* perm,
+                               const float* center, int normalize, int layout, int precision, void* out_bf16,
+                               int row_elems, float* sqnorm_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(rows && out_bf16, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n > 0 && d > 0 && ld >= d, NW_ERR_INVALID, "bad shape n=%lld d=%d ld=%lld", (long long)n, d, (long long)ld);
+  NW_REQUIRE(layout == NW_ROWS_BANK || layout == NW_ROWS_QUERY, NW_ERR_INVALID, "unknown layout %d", layout);
+  NW_REQUIRE(precision == NW_PREC_BF16 || precision == NW_PREC_BF16X3, NW_ERR_INVALID, "unknown precision %d", precision);
+  NW_REQUIRE(row_elems == nw_row_elems(d, precision), NW_ERR_INVALID, "row_elems %d != nw_row_elems(%d, %d)",
+             row_elems, d, precision);
+  const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0) &&
+                   (!center || (reinterpret_cast<uintptr_t>(center) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0);
+  const int warps_per_block = 8;
+  const long long blocks = ceil_div_ll(n, warps_per_block);
+  NW_REQUIRE(blocks < (1ll << 31), NW_ERR_UNSUPPORTED, "too many rows");
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_bf16);
+  if (vec)
+    k0::rows_to_bf16_kernel<true><<<unsigned(blocks), warps_per_block * 32, 0, stream>>>(
+        rows, n, d, ld, perm, center, normalize, layout, precision, out, row_elems, sqnorm_out);
+  else
+    k0::rows_to_bf16_kernel<false><<<unsigned(blocks), warps_per_block * 32, 0, stream>>>(
+        rows, n, d, ld, perm, center, normalize, layout, precision, out, row_elems, sqnorm_out);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}

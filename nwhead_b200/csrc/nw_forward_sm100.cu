@@ -1,0 +1,563 @@
+// K1 — fused NW-head forward on tcgen05 tensor cores (sm_100a).
+//
+// Replaces NWHead.forward (reference nwhead/nw.py:266-289) for a shared, class-sorted support bank:
+//   scores = kernel(q, S)            -> TMA-fed tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) + scalar epilogue
+//   softmax over supports            -> online running max / sum in the epilogue warps (exp2 domain)
+//   probs @ onehot(labels)           -> per-class segment sums, flushed on (warp-uniform) class change
+// The (B, N) score matrix never leaves the SM.  Output is the per-class log-sum-exp table
+// class_lse (B, C); nw_logp_from_class_lse turns it into log(P + 1e-12).
+//
+// Work decomposition: the bank is cut into `chunks` contiguous ranges of 256-row support tiles; a work
+// unit is (chunk, 128-query tile).  Units of one chunk are adjacent in the unit order, so the persistent
+// CTAs of one wave sweep the same support tiles at the same time and the bank is read from HBM once
+// (L2 hits for the other query tiles).  Inside a unit the epilogue carries (running max, class sum)
+// in registers across tiles; classes cut by a chunk boundary go to `side` and are merged in fixed order
+// by merge_side_kernel (deterministic, no atomics).
+//
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue (one thread per query row = TMEM lane).
+
+#include "nw_common.cuh"
+
+namespace nw {
+namespace k1 {
+
+constexpr int BM = 128;  // queries per tile  (UMMA M, TMEM lanes)
+constexpr int BN = 256;  // supports per tile (UMMA N, TMEM columns)
+constexpr int BK = 64;   // bf16 per k-block = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 = all of TMEM
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_THREADS = 128;
+
+struct TileMeta {
+  float cadd[BN];    // per-column additive term: |s|^2 (EUCLID) or 0 (LINEAR); +inf / -inf for padding columns
+  int lab[BN + 8];   // labels of the tile's columns plus one look-ahead entry
+};
+
+struct SmemTail {
+  TileMeta meta[ACC_STAGES];
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tfull[ACC_STAGES];
+  uint64_t tempty[ACC_STAGES];
+  uint32_t tmem_base;
+};
+
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + size_t(STAGES) * STAGE_BYTES + sizeof(SmemTail);
+
+struct Params {
+  const float* q_sqnorm;
+  const float* s_sqnorm;
+  const int32_t* labels;
+  float* class_lse;
+  float* side;
+  int n_query;
+  int n_support;
+  int n_classes;
+  int kblocks;
+  int q_tiles;
+  int s_tiles;
+  int chunks;
+  int tiles_per_chunk;
+  float scale_log2;  // LINEAR: scale * log2(e)
+};
+
+struct Flusher {
+  float* class_lse_row;  // class_lse + row * C
+  float* side_row;       // side + (chunk * B + row) * 2
+  int cf, cl;
+  bool head_cut, tail_cut, row_valid;
+  __device__ __forceinline__ void operator()(int cls, float m, float l) const {
+    const float v = (m + lg2_approx(l)) * kLn2;
+    if (!row_valid) return;
+    if (cls == cf && head_cut) side_row[0] = v;
+    else if (cls == cl && tail_cut) side_row[1] = v;
+    else class_lse_row[cls] = v;
+  }
+};
+
+// One 32-column chunk of the accumulator for one query row.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __restrict__ cadd,
+                                               const int* __restrict__ lab, uint32_t emask, float qn,
+                                               float scale2, float& m, float& l, const Flusher& flush) {
+  float mx;
+  if (EPI == NW_EPI_EUCLID) {
+    float dmin = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      acc[i] = fmaf(-2.0f, acc[i], qn + cadd[i]);  // squared distance
+      dmin = fminf(dmin, acc[i]);
+    }
+    mx = -sqrt_approx(fmaxf(dmin, 0.0f)) * kLog2e;
+  } else {
+    mx = __int_as_float(0xff800000);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      acc[i] = fmaf(acc[i], scale2, cadd[i]);  // score * log2(e)  (or -inf on padding columns)
+      mx = fmaxf(mx, acc[i]);
+    }
+  }
+  if (mx > m) {  // new running maximum: rescale the open class sum
+    l *= ex2_approx(m - mx);
+    m = mx;
+  }
+  if (emask == 0u) {  // warp-uniform fast path: no class ends inside this chunk
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float e;
+      if (EPI == NW_EPI_EUCLID) e = ex2_approx(fmaf(sqrt_approx(fmaxf(acc[i], 0.0f)), -kLog2e, -m));
+      else e = ex2_approx(acc[i] - m);
+      l += e;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float e;
+      if (EPI == NW_EPI_EUCLID) e = ex2_approx(fmaf(sqrt_approx(fmaxf(acc[i], 0.0f)), -kLog2e, -m));
+      else e = ex2_approx(acc[i] - m);
+      l += e;
+      if (emask & (1u << i)) {  // warp-uniform: column i is the last row of its class (in this unit)
+        flush(lab[i], m, l);
+        l = 0.0f;
+      }
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_s,
+                  const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;  // 1024-B aligned (swizzle-128B atoms)
+  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + size_t(STAGES) * STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_units = p.chunks * p.q_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_s);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(smem_u32(&tail->full[i]), 1);
+      mbar_init(smem_u32(&tail->empty[i]), 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(smem_u32(&tail->tfull[i]), 1);
+      mbar_init(smem_u32(&tail->tempty[i]), EPI_THREADS / 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&tail->tmem_base), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (elect_one()) {
+      const uint64_t pol_q = l2_policy_evict_last();    // queries are re-read for every support tile
+      const uint64_t pol_s = l2_policy_evict_normal();  // a support tile is shared by the CTAs of a wave
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int g = u / p.q_tiles;
+        const int qt = u - g * p.q_tiles;
+        const int t0 = g * p.tiles_per_chunk;
+        const int t1 = min(t0 + p.tiles_per_chunk, p.s_tiles);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+            const uint32_t s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
+            const uint32_t bar = smem_u32(&tail->full[s]);
+            const uint32_t a_dst = smem_u32(smem + size_t(s) * STAGE_BYTES);
+            mbar_arrive_expect_tx(bar, STAGE_BYTES);
+            tma_load_2d(a_dst, &map_q, bar, kb * BK, qt * BM, pol_q);
+            tma_load_2d(a_dst + A_BYTES, &map_s, bar, kb * BK, t * BN, pol_s);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      uint32_t it = 0, tc = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int g = u / p.q_tiles;
+        const int t0 = g * p.tiles_per_chunk;
+        const int t1 = min(t0 + p.tiles_per_chunk, p.s_tiles);
+        for (int t = t0; t < t1; ++t, ++tc) {
+          const uint32_t as = tc & 1u;
+          const uint32_t aph = (tc >> 1) & 1u;
+          mbar_wait(smem_u32(&tail->tempty[as]), aph ^ 1u);  // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BN;
+          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+            const uint32_t s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(smem_u32(&tail->full[s]), ph);  // TMA bytes have landed
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + size_t(s) * STAGE_BYTES);
+            const uint64_t adesc = umma_desc_k128(a_addr);
+            const uint64_t bdesc = umma_desc_k128(a_addr + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 32 B (= 16 bf16) inside the 128-B swizzled row: +2 in the 16-B address field
+              umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&tail->empty[s]));  // frees the smem stage once these MMAs retire
+          }
+          umma_commit(smem_u32(&tail->tfull[as]));  // accumulator complete -> epilogue
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    // ===================================== epilogue ==========================================
+    const int ew = warp - EPI_WARP0;  // == warp % 4: TMEM lane quarter this warp may read
+    const int et = threadIdx.x - EPI_WARP0 * 32;
+    const float scale2 = p.scale_log2;
+    const float neg_inf = __int_as_float(0xff800000);
+    const float pos_inf = __int_as_float(0x7f800000);
+    uint32_t tc = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int g = u / p.q_tiles;
+      const int qt = u - g * p.q_tiles;
+      const int t0 = g * p.tiles_per_chunk;
+      const int t1 = min(t0 + p.tiles_per_chunk, p.s_tiles);
+      const int n0 = t0 * BN;
+      const int n1 = min(t1 * BN, p.n_support);
+      const int row = qt * BM + ew * 32 + lane;
+
+      Flusher flush;
+      flush.row_valid = row < p.n_query;
+      flush.cf = __ldg(p.labels + n0);
+      flush.cl = __ldg(p.labels + n1 - 1);
+      flush.head_cut = n0 > 0 && __ldg(p.labels + n0 - 1) == flush.cf;
+      flush.tail_cut = n1 < p.n_support && __ldg(p.labels + n1) == flush.cl;
+      const int srow = flush.row_valid ? row : 0;
+      flush.class_lse_row = p.class_lse + size_t(srow) * p.n_classes;
+      flush.side_row = p.side + (size_t(g) * p.n_query + srow) * 2;
+      const float qn = (EPI == NW_EPI_EUCLID && flush.row_valid) ? __ldg(p.q_sqnorm + row) : 0.0f;
+
+      float m = neg_inf, l = 0.0f;
+      for (int t = t0; t < t1; ++t, ++tc) {
+        const uint32_t as = tc & 1u;
+        const uint32_t aph = (tc >> 1) & 1u;
+        TileMeta& meta = tail->meta[as];
+        const int j0 = t * BN;
+        // stage this tile's column metadata while the MMAs of the tile are still running
+#pragma unroll
+        for (int r = 0; r < BN / EPI_THREADS; ++r) {
+          const int i = et + r * EPI_THREADS;
+          const int j = j0 + i;
+          float ca;
+          if (EPI == NW_EPI_EUCLID) ca = j < n1 ? __ldg(p.s_sqnorm + j) : pos_inf;
+          else ca = j < n1 ? 0.0f : neg_inf;
+          meta.cadd[i] = ca;
+          meta.lab[i] = j < p.n_support ? __ldg(p.labels + j) : -1;
+        }
+        if (et == 0) meta.lab[BN] = (j0 + BN) < p.n_support ? __ldg(p.labels + j0 + BN) : -1;
+        named_bar_sync(1, EPI_THREADS);
+
+        uint32_t emask[BN / 32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          const int i = c * 32 + lane;
+          const int j = j0 + i;
+          const bool last = j < n1 && (j == n1 - 1 || meta.lab[i] != meta.lab[i + 1]);
+          emask[c] = __ballot_sync(0xffffffffu, last);
+        }
+
+        mbar_wait(smem_u32(&tail->tfull[as]), aph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + as * BN + (uint32_t(ew * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          float acc[32];
+          tmem_ld_32x32(t_addr + c * 32, acc);
+          tmem_ld_wait();
+          epilogue_chunk<EPI>(acc, meta.cadd + c * 32, meta.lab + c * 32, emask[c], qn, scale2, m, l, flush);
+        }
+        // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tail->tempty[as]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void fill_kernel(float* __restrict__ a, long long n, float* __restrict__ b, long long nb, float v) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = v;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) b[i] = v;
+}
+
+__device__ __forceinline__ float logaddexp_f(float a, float b) {
+  const float mx = fmaxf(a, b);
+  if (mx == __int_as_float(0xff800000)) return mx;
+  return mx + log1pf(expf(-fabsf(a - b)));
+}
+
+// Apply the chunk-boundary partials in chunk order (fixed order => bitwise reproducible).
+__global__ void merge_side_kernel(float* __restrict__ class_lse, const float* __restrict__ side,
+                                  const int32_t* __restrict__ labels, int n_query, int n_support, int n_classes,
+                                  int chunks, int tiles_per_chunk, int s_tiles) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_query) return;
+  float* row = class_lse + size_t(b) * n_classes;
+  const float neg_inf = __int_as_float(0xff800000);
+  for (int g = 0; g < chunks; ++g) {
+    const int t0 = g * tiles_per_chunk;
+    const int t1 = min(t0 + tiles_per_chunk, s_tiles);
+    const int n0 = t0 * BN;
+    const int n1 = min(t1 * BN, n_support);
+    const float v0 = side[(size_t(g) * n_query + b) * 2 + 0];
+    const float v1 = side[(size_t(g) * n_query + b) * 2 + 1];
+    if (v0 != neg_inf) {
+      const int c = labels[n0];
+      row[c] = logaddexp_f(row[c], v0);
+    }
+    if (v1 != neg_inf) {
+      const int c = labels[n1 - 1];
+      row[c] = logaddexp_f(row[c], v1);
+    }
+  }
+}
+
+// logp[b,c] = log(exp(L[b,c] - logsumexp_c L[b,:]) + 1e-12)   (reference nwhead/nw.py:285-289)
+__global__ void __launch_bounds__(256) logp_kernel(const float* __restrict__ class_lse, int n_classes,
+                                                   float* __restrict__ logp) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const float* row = class_lse + size_t(blockIdx.x) * n_classes;
+  float* out = logp + size_t(blockIdx.x) * n_classes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = __int_as_float(0xff800000);
+  for (int c = threadIdx.x; c < n_classes; c += blockDim.x) mx = fmaxf(mx, row[c]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = red[0];
+    for (int i = 1; i < 8; ++i) v = fmaxf(v, red[i]);
+    bcast = v;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.0f;
+  for (int c = threadIdx.x; c < n_classes; c += blockDim.x) sum += expf(row[c] - mx);
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.0f;
+    for (int i = 0; i < 8; ++i) v += red[i];
+    bcast = mx + logf(v);
+  }
+  __syncthreads();
+  const float lse = bcast;
+  for (int c = threadIdx.x; c < n_classes; c += blockDim.x) out[c] = logf(expf(row[c] - lse) + 1e-12f);
+}
+
+__global__ void lse_merge_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    a[i] = logaddexp_f(a[i], b[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-B swizzle, zero OOB fill.
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  NW_REQUIRE(fn != nullptr, NW_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NW_REQUIRE(r == CUDA_SUCCESS, NW_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+  return NW_OK;
+}
+
+}  // namespace k1
+}  // namespace nw
+
+using namespace nw;
+
+extern "C" int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t* plan) {
+  NW_REQUIRE(plan != nullptr, NW_ERR_INVALID, "plan_out is NULL");
+  NW_REQUIRE(n_query > 0 && n_support > 0, NW_ERR_INVALID, "n_query and n_support must be positive");
+  NW_REQUIRE(n_support < (int64_t(1) << 31) - 512, NW_ERR_UNSUPPORTED, "n_support must be < 2^31 - 512");
+  const int ncta = sm_count();
+  NW_REQUIRE(ncta > 0, NW_ERR_CUDA, "no CUDA device");
+  const int q_tiles = ceil_div(n_query, k1::BM);
+  const int s_tiles = int(ceil_div_ll(n_support, k1::BN));
+  // choose the number of chunks so that (chunks * q_tiles) fills whole waves of persistent CTAs
+  long long best_cost = -1;
+  int best_tpc = s_tiles;
+  for (int w = 1; w <= 64; ++w) {
+    long long want = ceil_div_ll((long long)w * ncta, q_tiles);
+    int G = int(want < s_tiles ? want : s_tiles);
+    if (G < 1) G = 1;
+    const int tpc = ceil_div(s_tiles, G);
+    const int Ge = ceil_div(s_tiles, tpc);
+    const long long waves = ceil_div_ll((long long)Ge * q_tiles, ncta);
+    const long long cost = waves * (tpc + 1);  // +1 tile-equivalent of per-unit pipeline fill / flush
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_tpc = tpc;
+    }
+    if (G == s_tiles) break;
+  }
+  plan->q_tiles = q_tiles;
+  plan->s_tiles = s_tiles;
+  plan->tiles_per_chunk = best_tpc;
+  plan->chunks = ceil_div(s_tiles, best_tpc);
+  const long long units = (long long)plan->chunks * q_tiles;
+  plan->grid = int(units < ncta ? units : ncta);
+  plan->side_elems = int64_t(plan->chunks) * n_query * 2;
+  return NW_OK;
+}
+
+extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm,
+                                    int n_query, const void* bank_bf16, const float* s_sqnorm,
+                                    const int32_t* labels, int64_t n_support, int row_elems, int n_classes,
+                                    float* class_lse, float* side, int64_t side_elems, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(epilogue == NW_EPI_EUCLID || epilogue == NW_EPI_LINEAR, NW_ERR_INVALID, "unknown epilogue %d", epilogue);
+  NW_REQUIRE(q_bf16 && bank_bf16 && labels && class_lse && side, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(epilogue != NW_EPI_EUCLID || (q_sqnorm && s_sqnorm), NW_ERR_INVALID,
+             "the euclidean epilogue needs q_sqnorm and s_sqnorm");
+  NW_REQUIRE(row_elems > 0 && row_elems % k1::BK == 0, NW_ERR_INVALID, "row_elems must be a positive multiple of 64");
+  NW_REQUIRE(n_classes > 0, NW_ERR_INVALID, "n_classes must be positive");
+  NW_REQUIRE((reinterpret_cast<uintptr_t>(q_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(bank_bf16) & 15) == 0,
+             NW_ERR_INVALID, "bf16 operands must be 16-byte aligned");
+  int rc = nw_device_check();
+  if (rc != NW_OK) return rc;
+  nw_forward_plan_t plan;
+  rc = nw_forward_plan(n_query, n_support, &plan);
+  if (rc != NW_OK) return rc;
+  NW_REQUIRE(side_elems >= plan.side_elems, NW_ERR_WORKSPACE, "side scratch too small: %lld < %lld floats",
+             (long long)side_elems, (long long)plan.side_elems);
+
+  CUtensorMap map_q, map_s;
+  rc = k1::make_map(&map_q, q_bf16, uint64_t(n_query), uint64_t(row_elems), k1::BM);
+  if (rc != NW_OK) return rc;
+  rc = k1::make_map(&map_s, bank_bf16, uint64_t(n_support), uint64_t(row_elems), k1::BN);
+  if (rc != NW_OK) return rc;
+
+  k1::fill_kernel<<<sm_count() * 4, 256, 0, stream>>>(class_lse, (long long)n_query * n_classes, side,
+                                                      (long long)plan.side_elems, -INFINITY);
+  NW_CUDA_OK(cudaGetLastError());
+
+  k1::Params p;
+  p.q_sqnorm = q_sqnorm;
+  p.s_sqnorm = s_sqnorm;
+  p.labels = labels;
+  p.class_lse = class_lse;
+  p.side = side;
+  p.n_query = n_query;
+  p.n_support = int(n_support);
+  p.n_classes = n_classes;
+  p.kblocks = row_elems / k1::BK;
+  p.q_tiles = plan.q_tiles;
+  p.s_tiles = plan.s_tiles;
+  p.chunks = plan.chunks;
+  p.tiles_per_chunk = plan.tiles_per_chunk;
+  p.scale_log2 = scale * kLog2e;
+
+  static bool attr_set[2] = {false, false};
+  if (epilogue == NW_EPI_EUCLID) {
+    if (!attr_set[0]) {
+      NW_CUDA_OK(cudaFuncSetAttribute(k1::nw_forward_kernel<NW_EPI_EUCLID>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, int(k1::SMEM_BYTES)));
+      attr_set[0] = true;
+    }
+    k1::nw_forward_kernel<NW_EPI_EUCLID><<<plan.grid, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(map_q, map_s, p);
+  } else {
+    if (!attr_set[1]) {
+      NW_CUDA_OK(cudaFuncSetAttribute(k1::nw_forward_kernel<NW_EPI_LINEAR>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, int(k1::SMEM_BYTES)));
+      attr_set[1] = true;
+    }
+    k1::nw_forward_kernel<NW_EPI_LINEAR><<<plan.grid, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(map_q, map_s, p);
+  }
+  NW_CUDA_OK(cudaGetLastError());
+
+  if (plan.chunks > 1) {
+    k1::merge_side_kernel<<<ceil_div(n_query, 128), 128, 0, stream>>>(class_lse, side, labels, n_query,
+                                                                      int(n_support), n_classes, plan.chunks,
+                                                                      plan.tiles_per_chunk, plan.s_tiles);
+    NW_CUDA_OK(cudaGetLastError());
+  }
+  return NW_OK;
+}
+
+extern "C" int nw_logp_from_class_lse(const float* class_lse, int n_query, int n_classes, float* logp,
+                                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(class_lse && logp, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n_query > 0 && n_classes > 0, NW_ERR_INVALID, "n_query and n_classes must be positive");
+  k1::logp_kernel<<<n_query, 256, 0, stream>>>(class_lse, n_classes, logp);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_class_lse_merge(float* a, const float* b, int64_t n_elems, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(a && b && n_elems >= 0, NW_ERR_INVALID, "bad arguments");
+  if (n_elems == 0) return NW_OK;
+  k1::lse_merge_kernel<<<sm_count() * 4, 256, 0, stream>>>(a, b, (long long)n_elems);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}

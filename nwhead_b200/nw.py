@@ -1,0 +1,278 @@
+"""NWHead / NWNet — the API of the reference's nwhead/nw.py on the B200 CUDA path.
+
+Two execution paths, both through libnw_sm100 (no PyTorch or CPU fallback):
+  * tensor-core path  (SupportBank.forward -> nw_forward_class_lse): shared 2-D support with more than
+    25 rows and no gradient required — inference (`predict`) and any no-grad call.  torch.cdist itself
+    switches to the expanded |q|^2+|s|^2-2q.s form above 25 rows.
+  * direct fp32 path  (nw_direct_*): exact differences, differentiable, per-query 3-D supports —
+    episodic training (`forward`) and tiny supports.
+"""
+import torch
+import torch.nn as nn
+
+from . import _abi
+from ._abi import KIND, check, load, ptr, stream_of
+from .bank import SupportBank
+from .kernel import get_kernel
+from .support import SupportSetEval, SupportSetTrain
+
+MM_PATH_MIN_ROWS = 26  # torch.cdist uses the matmul form when a side has more than 25 rows
+
+
+class _NWDirectFunction(torch.autograd.Function):
+    """Differentiable NWHead.forward (reference nwhead/nw.py:266-289) on the direct fp32 kernels;
+    backward is the closed form of SURVEY.md B.2 (nw_direct_backward)."""
+
+    @staticmethod
+    def forward(ctx, x, sx, sy, logit_scale, kind, n_classes):
+        lib = load()
+        dev = _abi.require_cuda(x, sx, sy)
+        xq = x.detach().contiguous()
+        sxd = sx.detach().contiguous()
+        syd = sy.detach().contiguous()
+        b, d = xq.shape
+        batched = sxd.dim() == 3
+        n = sxd.shape[-2]
+        scale = float(logit_scale.detach().exp()) if logit_scale is not None else 1.0
+        st = stream_of(dev)
+        scores = torch.empty((b, n), dtype=torch.float32, device=dev)
+        check(lib.nw_direct_scores(KIND[kind], scale, ptr(xq), b, d, ptr(sxd), n, int(batched), ptr(scores), st),
+              "nw_direct_scores")
+        logp = torch.empty((b, n_classes), dtype=torch.float32, device=dev)
+        row_lse = torch.empty((b,), dtype=torch.float32, device=dev)
+        status = torch.empty((1,), dtype=torch.int32, device=dev)
+        check(lib.nw_direct_aggregate(ptr(scores), ptr(syd), int(syd.dim() == 2), b, n, n_classes, ptr(logp),
+                                      ptr(row_lse), ptr(status), st), "nw_direct_aggregate")
+        if status.item():
+            raise RuntimeError("Class values must be smaller than num_classes.")  # F.one_hot's error
+        ctx.save_for_backward(xq, sxd, syd, scores, row_lse, logp)
+        ctx.kind, ctx.n_classes, ctx.scale = kind, n_classes, scale
+        ctx.has_scale = logit_scale is not None
+        return logp
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = load()
+        xq, sxd, syd, scores, row_lse, logp = ctx.saved_tensors
+        dev = xq.device
+        b, d = xq.shape
+        batched = sxd.dim() == 3
+        n = sxd.shape[-2]
+        need_q, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_scale = ctx.has_scale and ctx.needs_input_grad[3]
+        g = grad_out.detach().float().contiguous()
+        gq = torch.empty_like(xq) if (need_q or not need_s) else None
+        gs = torch.empty_like(sxd) if need_s else None
+        gscale = torch.empty((b,), dtype=torch.float32, device=dev) if need_scale else None
+        ws = torch.empty((lib.nw_direct_backward_workspace_elems(b, n, int(batched)),), dtype=torch.float32,
+                         device=dev)
+        check(lib.nw_direct_backward(KIND[ctx.kind], ctx.scale, ptr(xq), b, d, ptr(sxd), n, int(batched),
+                                     ptr(syd), int(syd.dim() == 2), ctx.n_classes, ptr(scores), ptr(row_lse),
+                                     ptr(logp), ptr(g), ptr(ws), ptr(gq), ptr(gs), ptr(gscale),
+                                     stream_of(dev)), "nw_direct_backward")
+        return (gq if need_q else None, gs, None, gscale.sum() if need_scale else None, None, None)
+
+
+class NWHead(nn.Module):
+    def __init__(self, kernel, n_classes, precision="auto"):
+        super().__init__()
+        self.kernel = kernel
+        self.n_classes = n_classes
+        self.precision = precision
+
+    def _kind(self):
+        kind = getattr(self.kernel, "kind", None)
+        if kind not in KIND:
+            raise NotImplementedError(f"kernel {type(self.kernel).__name__} has no CUDA implementation")
+        return kind
+
+    def forward(self, x, sx, sy=None):
+        """
+        Computes Nadaraya-Watson head given query x, support x, and support y tensors.
+        :param x: Query data (b, feat_dim)
+        :param sx: Support data (num_support, feat_dim) or (b, num_support, feat_dim), or a prebuilt
+            SupportBank (then sy is ignored).
+        :param sy: Support targets (num_support) or (b, num_support), int64
+        :return: log of softmaxed probabilities (b, num_classes)
+        """
+        kind = self._kind()
+        if isinstance(sx, SupportBank):
+            return sx.forward(x, self.kernel.scale_value())
+        _abi.require_cuda(x, sx, sy)
+        if x.dtype != torch.float32 or sx.dtype != torch.float32:
+            raise TypeError("NWHead expects float32 features")  # the reference raises on fp64 too
+        if sy.dtype != torch.int64:
+            raise RuntimeError("one_hot is only applicable to index tensor of type LongTensor.")
+        logit_scale = self.kernel.logit_scale if kind == "clip" else None
+        needs_grad = torch.is_grad_enabled() and (
+            x.requires_grad or sx.requires_grad or (logit_scale is not None and logit_scale.requires_grad))
+        n = sx.shape[-2]
+        if needs_grad or sx.dim() == 3 or n < MM_PATH_MIN_ROWS:
+            return _NWDirectFunction.apply(x, sx, sy, logit_scale, kind, self.n_classes)
+        bank = SupportBank.build(sx, sy, self.n_classes, kind, self.precision)
+        return bank.forward(x, self.kernel.scale_value())
+
+
+class NWNet(nn.Module):
+    def __init__(self,
+                 featurizer,
+                 n_classes,
+                 support_dataset=None,
+                 feat_dim=None,
+                 proj_dim=0,
+                 kernel_type='euclidean',
+                 train_type='random',
+                 n_way=None,
+                 n_shot=1,
+                 n_shot_random=1,
+                 n_shot_full=100,
+                 n_shot_cluster=1,
+                 n_neighbors=10,
+                 env_array=None,
+                 debug_mode=False,
+                 device='cuda:0',
+                 return_mask=False,
+                 precision='auto',
+                 ):
+        '''
+        Top level NW net class (constructor of the reference, nwhead/nw.py:12-105, plus `precision`).
+
+        :param featurizer: Feature extractor
+        :param n_classes: Number of classes in dataset
+        :param support_dataset: Pytorch Dataset with a .targets attribute of categorical labels
+        :param feat_dim: Output dimension of featurizer
+        :param proj_dim: If > 0, adds a linear projection down to proj_dim after featurizer
+        :param kernel_type: Type of kernel to use
+        :param train_type: 'random' ('irm' is outside the accelerated path)
+        :param n_way: Number of classes to put in support during training
+        :param n_shot: Number of datapoints per class to sample for support during training
+        :param n_shot_random / n_shot_full / n_shot_cluster: per-class support sizes of the eval modes
+        :param n_neighbors: Number of neighbors for knn inference
+        :param device: Device used for computation (must be a CUDA device)
+        :param return_mask: If true, also returns a mask telling if the query class is in the support
+        :param precision: 'auto' | 'bf16' | 'bf16x3' operand precision of the tensor-core path
+        '''
+        super().__init__()
+        self.featurizer = featurizer
+        self.train_type = train_type
+        self.n_way = n_way
+        self.debug_mode = debug_mode
+        self.n_classes = n_classes
+        self.n_shot = n_shot
+        self.n_shot_random = n_shot_random
+        self.n_shot_full = n_shot_full
+        self.n_shot_cluster = n_shot_cluster
+        self.n_neighbors = n_neighbors
+        self.env_array = env_array
+        self.device = device
+        self.return_mask = return_mask
+        self.precision = precision
+        if support_dataset is not None:
+            assert hasattr(support_dataset, 'targets'), 'Support set must have .targets attribute'
+
+        if proj_dim > 0:
+            assert feat_dim is not None, 'Feature dimension must be specified'
+            self.featurizer = nn.Sequential(self.featurizer, nn.Linear(feat_dim, proj_dim))
+
+        self.kernel = get_kernel(kernel_type)
+        self.nwhead = NWHead(kernel=self.kernel, n_classes=n_classes, precision=precision)
+
+        if support_dataset is not None:
+            self.support_train = SupportSetTrain(support_dataset, self.n_classes, self.train_type, self.n_shot,
+                                                 n_way=self.n_way, env_array=self.env_array)
+            self.process_support_eval(support_dataset)
+
+    def process_support_eval(self, support_dataset):
+        '''Processes support dataset into SupportSet object.'''
+        self.support_eval = SupportSetEval(support_dataset, self.n_classes, self.n_shot_random,
+                                           self.n_shot_full, n_shot_cluster=self.n_shot_cluster,
+                                           n_neighbors=self.n_neighbors, env_array=self.env_array,
+                                           kernel_type=self.kernel.kind, precision=self.precision)
+
+    def precompute(self):
+        '''Precomputes all support features, cluster centroids, and random iterator.
+        Call before running inference.  The bank stays on the GPU (bf16 + norms + labels).'''
+        assert not self.featurizer.training
+        sinfo = self._compute_all_support_feats()
+        self.full_feat = sinfo[0]
+        self.full_y = sinfo[1]
+        self.support_eval.build_infer_iters(*sinfo)
+
+    def predict(self, x, mode='random'):
+        '''
+        Perform prediction given test images.
+
+        :param x: Input datapoints (bs, nch, l, w)
+        :param mode: Inference mode. One of ['random', 'full', 'cluster', 'knn']
+        '''
+        qfeat = self.featurizer(x)
+        support = self.support_eval.get_support(mode, x=qfeat)
+        if self.debug_mode:
+            print('qx shape:', x.shape)
+        if isinstance(support, SupportBank):
+            out = self.nwhead(qfeat, support)
+        else:
+            sfeat, sy = support
+            out = self.nwhead(qfeat, sfeat.to(x.device), sy.to(x.device))
+        if self.return_mask:
+            return out, torch.full((len(x),), True)
+        return out
+
+    def forward(self, x, y, metadata=None, support_data=None):
+        '''
+        Forward pass using images for query and support (episodic training step).
+
+        :param x: Input datapoints (bs, nch, l, w)
+        :param y: Corresponding labels (bs)
+        :param metadata: Corresponding metadata (bs)
+        :param support_data: Optional (sx, sy, sm) tuple for functional implementation
+        '''
+        if support_data is not None:
+            sx, sy, sm = support_data
+        else:
+            sx, sy, sm = self.support_train.get_support(y)
+        if sm is None:
+            sm = torch.zeros_like(sy)
+        sx, sy, sm = sx.to(x.device), sy.to(x.device), sm.to(x.device)
+
+        batch_size = len(x)
+        feats = self.featurizer(torch.cat((x, sx), dim=0))
+        qfeat, sfeat = feats[:batch_size], feats[batch_size:]
+        isin = torch.isin(y, sy)
+        if self.debug_mode:
+            print('qx shape:', x.shape, 'sx shape:', sx.shape)
+            print('qy:', y, 'sy:', sy, 'qy in sy:', isin)
+        out = self.nwhead(qfeat, sfeat, sy)
+        if self.return_mask:
+            return out, isin
+        return out
+
+    def _compute_all_support_feats(self):
+        """Runs the featurizer over the class-balanced support loaders (reference nwhead/nw.py:213-243);
+        features stay on the device instead of being copied to the host per batch."""
+        feats, labels, meta = [], [], []
+        sep_feats, sep_labels, sep_meta = [], [], []
+        for loader in self.support_eval.support_loaders:
+            env_feats, env_labels, env_meta = [], [], []
+            for qimg, qlabel, qmeta in loader:
+                feat = self.featurizer(qimg.to(self.device)).detach().float()
+                env_feats.append(feat)
+                env_labels.append(qlabel.to(self.device))
+                env_meta.append(torch.as_tensor(qmeta))
+            feats += env_feats
+            labels += env_labels
+            meta += env_meta
+            sep_feats.append(torch.cat(env_feats, dim=0))
+            sep_labels.append(torch.cat(env_labels, dim=0))
+            sep_meta.append(torch.cat(env_meta, dim=0))
+        return (torch.cat(feats, dim=0), torch.cat(labels, dim=0), torch.cat(meta, dim=0), sep_feats, sep_labels,
+                sep_meta)
+
+    def get_neighbors(self, x, k=None):
+        '''Returns indices of nearest neighbors of x in the support set, nearest first
+        (reference nwhead/nw.py:245-249: the full ranking; pass k to keep only the first k).'''
+        from .utils import rank_rows
+
+        qfeat = self.featurizer(x).detach()
+        distances = self.kernel(qfeat, self.full_feat)
+        return rank_rows(distances, k)

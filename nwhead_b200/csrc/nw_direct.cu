@@ -64,12 +64,13 @@ __global__ void __launch_bounds__(256) scores_kernel(int kind, float scale, cons
     float acc = 0.f;
     if (kind == NW_KIND_HYPERSPHERE) {
       for (int c = lane; c < d; c += 32) {
-        const float df = qp[c] * iq - sp[c] * is;
+        // separately rounded products (no FMA contraction): identical rows must give exactly 0
+        const float df = __fsub_rn(__fmul_rn(qp[c], iq), __fmul_rn(sp[c], is));
         acc = fmaf(df, df, acc);
       }
       out = -sqrtf(warp_sum(acc));
     } else {
-      for (int c = lane; c < d; c += 32) acc = fmaf(qp[c] * iq, sp[c] * is, acc);
+      for (int c = lane; c < d; c += 32) acc = fmaf(__fmul_rn(qp[c], iq), __fmul_rn(sp[c], is), acc);
       out = warp_sum(acc);
       if (kind == NW_KIND_CLIP) out *= scale;
     }

@@ -1,0 +1,116 @@
+"""GPU: bank build, class centroids, support influence, neighbour ranking."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nw_oracle as O
+from gpu_util import clustered_features
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_bank_layout_bit_exact(cuda_lib):
+    """bf16 rows = round-to-nearest-even of (x - mean); norms are those of the rounded rows; labels
+    int32, class offsets, stable class sort of an unsorted support — all bit exact vs numpy."""
+    from nwhead_b200 import SupportBank
+
+    rng = np.random.default_rng(0)
+    N, d, C = 1000, 100, 13
+    y = rng.integers(0, C - 1, N).astype(np.int64)  # class C-1 absent; unsorted
+    s = rng.normal(size=(N, d)).astype(np.float32) * 3 + 1
+    bank = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, "euclidean", "bf16")
+    perm = np.argsort(y, kind="stable")
+    assert np.array_equal(bank.perm.cpu().numpy(), perm)
+    assert np.array_equal(bank.labels.cpu().numpy(), y[perm].astype(np.int32))
+    assert np.array_equal(bank.offsets.cpu().numpy(), O.class_offsets(y[perm], C).astype(np.int32))
+    center = bank.center.cpu().numpy()
+    assert np.abs(center - s.mean(0, dtype=np.float64)).max() < 1e-5
+    expect = O.quantize_bf16(s[perm] - center)
+    got = bank.feats_bf16.float().cpu().numpy()
+    assert got.shape == (N, 128)
+    assert np.array_equal(got[:, :d], expect) and not got[:, d:].any()
+    sq = (expect.astype(np.float64) ** 2).sum(1)
+    assert np.allclose(bank.sqnorm.cpu().numpy(), sq, rtol=1e-5)
+    # 3-product split: [hi | hi | lo] with lo = bf16(x - hi)
+    b3 = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, "cosine", "bf16x3")
+    sn = (s[perm] / np.maximum(np.sqrt((s[perm].astype(np.float64) ** 2).sum(1, keepdims=True)), 1e-12)).astype(np.float32)
+    g3 = b3.feats_bf16.float().cpu().numpy()
+    hi = g3[:, :d]
+    assert np.abs(hi - sn).max() < 2 ** -8 and np.array_equal(g3[:, d:2 * d], hi)
+    assert np.abs(hi + g3[:, 2 * d:3 * d] - sn).max() < 2 ** -15
+
+
+def test_class_centroids_golden(cuda_lib, golden_clusters):
+    from nwhead_b200 import compute_clusters
+
+    g = golden_clusters
+    cf, cy = compute_clusters(torch.from_numpy(g["f"]).to(DEV), torch.from_numpy(g["y"]).to(DEV), 1)
+    assert np.array_equal(cy.cpu().numpy(), g["cy"])
+    assert np.abs(cf.cpu().numpy() - g["cf"]).max() < 2e-6
+
+
+@pytest.mark.parametrize("shape", [(1000, 2048, 10), (5000, 512, 200), (777, 100, 31)])
+def test_class_centroids_shapes(cuda_lib, shape):
+    from nwhead_b200 import compute_clusters
+
+    N, d, C = shape
+    rng = np.random.default_rng(N)
+    y = rng.integers(0, C, N).astype(np.int64)  # unsorted
+    f = rng.normal(size=(N, d)).astype(np.float32) + 2
+    cf, cy = compute_clusters(torch.from_numpy(f).to(DEV), torch.from_numpy(y).to(DEV), 1)
+    oc, oy = O.class_centroids(f, y)
+    assert np.array_equal(cy.cpu().numpy(), oy)
+    assert np.abs(cf.cpu().numpy() - oc).max() < 5e-6
+
+
+def test_support_influence_golden(cuda_lib, golden_influence):
+    from nwhead_b200 import support_influence
+
+    g = golden_influence
+    B, N = g["w"].shape
+    C = g["P"].shape[1]
+    P, w = torch.from_numpy(g["P"]).to(DEV), torch.from_numpy(g["w"]).to(DEV)
+    qoh = torch.nn.functional.one_hot(torch.from_numpy(g["qy"]), C).float().to(DEV)
+    soh = torch.nn.functional.one_hot(torch.from_numpy(g["sy"]), C).float().to(DEV)
+    out = support_influence(P, qoh, w, soh).cpu().numpy()
+    assert out.shape == (B, N)
+    assert np.allclose(out, g["infl"], rtol=1e-5, atol=2e-7)
+    out3 = support_influence(P, qoh, w, soh[None].expand(B, N, C).contiguous()).cpu().numpy()
+    assert out3.shape == (B, B, N)
+    assert np.allclose(out3, g["infl3"], rtol=1e-5, atol=2e-7)
+    e = support_influence(torch.from_numpy(g["edge_P"]).to(DEV), torch.tensor([[1.0, 0.0]], device=DEV),
+                          torch.from_numpy(g["edge_w"]).to(DEV), torch.eye(2, device=DEV)).cpu().numpy()
+    assert np.isposinf(e[0, 0]) and np.isclose(e[0, 1], g["edge_infl"][0, 1], rtol=1e-6)
+
+
+def test_support_influence_ragged(cuda_lib):
+    """N not a multiple of 4 (scalar path) and a larger vectorised case, vs the oracle."""
+    from nwhead_b200.metric import support_influence_from_labels
+
+    for B, N, C in [(7, 1001, 9), (64, 4096, 200)]:
+        q, s, y, qy = clustered_features(C, (N + C - 1) // C, 32, B, seed=N)
+        s, y = s[:N], y[:N]
+        sc = O.pairwise_scores(q, s, "euclidean")
+        w = np.exp(sc - sc.max(1, keepdims=True))
+        w = (w / w.sum(1, keepdims=True)).astype(np.float32)
+        P = np.zeros((B, C), np.float32)
+        np.add.at(P.T, y, w.T)
+        got = support_influence_from_labels(torch.from_numpy(P).to(DEV), torch.from_numpy(qy).to(DEV),
+                                            torch.from_numpy(w).to(DEV), torch.from_numpy(y).to(DEV)).cpu().numpy()
+        ref = O.support_influence(P, qy, w, y)
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), ok)
+        assert np.allclose(got[ok], ref[ok], rtol=2e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("n", [10, 300, 4096, 5800, 20000])
+def test_rank_rows_bit_exact(cuda_lib, n):
+    from nwhead_b200.utils import rank_rows
+
+    rng = np.random.default_rng(n)
+    sc = rng.permutation(n * 3).reshape(3, n).astype(np.float32) - n  # ties-free
+    got = rank_rows(torch.from_numpy(sc).to(DEV)).cpu().numpy()
+    assert np.array_equal(got, np.argsort(-sc, axis=1, kind="stable"))
+    k = min(7, n)
+    assert np.array_equal(rank_rows(torch.from_numpy(sc).to(DEV), k).cpu().numpy(), got[:, :k])

@@ -1,0 +1,112 @@
+"""GPU: the fused tcgen05 forward (through the C ABI) against the oracle and the reference fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nw_oracle as O
+from gpu_util import assert_head_parity, clustered_features
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def run_bank(q, s, y, C, kind, precision, scale=1.0):
+    from nwhead_b200 import SupportBank
+
+    bank = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, kind, precision)
+    out = bank.forward(torch.from_numpy(q).to(DEV), scale)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("kind", ["euclidean", "cosine", "hypersphere_euclidean", "dotproduct"])
+@pytest.mark.parametrize("shape", [(8, 10, 30, 64), (37, 20, 29, 512), (130, 7, 300, 96), (300, 1000, 1, 128)])
+def test_forward_matches_oracle(cuda_lib, shape, kind, precision):
+    B, C, per, d = shape
+    # one support row per class (cluster / random mode shape): keep the classes separated so that top-1 is
+    # decided by a margin larger than the bf16 rounding error rather than by near-ties
+    q, s, y, _ = clustered_features(C, per, d, B, seed=B + d, spread=0.25 if per == 1 else 1.0)
+    if kind == "dotproduct":  # keep exp() in range: the reference has no temperature either
+        q, s = q * 0.05, s * 0.05
+    out = run_bank(q, s, y, C, kind, precision)
+    ref = O.nw_forward(q, s, y, C, kind)
+    perr, _ = assert_head_parity(out, ref)
+    if precision == "bf16x3":
+        assert perr < 2e-5, f"3-product split should be near fp32, got {perr:.2e}"
+
+
+def test_clip_scale(cuda_lib):
+    q, s, y, _ = clustered_features(12, 40, 64, 16, seed=3)
+    out = run_bank(q, s, y, 12, "clip", "bf16", scale=float(np.exp(O.CLIP_LOGIT_SCALE_INIT)))
+    assert_head_parity(out, O.nw_forward(q, s, y, 12, "clip"))
+
+
+@pytest.mark.parametrize("kind", O.KERNEL_KINDS)
+@pytest.mark.parametrize("case", ["mm_medium", "wide"])
+def test_reference_fixtures_through_nwhead(cuda_lib, golden_head, case, kind):
+    """NWHead.forward drop-in on the reference's own inputs: unsorted labels, duplicates, absent
+    classes, a query that coincides with a support row."""
+    import nwhead_b200
+
+    g = golden_head
+    C = int(g[f"{case}/C"])
+    head = nwhead_b200.NWHead(nwhead_b200.get_kernel(kind), C).to(DEV)
+    with torch.no_grad():
+        out = head(torch.from_numpy(g[f"{case}/q"]).to(DEV), torch.from_numpy(g[f"{case}/s"]).to(DEV),
+                   torch.from_numpy(g[f"{case}/y"]).to(DEV))
+    ref = g[f"{case}/{kind}/logp"]
+    assert_head_parity(out, ref)
+    absent = np.setdiff1d(np.arange(C), np.unique(g[f"{case}/y"]))
+    got = out.cpu().numpy()[:, absent]
+    assert np.array_equal(got, np.full_like(got, np.log(np.float32(1e-12))))  # exactly log(1e-12)
+
+
+def test_multi_chunk_boundaries_and_ragged_tail(cuda_lib):
+    """N not a multiple of the 256-row tile, classes of uneven size cut by tile and chunk boundaries,
+    B not a multiple of 128; compared class-LSE by class-LSE with the oracle."""
+    from nwhead_b200 import SupportBank, _abi
+
+    rng = np.random.default_rng(5)
+    C, d, B = 23, 128, 200
+    sizes = rng.integers(1, 900, C)
+    sizes[4] = 0  # an absent class in the middle
+    y = np.repeat(np.arange(C), sizes).astype(np.int64)
+    mu = rng.normal(size=(C, d))
+    s = (mu[y] + rng.normal(size=(len(y), d))).astype(np.float32)
+    q = (mu[rng.integers(0, C, B)] + rng.normal(size=(B, d))).astype(np.float32)
+    plan = _abi.forward_plan(B, len(y))
+    assert plan.chunks > 1 and len(y) % 256 != 0
+    bank = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, "euclidean", "bf16x3")
+    lse = bank.class_lse(torch.from_numpy(q).to(DEV)).cpu().numpy()
+    ref = O.class_lse(O.pairwise_scores(q, s, "euclidean"), y, C)
+    assert np.isneginf(lse[:, 4]).all() and np.isneginf(ref[:, 4]).all()
+    fin = np.isfinite(ref)
+    assert np.abs(lse[fin] - ref[fin]).max() < 2e-3
+    out = bank.forward(torch.from_numpy(q).to(DEV))
+    assert_head_parity(out, O.logp_from_class_lse(ref), prob_tol=2e-5)
+
+
+def test_bitwise_reproducible(cuda_lib):
+    q, s, y, _ = clustered_features(50, 100, 256, 300, seed=9)
+    a = run_bank(q, s, y, 50, "euclidean", "bf16")
+    b = run_bank(q, s, y, 50, "euclidean", "bf16")
+    assert torch.equal(a, b)
+
+
+def test_large_distances_do_not_underflow(cuda_lib):
+    """Distances of several hundred: exp(-dist) underflows in fp32 without the running max."""
+    q, s, y, _ = clustered_features(10, 40, 512, 32, seed=1)
+    q, s = q * 40.0, s * 40.0
+    out = run_bank(q, s, y, 10, "euclidean", "bf16x3")
+    assert_head_parity(out, O.nw_forward(q, s, y, 10, "euclidean"), prob_tol=1e-3)
+
+
+def test_label_errors_raise(cuda_lib):
+    from nwhead_b200 import SupportBank
+
+    s = torch.randn(40, 16, device=DEV)
+    with pytest.raises(RuntimeError, match="num_classes"):
+        SupportBank.build(s, torch.full((40,), 7, device=DEV, dtype=torch.int64), 5)
+    with pytest.raises(RuntimeError, match="LongTensor"):
+        SupportBank.build(s, torch.zeros(40, device=DEV, dtype=torch.int32), 5)

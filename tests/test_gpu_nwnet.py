@@ -1,0 +1,77 @@
+"""GPU: the unmodified NWNet flow (precompute -> predict in three modes -> get_neighbors -> one training
+step) with the CUDA head, against the reference run recorded in tests/golden/nwnet_flow.npz."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class TinyDataset(torch.utils.data.Dataset):
+    def __init__(self, x, y):
+        self.x, self.targets = torch.from_numpy(x), [int(v) for v in y]
+
+    def __len__(self):
+        return len(self.targets)
+
+    def __getitem__(self, i):
+        return self.x[i], self.targets[i]
+
+
+def make_net(g, kind):
+    import nwhead_b200
+
+    feat = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(192, 16), torch.nn.ReLU())
+    with torch.no_grad():
+        feat[1].weight.copy_(torch.from_numpy(g["W"]))
+        feat[1].bias.copy_(torch.from_numpy(g["b"]))
+    ds = TinyDataset(g["ds_x"], g["ds_y"])
+    net = nwhead_b200.NWNet(feat, 6, support_dataset=ds, feat_dim=16, kernel_type=kind, n_shot=2, n_way=4,
+                            n_shot_random=2, n_shot_full=5, n_shot_cluster=1, device=DEV)
+    return net.to(DEV), feat
+
+
+@pytest.mark.parametrize("kind", ["euclidean", "cosine"])
+def test_precompute_predict_neighbors(cuda_lib, golden_flow, kind):
+    g = golden_flow
+    net, _ = make_net(g, kind)
+    net.eval()
+    xq = torch.from_numpy(g["xq"]).to(DEV)
+    with torch.no_grad():
+        with pytest.raises(AttributeError, match="precompute"):
+            net.predict(xq, mode="full")
+        net.precompute()
+        assert np.array_equal(net.full_y.cpu().numpy(), g[f"{kind}/full_y"])
+        assert np.abs(net.full_feat.cpu().numpy() - g[f"{kind}/full_feat"]).max() < 1e-4
+        assert np.array_equal(net.support_eval.cluster_y.cpu().numpy(), g[f"{kind}/cluster_y"])
+        assert np.abs(net.support_eval.cluster_feat.cpu().numpy() - g[f"{kind}/cluster_feat"]).max() < 1e-4
+        for mode in ("full", "cluster"):
+            out = net.predict(xq, mode=mode).cpu().numpy()
+            ref = g[f"{kind}/pred_{mode}"]
+            assert np.abs(np.exp(out) - np.exp(ref)).max() < 1e-3
+            assert (out.argmax(1) == ref.argmax(1)).all()
+        np.random.seed(123)  # same numpy stream as the reference run -> same sampled support
+        out = net.predict(xq, mode="random").cpu().numpy()
+        assert np.abs(np.exp(out) - np.exp(g[f"{kind}/pred_random"])).max() < 1e-3
+        with pytest.raises(NotImplementedError):
+            net.predict(xq, mode="bogus")
+        if kind == "euclidean":
+            nb = net.get_neighbors(xq).cpu().numpy()
+            assert nb.shape == g[f"{kind}/neighbors"].shape and nb.dtype == np.int64
+            assert np.array_equal(nb, g[f"{kind}/neighbors"])
+
+
+@pytest.mark.parametrize("kind", ["euclidean", "cosine"])
+def test_training_step(cuda_lib, golden_flow, kind):
+    g = golden_flow
+    net, feat = make_net(g, kind)
+    net.train()
+    np.random.seed(321)
+    x, y = torch.from_numpy(g["xq"][:4]).to(DEV), torch.from_numpy(g["yq"][:4]).to(DEV)
+    logp = net(x, y)
+    loss = torch.nn.functional.nll_loss(logp, y)
+    loss.backward()
+    assert np.abs(logp.detach().cpu().numpy() - g[f"{kind}/train_logp"]).max() < 1e-4
+    gw = g[f"{kind}/train_gW"]
+    assert np.abs(feat[1].weight.grad.cpu().numpy() - gw).max() < 1e-6 + 2e-4 * np.abs(gw).max()

@@ -1,0 +1,90 @@
+"""CPU: host-side support-set bookkeeping of the drop-in package (no GPU, no compute calls) — class
+index separation, class-balanced bank order, and numpy-RNG-stream parity of the samplers with the
+reference (when /root/reference is importable; the properties are checked either way)."""
+import numpy as np
+import pytest
+import torch
+
+from nwhead_b200 import utils as U
+from oracle import nw_oracle as O
+from oracle.ref_import import load_reference, reference_available
+
+
+class ToyDataset(torch.utils.data.Dataset):
+    def __init__(self, targets):
+        self.targets = list(targets)
+
+    def __len__(self):
+        return len(self.targets)
+
+    def __getitem__(self, i):
+        return torch.full((2,), float(i)), self.targets[i]
+
+
+def test_separated_indices_docstring_example():
+    assert U.get_separated_indices([0, 1, 1, 2, 3]) == [[0], [1, 2], [3], [4]]
+    # non-consecutive labels map to consecutive slots in sorted order (reference nwhead/utils.py:152-153)
+    assert U.get_separated_indices(torch.tensor([7, 3, 7, 5])) == [[1], [3], [0, 2]]
+
+
+def test_full_dataset_is_class_sorted_balanced_truncated():
+    rng = np.random.default_rng(0)
+    targets = rng.integers(0, 7, 200).tolist()
+    fd = U.FullDataset(ToyDataset(targets), 12)
+    keys = np.asarray(fd.keys)
+    assert np.array_equal(keys, O.full_bank_keys(targets, 12))
+    labs = np.asarray(targets)[keys]
+    assert (np.diff(labs) >= 0).all()                       # class-sorted
+    assert len(set(np.bincount(labs))) == 1                  # balanced
+    assert len(fd) == 7 * min(12, np.bincount(targets).min())
+    assert fd[3][1] == labs[3]
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference not mounted (GPU box)")
+def test_sampler_rng_stream_matches_reference():
+    ref = load_reference()
+    rng = np.random.default_rng(1)
+    targets = rng.integers(0, 9, 120).tolist()
+    ds = ToyDataset(targets)
+    for n_way, n_shot in [(None, 2), (5, 1), (6, 3)]:
+        a = U.InfiniteUniformClassLoader(U.DatasetMetadata(ds, np.zeros(len(ds))), n_shot, n_way)
+        b = ref.InfiniteUniformClassLoader(ref_meta(ref, ds), n_shot, n_way)
+        qy = torch.tensor([3, 3, 8]) if n_way else None
+        np.random.seed(42)
+        xa = a.next(qy)
+        np.random.seed(42)
+        xb = b.next(qy)
+        for ta, tb in zip(xa, xb):
+            assert torch.equal(torch.as_tensor(ta), torch.as_tensor(tb))
+        assert U.get_separated_indices(targets) == ref.get_separated_indices(targets)
+
+
+def ref_meta(ref, ds):
+    import importlib
+
+    return importlib.import_module("nwhead.utils").DatasetMetadata(ds, np.zeros(len(ds)))
+
+
+def test_sampler_properties():
+    rng = np.random.default_rng(2)
+    targets = rng.integers(0, 9, 150).tolist()
+    ld = U.InfiniteUniformClassLoader(U.DatasetMetadata(ToyDataset(targets), np.zeros(150)), 2, n_way=5)
+    np.random.seed(0)
+    qy = torch.tensor([1, 1, 4])
+    idx = ld.sample_indices(qy)
+    labs = np.asarray(targets)[idx]
+    assert len(idx) == 5 * 2                                 # n_way rows (query labels WITH duplicates) x n_shot
+    assert {1, 4} <= set(labs.tolist())
+    assert (labs[-6:] == np.repeat([1, 1, 4], 2)).all()      # query classes come last, duplicates kept
+    with pytest.raises(AssertionError):
+        ld.sample_indices(torch.arange(6))                  # len(qy) must be <= n_way
+
+
+def test_unknown_names_raise_like_the_reference():
+    import nwhead_b200
+
+    with pytest.raises(NotImplementedError):
+        nwhead_b200.get_kernel("nope")
+    assert nwhead_b200.get_kernel("clip").logit_scale.item() == pytest.approx(np.log(1 / 0.07))
+    with pytest.raises(NotImplementedError):
+        nwhead_b200.NWNet(torch.nn.Identity(), 3, support_dataset=ToyDataset([0, 1, 2]), env_array=np.zeros(3))

@@ -106,11 +106,12 @@ NW_API int nw_rows_to_bf16(const float* rows, int64_t n, int d, int64_t ld, cons
  * The (B, N) score matrix never reaches HBM.
  * ------------------------------------------------------------------------------------------ */
 typedef struct nw_forward_plan_t {
-  int q_tiles;         /* ceil(B / 128) */
+  int q_tiles;         /* query tiles: ceil(B / 128), or ceil(B / 256) when cta_pair */
   int s_tiles;         /* ceil(N / 256) */
   int chunks;          /* contiguous support chunks the bank is cut into */
   int tiles_per_chunk; /* support tiles per chunk */
   int grid;            /* persistent CTAs launched */
+  int cta_pair;        /* 1: CTA pairs (cluster of 2, tcgen05 cta_group::2, 256x256 tiles); 0: single CTAs */
   int64_t side_elems;  /* floats of scratch `side` required: chunks * B * 2 */
 } nw_forward_plan_t;
 

@@ -32,6 +32,7 @@ class ForwardPlan(ctypes.Structure):
         ("chunks", c_int),
         ("tiles_per_chunk", c_int),
         ("grid", c_int),
+        ("cta_pair", c_int),
         ("side_elems", c_int64),
     ]
 

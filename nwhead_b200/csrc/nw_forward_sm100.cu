@@ -17,24 +17,36 @@
 // Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
 // warps 4-7 epilogue (one thread per query row = TMEM lane).
 
+#include <stdlib.h>
+
 #include "nw_common.cuh"
 
 namespace nw {
 namespace k1 {
 
-constexpr int BM = 128;  // queries per tile  (UMMA M, TMEM lanes)
-constexpr int BN = 256;  // supports per tile (UMMA N, TMEM columns)
+constexpr int BM = 128;  // queries per CTA tile (TMEM lanes)
+constexpr int BN = 256;  // supports per tile    (UMMA N, TMEM columns)
 constexpr int BK = 64;   // bf16 per k-block = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 = all of TMEM
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 128;
+
+// NCTA = 1: one CTA computes a 128 x 256 tile (UMMA M=128).
+// NCTA = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x 256 tile (UMMA M=256); each CTA stages
+//           its own 128 query rows and HALF of the support tile, so L2->SM traffic and shared-memory operand
+//           reads per FLOP drop by a third and the smaller stages allow a 6-deep TMA ring.
+template <int NCTA>
+struct Cfg {
+  static constexpr int STAGES = NCTA == 1 ? 4 : 6;
+  static constexpr int B_ROWS = BN / NCTA;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+};
 
 struct TileMeta {
   float cadd[BN];    // per-column additive term: |s|^2 (EUCLID) or 0 (LINEAR); +inf / -inf for padding columns
@@ -43,14 +55,17 @@ struct TileMeta {
 
 struct SmemTail {
   TileMeta meta[ACC_STAGES];
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
   uint64_t tfull[ACC_STAGES];
   uint64_t tempty[ACC_STAGES];
   uint32_t tmem_base;
 };
 
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + size_t(STAGES) * STAGE_BYTES + sizeof(SmemTail);
+template <int NCTA>
+constexpr size_t smem_bytes() {
+  return 1024 /*align slack*/ + size_t(Cfg<NCTA>::STAGES) * Cfg<NCTA>::STAGE_BYTES + sizeof(SmemTail);
+}
 
 struct Params {
   const float* q_sqnorm;
@@ -62,7 +77,7 @@ struct Params {
   int n_support;
   int n_classes;
   int kblocks;
-  int q_tiles;
+  int q_groups;  // query tiles of 128 * NCTA rows
   int s_tiles;
   int chunks;
   int tiles_per_chunk;
@@ -132,19 +147,26 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
   }
 }
 
-template <int EPI>
+template <int EPI, int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_s,
                   const Params p) {
+  using C = Cfg<NCTA>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int STAGE_BYTES = C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
-  uint8_t* smem = smem_raw + pad;  // 1024-B aligned (swizzle-128B atoms)
+  uint8_t* smem = smem_raw + pad;  // 1024-B aligned (swizzle-128B atoms); same offset in both CTAs of a pair
   SmemTail* tail = reinterpret_cast<SmemTail*>(smem + size_t(STAGES) * STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_units = p.chunks * p.q_tiles;
+  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int worker = blockIdx.x / NCTA;
+  const int n_workers = gridDim.x / NCTA;
+  const int n_units = p.chunks * p.q_groups;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -157,16 +179,22 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(smem_u32(&tail->tfull[i]), 1);
-      mbar_init(smem_u32(&tail->tempty[i]), EPI_THREADS / 32);
+      mbar_init(smem_u32(&tail->tempty[i]), NCTA * EPI_THREADS / 32);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(&tail->tmem_base), TMEM_COLS);
-    tmem_relinquish();
+    if (NCTA == 2) {
+      tmem_alloc_pair(smem_u32(&tail->tmem_base), TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32(&tail->tmem_base), TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
@@ -174,47 +202,57 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     // ===================================== TMA producer =====================================
     if (elect_one()) {
       const uint64_t pol_q = l2_policy_evict_last();    // queries are re-read for every support tile
-      const uint64_t pol_s = l2_policy_evict_normal();  // a support tile is shared by the CTAs of a wave
+      const uint64_t pol_s = l2_policy_evict_normal();  // a support tile is shared by the workers of a wave
       uint32_t it = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int g = u / p.q_tiles;
-        const int qt = u - g * p.q_tiles;
+      for (int u = worker; u < n_units; u += n_workers) {
+        const int g = u / p.q_groups;
+        const int qg = u - g * p.q_groups;
         const int t0 = g * p.tiles_per_chunk;
         const int t1 = min(t0 + p.tiles_per_chunk, p.s_tiles);
+        const int q_row0 = (qg * NCTA + int(cta_rank)) * BM;
         for (int t = t0; t < t1; ++t) {
+          const int s_row0 = t * BN + int(cta_rank) * C::B_ROWS;
           for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
             const uint32_t s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
-            const uint32_t bar = smem_u32(&tail->full[s]);
             const uint32_t a_dst = smem_u32(smem + size_t(s) * STAGE_BYTES);
-            mbar_arrive_expect_tx(bar, STAGE_BYTES);
-            tma_load_2d(a_dst, &map_q, bar, kb * BK, qt * BM, pol_q);
-            tma_load_2d(a_dst + A_BYTES, &map_s, bar, kb * BK, t * BN, pol_s);
+            if (NCTA == 2) {
+              // both CTAs' bytes are accounted on the LEADER's full barrier (the MMA issuer waits there)
+              const uint32_t bar = mapa_u32(smem_u32(&tail->full[s]), 0);
+              if (leader) mbar_arrive_expect_tx(smem_u32(&tail->full[s]), 2 * STAGE_BYTES);
+              tma_load_2d_pair(a_dst, &map_q, bar, kb * BK, q_row0, pol_q);
+              tma_load_2d_pair(a_dst + A_BYTES, &map_s, bar, kb * BK, s_row0, pol_s);
+            } else {
+              const uint32_t bar = smem_u32(&tail->full[s]);
+              mbar_arrive_expect_tx(bar, STAGE_BYTES);
+              tma_load_2d(a_dst, &map_q, bar, kb * BK, q_row0, pol_q);
+              tma_load_2d(a_dst + A_BYTES, &map_s, bar, kb * BK, s_row0, pol_s);
+            }
           }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    // ===================================== MMA issuer (leader CTA only) ======================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * NCTA, BN);
       uint32_t it = 0, tc = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int g = u / p.q_tiles;
+      for (int u = worker; u < n_units; u += n_workers) {
+        const int g = u / p.q_groups;
         const int t0 = g * p.tiles_per_chunk;
         const int t1 = min(t0 + p.tiles_per_chunk, p.s_tiles);
         for (int t = t0; t < t1; ++t, ++tc) {
           const uint32_t as = tc & 1u;
           const uint32_t aph = (tc >> 1) & 1u;
-          mbar_wait(smem_u32(&tail->tempty[as]), aph ^ 1u);  // epilogue has drained this accumulator
+          mbar_wait(smem_u32(&tail->tempty[as]), aph ^ 1u);  // epilogues have drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * BN;
           for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
             const uint32_t s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
-            mbar_wait(smem_u32(&tail->full[s]), ph);  // TMA bytes have landed
+            mbar_wait(smem_u32(&tail->full[s]), ph);  // TMA bytes (of both CTAs) have landed
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + size_t(s) * STAGE_BYTES);
             const uint64_t adesc = umma_desc_k128(a_addr);
@@ -222,11 +260,16 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               // advance 32 B (= 16 bf16) inside the 128-B swizzled row: +2 in the 16-B address field
-              umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (NCTA == 2) umma_bf16_ss_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(smem_u32(&tail->empty[s]));  // frees the smem stage once these MMAs retire
+            // frees the smem stage (in both CTAs) once these MMAs retire
+            if (NCTA == 2) umma_commit_pair(smem_u32(&tail->empty[s]), 3);
+            else umma_commit(smem_u32(&tail->empty[s]));
           }
-          umma_commit(smem_u32(&tail->tfull[as]));  // accumulator complete -> epilogue
+          // accumulator complete -> epilogue warps (of both CTAs)
+          if (NCTA == 2) umma_commit_pair(smem_u32(&tail->tfull[as]), 3);
+          else umma_commit(smem_u32(&tail->tfull[as]));
         }
       }
     }
@@ -239,14 +282,14 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const float neg_inf = __int_as_float(0xff800000);
     const float pos_inf = __int_as_float(0x7f800000);
     uint32_t tc = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int g = u / p.q_tiles;
-      const int qt = u - g * p.q_tiles;
+    for (int u = worker; u < n_units; u += n_workers) {
+      const int g = u / p.q_groups;
+      const int qg = u - g * p.q_groups;
       const int t0 = g * p.tiles_per_chunk;
       const int t1 = min(t0 + p.tiles_per_chunk, p.s_tiles);
       const int n0 = t0 * BN;
       const int n1 = min(t1 * BN, p.n_support);
-      const int row = qt * BM + ew * 32 + lane;
+      const int row = (qg * NCTA + int(cta_rank)) * BM + ew * 32 + lane;
 
       Flusher flush;
       flush.row_valid = row < p.n_query;
@@ -298,19 +341,24 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           tmem_ld_wait();
           epilogue_chunk<EPI>(acc, meta.cadd + c * 32, meta.lab + c * 32, emask[c], qn, scale2, m, l, flush);
         }
-        // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+        // all TMEM reads of this accumulator are complete -> hand it back to the (leader's) MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tail->tempty[as]));
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tempty[as]), 0));
+          else mbar_arrive(smem_u32(&tail->tempty[as]));
+        }
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();  // no CTA may exit while its peer can still signal into its shared memory
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (NCTA == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -434,24 +482,32 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
 
 using namespace nw;
 
+static bool force_single_cta() {
+  const char* e = getenv("NW_B200_FORCE_1CTA");
+  return e && e[0] == '1';
+}
+
 extern "C" int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t* plan) {
   NW_REQUIRE(plan != nullptr, NW_ERR_INVALID, "plan_out is NULL");
   NW_REQUIRE(n_query > 0 && n_support > 0, NW_ERR_INVALID, "n_query and n_support must be positive");
   NW_REQUIRE(n_support < (int64_t(1) << 31) - 512, NW_ERR_UNSUPPORTED, "n_support must be < 2^31 - 512");
-  const int ncta = sm_count();
-  NW_REQUIRE(ncta > 0, NW_ERR_CUDA, "no CUDA device");
-  const int q_tiles = ceil_div(n_query, k1::BM);
+  const int sms = sm_count();
+  NW_REQUIRE(sms > 0, NW_ERR_CUDA, "no CUDA device");
+  // more than one 128-row query tile: pair CTAs (cta_group::2, 256 x 256 tiles)
+  const int ncta = (n_query > k1::BM && !force_single_cta() && sms >= 2) ? 2 : 1;
+  const int workers = sms / ncta;
+  const int q_groups = ceil_div(n_query, k1::BM * ncta);
   const int s_tiles = int(ceil_div_ll(n_support, k1::BN));
-  // choose the number of chunks so that (chunks * q_tiles) fills whole waves of persistent CTAs
+  // choose the number of chunks so that (chunks * q_groups) fills whole waves of persistent workers
   long long best_cost = -1;
   int best_tpc = s_tiles;
   for (int w = 1; w <= 64; ++w) {
-    long long want = ceil_div_ll((long long)w * ncta, q_tiles);
+    long long want = ceil_div_ll((long long)w * workers, q_groups);
     int G = int(want < s_tiles ? want : s_tiles);
     if (G < 1) G = 1;
     const int tpc = ceil_div(s_tiles, G);
     const int Ge = ceil_div(s_tiles, tpc);
-    const long long waves = ceil_div_ll((long long)Ge * q_tiles, ncta);
+    const long long waves = ceil_div_ll((long long)Ge * q_groups, workers);
     const long long cost = waves * (tpc + 1);  // +1 tile-equivalent of per-unit pipeline fill / flush
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
@@ -459,15 +515,46 @@ extern "C" int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t
     }
     if (G == s_tiles) break;
   }
-  plan->q_tiles = q_tiles;
+  plan->q_tiles = q_groups;
   plan->s_tiles = s_tiles;
   plan->tiles_per_chunk = best_tpc;
   plan->chunks = ceil_div(s_tiles, best_tpc);
-  const long long units = (long long)plan->chunks * q_tiles;
-  plan->grid = int(units < ncta ? units : ncta);
+  const long long units = (long long)plan->chunks * q_groups;
+  plan->grid = int(units < workers ? units : workers) * ncta;
+  plan->cta_pair = ncta == 2 ? 1 : 0;
   plan->side_elems = int64_t(plan->chunks) * n_query * 2;
   return NW_OK;
 }
+
+namespace nw {
+namespace k1 {
+template <int EPI, int NCTA>
+static int launch_forward(const CUtensorMap& map_q, const CUtensorMap& map_s, const Params& p, int grid,
+                          cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = nw_forward_kernel<EPI, NCTA>;
+  constexpr size_t smem = smem_bytes<NCTA>();
+  if (!attr_set) {
+    NW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NW_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, map_q, map_s, p));
+  return NW_OK;
+}
+}  // namespace k1
+}  // namespace nw
 
 extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm,
                                     int n_query, const void* bank_bf16, const float* s_sqnorm,
@@ -489,11 +576,12 @@ extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf1
   if (rc != NW_OK) return rc;
   NW_REQUIRE(side_elems >= plan.side_elems, NW_ERR_WORKSPACE, "side scratch too small: %lld < %lld floats",
              (long long)side_elems, (long long)plan.side_elems);
+  const int ncta = plan.cta_pair ? 2 : 1;
 
   CUtensorMap map_q, map_s;
   rc = k1::make_map(&map_q, q_bf16, uint64_t(n_query), uint64_t(row_elems), k1::BM);
   if (rc != NW_OK) return rc;
-  rc = k1::make_map(&map_s, bank_bf16, uint64_t(n_support), uint64_t(row_elems), k1::BN);
+  rc = k1::make_map(&map_s, bank_bf16, uint64_t(n_support), uint64_t(row_elems), k1::BN / ncta);
   if (rc != NW_OK) return rc;
 
   k1::fill_kernel<<<sm_count() * 4, 256, 0, stream>>>(class_lse, (long long)n_query * n_classes, side,
@@ -510,29 +598,20 @@ extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf1
   p.n_support = int(n_support);
   p.n_classes = n_classes;
   p.kblocks = row_elems / k1::BK;
-  p.q_tiles = plan.q_tiles;
+  p.q_groups = plan.q_tiles;
   p.s_tiles = plan.s_tiles;
   p.chunks = plan.chunks;
   p.tiles_per_chunk = plan.tiles_per_chunk;
   p.scale_log2 = scale * kLog2e;
 
-  static bool attr_set[2] = {false, false};
   if (epilogue == NW_EPI_EUCLID) {
-    if (!attr_set[0]) {
-      NW_CUDA_OK(cudaFuncSetAttribute(k1::nw_forward_kernel<NW_EPI_EUCLID>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, int(k1::SMEM_BYTES)));
-      attr_set[0] = true;
-    }
-    k1::nw_forward_kernel<NW_EPI_EUCLID><<<plan.grid, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(map_q, map_s, p);
+    rc = ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2>(map_q, map_s, p, plan.grid, stream)
+                   : k1::launch_forward<NW_EPI_EUCLID, 1>(map_q, map_s, p, plan.grid, stream);
   } else {
-    if (!attr_set[1]) {
-      NW_CUDA_OK(cudaFuncSetAttribute(k1::nw_forward_kernel<NW_EPI_LINEAR>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, int(k1::SMEM_BYTES)));
-      attr_set[1] = true;
-    }
-    k1::nw_forward_kernel<NW_EPI_LINEAR><<<plan.grid, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(map_q, map_s, p);
+    rc = ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2>(map_q, map_s, p, plan.grid, stream)
+                   : k1::launch_forward<NW_EPI_LINEAR, 1>(map_q, map_s, p, plan.grid, stream);
   }
-  NW_CUDA_OK(cudaGetLastError());
+  if (rc != NW_OK) return rc;
 
   if (plan.chunks > 1) {
     k1::merge_side_kernel<<<ceil_div(n_query, 128), 128, 0, stream>>>(class_lse, side, labels, n_query,

@@ -147,10 +147,17 @@ NW_API int nw_direct_scores(int kind, float scale, const float* q, int n_query, 
                      int64_t n_support, int support_batched, float* scores, void* stream);
 
 /* softmax over the support axis + label aggregation + log: logp (B, C), row_lse (B) = logsumexp_j
- * scores[b, :] (saved for backward).  labels int64 as handed to F.one_hot: (N) or (B, N). */
+ * scores[b, :] (saved for backward).  labels int64 as handed to F.one_hot: (N) or (B, N).
+ * status_flag: caller-zeroed int32, bit 0 is OR-ed in when a label is outside [0, C) (never cleared). */
 NW_API int nw_direct_aggregate(const float* scores, const int64_t* labels, int labels_batched, int n_query,
-                        int64_t n_support, int n_classes, float* logp, float* row_lse, int32_t* status_out,
+                        int64_t n_support, int n_classes, float* logp, float* row_lse, int32_t* status_flag,
                         void* stream);
+
+/* scores + aggregate in one call; a single fused launch when n_support <= 1024 (episodic training). */
+NW_API int nw_direct_forward(int kind, float scale, const float* q, int n_query, int d, const float* s,
+                      int64_t n_support, int support_batched, const int64_t* labels, int labels_batched,
+                      int n_classes, float* scores, float* logp, float* row_lse, int32_t* status_flag,
+                      void* stream);
 
 /* closed-form backward.  workspace: nw_direct_backward_workspace_elems(...) floats.
  * grad_q (B, d) and grad_s ((N, d) or (B, N, d)) may each be NULL when not needed.

@@ -58,6 +58,8 @@ SIGNATURES = {
                                  c_void_p]),
     "nw_direct_aggregate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
+    "nw_direct_forward": (c_int, [c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p, c_int,
+                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nw_direct_backward_workspace_elems": (c_int64, [c_int, c_int64, c_int]),
     "nw_direct_backward": (c_int, [c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p,
                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

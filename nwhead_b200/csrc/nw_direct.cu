@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const float* __restrict_
     const long long y = lab[j];
     if (y < 0 || y >= n_classes) ++bad;
   }
-  if (bad && b == 0) atomicAdd(status, bad);
+  if (bad) atomicOr(status, 1);
   mx = block_max(mx, red);
   float sum = 0.f;
   for (long long j = threadIdx.x; j < n_support; j += blockDim.x) sum += expf(sc[j] - mx);
@@ -283,6 +283,240 @@ __global__ void __launch_bounds__(128) grad_s_batched_kernel(int kind, const flo
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused small-support kernels (episodic training: N <= SMALL_N supports per query).  One launch for the
+// whole forward, two for the backward; inverse norms are recomputed in registers instead of staged.
+// ---------------------------------------------------------------------------------------------
+constexpr int SMALL_N = 1024;
+
+__device__ __forceinline__ float pair_score(int kind, float scale, const float* __restrict__ qp,
+                                            const float* __restrict__ sp, int d, int lane) {
+  if (kind == NW_KIND_EUCLIDEAN) {
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float df = qp[c] - sp[c];
+      acc = fmaf(df, df, acc);
+    }
+    return -sqrtf(warp_sum(acc));
+  }
+  if (kind == NW_KIND_DOT) {
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc = fmaf(qp[c], sp[c], acc);
+    return warp_sum(acc);
+  }
+  float qq = 0.f, ss = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    qq = fmaf(qp[c], qp[c], qq);
+    ss = fmaf(sp[c], sp[c], ss);
+  }
+  const float iq = 1.0f / fmaxf(sqrtf(warp_sum(qq)), 1e-12f);
+  const float is = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  float acc = 0.f;
+  if (kind == NW_KIND_HYPERSPHERE) {
+    for (int c = lane; c < d; c += 32) {
+      const float df = __fsub_rn(__fmul_rn(qp[c], iq), __fmul_rn(sp[c], is));
+      acc = fmaf(df, df, acc);
+    }
+    return -sqrtf(warp_sum(acc));
+  }
+  for (int c = lane; c < d; c += 32) acc = fmaf(__fmul_rn(qp[c], iq), __fmul_rn(sp[c], is), acc);
+  const float out = warp_sum(acc);
+  return kind == NW_KIND_CLIP ? out * scale : out;
+}
+
+// one block per query: scores row -> softmax statistics -> per-class sums -> log-probs
+__global__ void __launch_bounds__(256) small_forward_kernel(int kind, float scale, const float* __restrict__ q,
+                                                            int d, const float* __restrict__ s, int n_support,
+                                                            int batched, const int64_t* __restrict__ labels,
+                                                            int labels_batched, int n_classes,
+                                                            float* __restrict__ scores, float* __restrict__ logp,
+                                                            float* __restrict__ row_lse,
+                                                            int32_t* __restrict__ status) {
+  __shared__ float sc[SMALL_N];
+  __shared__ int lab[SMALL_N];
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* qp = q + (long long)b * d;
+  const float* sb = s + (batched ? (long long)b * n_support * d : 0);
+  const int64_t* lb = labels + (labels_batched ? (long long)b * n_support : 0);
+  for (int j = warp; j < n_support; j += 8) {
+    const float v = pair_score(kind, scale, qp, sb + (long long)j * d, d, lane);
+    if (lane == 0) {
+      sc[j] = v;
+      scores[(long long)b * n_support + j] = v;
+    }
+  }
+  bool bad = false;
+  for (int j = threadIdx.x; j < n_support; j += 256) {
+    const long long y = lb[j];
+    bad |= (y < 0 || y >= n_classes);
+    lab[j] = int(y);
+  }
+  if (bad) atomicOr(status, 1);
+  __syncthreads();
+  float mx = __int_as_float(0xff800000);
+  for (int j = threadIdx.x; j < n_support; j += 256) mx = fmaxf(mx, sc[j]);
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < n_support; j += 256) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = block_sum(sum, red);  // (contains the barriers that publish sc[])
+  if (threadIdx.x == 0) row_lse[b] = mx + logf(sum);
+  const float inv = 1.0f / sum;
+  for (int c = threadIdx.x; c < n_classes; c += 256) {
+    float acc = 0.f;
+    for (int j = 0; j < n_support; ++j)
+      if (lab[j] == c) acc += sc[j];
+    logp[(long long)b * n_classes + c] = logf(acc * inv + 1e-12f);
+  }
+}
+
+// one block per query: dL/dscore coefficients (kept in shared memory and written for the grad_s pass) + grad_q
+__global__ void __launch_bounds__(256) small_coef_gradq_kernel(
+    int kind, float scale, const float* __restrict__ q, int d, const float* __restrict__ s, int n_support,
+    int batched, const int64_t* __restrict__ labels, int labels_batched, int n_classes,
+    const float* __restrict__ scores, const float* __restrict__ row_lse, const float* __restrict__ logp,
+    const float* __restrict__ grad_out, float* __restrict__ coef, float* __restrict__ grad_q,
+    float* __restrict__ grad_scale_rows) {
+  extern __shared__ float dyn[];  // [n_classes] gP, then [d] row
+  __shared__ float cf[SMALL_N];
+  __shared__ float isn[SMALL_N];
+  __shared__ float red[8];
+  float* gP = dyn;
+  float* row = dyn + n_classes;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool norm = kind_normalised(kind);
+  const bool euc = kind_euclid(kind);
+  const float* lp = logp + (long long)b * n_classes;
+  const float* g = grad_out + (long long)b * n_classes;
+  const float* qp = q + (long long)b * d;
+  const float* sb = s + (batched ? (long long)b * n_support * d : 0);
+  const int64_t* lb = labels + (labels_batched ? (long long)b * n_support : 0);
+  float dsum = 0.f;
+  for (int c = threadIdx.x; c < n_classes; c += 256) {
+    const float pe = expf(lp[c]);
+    const float gp = g[c] / pe;
+    gP[c] = gp;
+    dsum += fmaxf(pe - 1e-12f, 0.f) * gp;
+  }
+  dsum = block_sum(dsum, red);
+  const float z = row_lse[b];
+  float gscale = 0.f;
+  for (int j = threadIdx.x; j < n_support; j += 256) {
+    const float sv = scores[(long long)b * n_support + j];
+    const float gs = expf(sv - z) * (gP[lb[j]] - dsum);
+    float v;
+    if (euc) {
+      const float dist = -sv;
+      v = dist > 0.f ? gs / dist : 0.f;
+    } else {
+      v = (kind == NW_KIND_CLIP) ? gs * scale : gs;
+      gscale += gs * sv;
+    }
+    cf[j] = v;
+    coef[(long long)b * n_support + j] = v;
+  }
+  if (grad_scale_rows) {
+    gscale = block_sum(gscale, red);
+    if (threadIdx.x == 0) grad_scale_rows[b] = gscale;
+  }
+  float iq = 1.0f;
+  if (norm) {
+    for (int j = warp; j < n_support; j += 8) {
+      const float* sp = sb + (long long)j * d;
+      float ss = 0.f;
+      for (int c = lane; c < d; c += 32) ss = fmaf(sp[c], sp[c], ss);
+      ss = warp_sum(ss);
+      if (lane == 0) isn[j] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+    float qq = 0.f;
+    for (int c = threadIdx.x; c < d; c += 256) qq = fmaf(qp[c], qp[c], qq);
+    qq = block_sum(qq, red);
+    iq = 1.0f / fmaxf(sqrtf(qq), 1e-12f);
+  }
+  __syncthreads();
+  if (grad_q == nullptr) return;
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < d; c += 256) {
+    const float qv = qp[c] * iq;
+    float acc = 0.f, csum = 0.f;
+    for (int j = 0; j < n_support; ++j) {
+      const float w = cf[j];
+      const float sv = sb[(long long)j * d + c] * (norm ? isn[j] : 1.0f);
+      acc = fmaf(w, sv, acc);
+      csum += w;
+    }
+    if (euc) acc -= csum * qv;
+    row[c] = acc;
+    dot += acc * qv;
+  }
+  if (norm) {
+    dot = block_sum(dot, red);
+    for (int c = threadIdx.x; c < d; c += 256) grad_q[(long long)b * d + c] = (row[c] - dot * (qp[c] * iq)) * iq;
+  } else {
+    for (int c = threadIdx.x; c < d; c += 256) grad_q[(long long)b * d + c] = row[c];
+  }
+}
+
+// grad_s for a shared small support: one block per support row, inverse norms recomputed in the block
+__global__ void __launch_bounds__(256) small_grad_s_kernel(int kind, const float* __restrict__ q, int n_query, int d,
+                                                           const float* __restrict__ s, int n_support, int batched,
+                                                           const float* __restrict__ coef,
+                                                           float* __restrict__ grad_s) {
+  extern __shared__ float row[];  // d floats
+  __shared__ float iqs[256];
+  __shared__ float red[8];
+  const bool norm = kind_normalised(kind);
+  const bool euc = kind_euclid(kind);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pair = blockIdx.x;  // batched: (b, j) pair; shared: j
+  const int b0 = batched ? int(pair / n_support) : 0;
+  const int nb = batched ? 1 : n_query;
+  const int j = batched ? int(pair % n_support) : int(pair);
+  const float* sp = s + pair * d;
+  float is = 1.0f;
+  if (norm) {
+    float ss = 0.f;
+    for (int c = threadIdx.x; c < d; c += 256) ss = fmaf(sp[c], sp[c], ss);
+    ss = block_sum(ss, red);
+    is = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int bb = warp; bb < nb; bb += 8) {
+      const float* qp = q + (long long)(b0 + bb) * d;
+      float qq = 0.f;
+      for (int c = lane; c < d; c += 32) qq = fmaf(qp[c], qp[c], qq);
+      qq = warp_sum(qq);
+      if (lane == 0) iqs[bb] = 1.0f / fmaxf(sqrtf(qq), 1e-12f);
+    }
+    __syncthreads();
+  }
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < d; c += 256) {
+    const float sv = sp[c] * is;
+    float acc = 0.f, csum = 0.f;
+    for (int bb = 0; bb < nb; ++bb) {
+      const float w = coef[(long long)(b0 + bb) * n_support + j];
+      const float qv = q[(long long)(b0 + bb) * d + c] * (norm ? iqs[bb] : 1.0f);
+      acc = fmaf(w, qv, acc);
+      csum += w;
+    }
+    if (euc) acc -= csum * sv;
+    row[c] = acc;
+    dot += acc * sv;
+  }
+  if (norm) {
+    dot = block_sum(dot, red);
+    for (int c = threadIdx.x; c < d; c += 256) grad_s[pair * d + c] = (row[c] - dot * (sp[c] * is)) * is;
+  } else {
+    for (int c = threadIdx.x; c < d; c += 256) grad_s[pair * d + c] = row[c];
+  }
+}
+
 }  // namespace direct
 }  // namespace nw
 
@@ -315,9 +549,32 @@ extern "C" int nw_direct_aggregate(const float* scores, const int64_t* labels, i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NW_REQUIRE(scores && labels && logp && row_lse && status_out, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(n_query > 0 && n_support > 0 && n_classes > 0, NW_ERR_INVALID, "shapes must be positive");
-  NW_CUDA_OK(cudaMemsetAsync(status_out, 0, sizeof(int32_t), stream));
   direct::aggregate_kernel<<<n_query, 256, 0, stream>>>(scores, labels, labels_batched, n_support, n_classes, logp,
                                                         row_lse, status_out);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_direct_forward(int kind, float scale, const float* q, int n_query, int d, const float* s,
+                                 int64_t n_support, int support_batched, const int64_t* labels, int labels_batched,
+                                 int n_classes, float* scores, float* logp, float* row_lse, int32_t* status_flag,
+                                 void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_kind(kind);
+  if (rc != NW_OK) return rc;
+  NW_REQUIRE(q && s && labels && scores && logp && row_lse && status_flag, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n_query > 0 && d > 0 && n_support > 0 && n_classes > 0, NW_ERR_INVALID, "shapes must be positive");
+  if (n_support <= direct::SMALL_N) {
+    direct::small_forward_kernel<<<n_query, 256, 0, stream>>>(kind, scale, q, d, s, int(n_support), support_batched,
+                                                              labels, labels_batched, n_classes, scores, logp,
+                                                              row_lse, status_flag);
+    NW_CUDA_OK(cudaGetLastError());
+    return NW_OK;
+  }
+  rc = nw_direct_scores(kind, scale, q, n_query, d, s, n_support, support_batched, scores, stream_);
+  if (rc != NW_OK) return rc;
+  direct::aggregate_kernel<<<n_query, 256, 0, stream>>>(scores, labels, labels_batched, n_support, n_classes, logp,
+                                                        row_lse, status_flag);
   NW_CUDA_OK(cudaGetLastError());
   return NW_OK;
 }
@@ -339,11 +596,25 @@ extern "C" int nw_direct_backward(int kind, float scale, const float* q, int n_q
              "NULL pointer argument");
   NW_REQUIRE(grad_q || grad_s, NW_ERR_INVALID, "at least one of grad_q / grad_s must be requested");
   NW_REQUIRE(n_query > 0 && d > 0 && n_support > 0 && n_classes > 0, NW_ERR_INVALID, "shapes must be positive");
-  NW_REQUIRE(d <= 12288 && n_classes <= 12288, NW_ERR_UNSUPPORTED,
-             "direct backward stages one row / one class table in 48 KB of shared memory (d, C <= 12288)");
+  NW_REQUIRE(d + n_classes <= 10240, NW_ERR_UNSUPPORTED,
+             "direct backward stages one feature row and one class table in 40 KB of shared memory (d + C <= 10240)");
   const long long pairs = (long long)n_query * n_support;
   NW_REQUIRE(pairs < (1ll << 31), NW_ERR_UNSUPPORTED, "too many (query, support) pairs for the direct path");
   float* coef = workspace;
+  if (n_support <= direct::SMALL_N && (support_batched || n_query <= 256)) {
+    // fused small path: coefficients + grad_q in one launch, grad_s in a second
+    direct::small_coef_gradq_kernel<<<n_query, 256, (n_classes + d) * sizeof(float), stream>>>(
+        kind, scale, q, d, s, int(n_support), support_batched, labels, labels_batched, n_classes, scores, row_lse,
+        logp, grad_out, coef, grad_q, kind == NW_KIND_CLIP ? grad_scale_rows : nullptr);
+    NW_CUDA_OK(cudaGetLastError());
+    if (grad_s) {
+      const long long rows = support_batched ? pairs : n_support;
+      direct::small_grad_s_kernel<<<unsigned(rows), 256, d * sizeof(float), stream>>>(
+          kind, q, n_query, d, s, int(n_support), support_batched, coef, grad_s);
+      NW_CUDA_OK(cudaGetLastError());
+    }
+    return NW_OK;
+  }
   float* inv_s = workspace + pairs;
   float* inv_q = inv_s + (support_batched ? pairs : n_support);
   const bool norm = direct::kind_normalised(kind);

@@ -19,6 +19,55 @@ from .support import SupportSetEval, SupportSetTrain
 MM_PATH_MIN_ROWS = 26  # torch.cdist uses the matmul form when a side has more than 25 rows
 
 
+class _LabelGuard:
+    """Deferred label validation for the direct path.  The kernels OR a bit into a device flag when a label is
+    outside [0, n_classes) (what F.one_hot rejects, reference nwhead/nw.py:276).  The flag is copied to pinned
+    host memory asynchronously and inspected on a LATER call once its event has completed, so the training loop
+    never blocks on the GPU; `check(block=True)` forces the inspection."""
+
+    POLL_EVERY = 32  # the device flag is sticky, so polling it on every 32nd call loses nothing
+
+    def __init__(self, device):
+        self.flag = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self.event = None
+        self.calls = 0
+
+    def after_launch(self):
+        self.calls += 1
+        if self.calls % self.POLL_EVERY and self.calls != 1:
+            return
+        self.host.copy_(self.flag, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def check(self, block=False):
+        if self.event is None:
+            return
+        if block:
+            self.event.synchronize()
+        if self.event.query():
+            self.event = None
+            if int(self.host[0]) != 0:
+                self.flag.zero_()
+                self.host.zero_()
+                raise RuntimeError("Class values must be smaller than num_classes.")
+
+
+_guards = {}
+
+
+def label_guard(device) -> _LabelGuard:
+    key = (device.type, device.index)
+    if key not in _guards:
+        _guards[key] = _LabelGuard(device)
+    return _guards[key]
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
 class _NWDirectFunction(torch.autograd.Function):
     """Differentiable NWHead.forward (reference nwhead/nw.py:266-289) on the direct fp32 kernels;
     backward is the closed form of SURVEY.md B.2 (nw_direct_backward)."""
@@ -27,24 +76,21 @@ class _NWDirectFunction(torch.autograd.Function):
     def forward(ctx, x, sx, sy, logit_scale, kind, n_classes):
         lib = load()
         dev = _abi.require_cuda(x, sx, sy)
-        xq = x.detach().contiguous()
-        sxd = sx.detach().contiguous()
-        syd = sy.detach().contiguous()
+        xq, sxd, syd = _c(x.detach()), _c(sx.detach()), _c(sy.detach())
         b, d = xq.shape
         batched = sxd.dim() == 3
         n = sxd.shape[-2]
         scale = float(logit_scale.detach().exp()) if logit_scale is not None else 1.0
-        st = stream_of(dev)
-        scores = torch.empty((b, n), dtype=torch.float32, device=dev)
-        check(lib.nw_direct_scores(KIND[kind], scale, ptr(xq), b, d, ptr(sxd), n, int(batched), ptr(scores), st),
-              "nw_direct_scores")
-        logp = torch.empty((b, n_classes), dtype=torch.float32, device=dev)
-        row_lse = torch.empty((b,), dtype=torch.float32, device=dev)
-        status = torch.empty((1,), dtype=torch.int32, device=dev)
-        check(lib.nw_direct_aggregate(ptr(scores), ptr(syd), int(syd.dim() == 2), b, n, n_classes, ptr(logp),
-                                      ptr(row_lse), ptr(status), st), "nw_direct_aggregate")
-        if status.item():
-            raise RuntimeError("Class values must be smaller than num_classes.")  # F.one_hot's error
+        guard = label_guard(dev)
+        guard.check()
+        buf = torch.empty((b * (n + n_classes + 1),), dtype=torch.float32, device=dev)  # one allocation
+        scores = buf[:b * n].view(b, n)
+        logp = buf[b * n:b * (n + n_classes)].view(b, n_classes)
+        row_lse = buf[b * (n + n_classes):]
+        check(lib.nw_direct_forward(KIND[kind], scale, ptr(xq), b, d, ptr(sxd), n, int(batched), ptr(syd),
+                                    int(syd.dim() == 2), n_classes, ptr(scores), ptr(logp), ptr(row_lse),
+                                    ptr(guard.flag), stream_of(dev)), "nw_direct_forward")
+        guard.after_launch()
         ctx.save_for_backward(xq, sxd, syd, scores, row_lse, logp)
         ctx.kind, ctx.n_classes, ctx.scale = kind, n_classes, scale
         ctx.has_scale = logit_scale is not None
@@ -60,7 +106,7 @@ class _NWDirectFunction(torch.autograd.Function):
         n = sxd.shape[-2]
         need_q, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         need_scale = ctx.has_scale and ctx.needs_input_grad[3]
-        g = grad_out.detach().float().contiguous()
+        g = _c(grad_out.detach().float())
         gq = torch.empty_like(xq) if (need_q or not need_s) else None
         gs = torch.empty_like(sxd) if need_s else None
         gscale = torch.empty((b,), dtype=torch.float32, device=dev) if need_scale else None

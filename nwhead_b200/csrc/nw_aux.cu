@@ -115,6 +115,8 @@ __device__ __forceinline__ float influence_one(float p, float w, bool same) {
   return logf((p - p * w) / den);
 }
 
+constexpr int INFL_VEC_PER_THREAD = 4;  // 16-byte vectors per thread: 4 independent loads in flight
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) influence_kernel(const float* __restrict__ softmaxes,
                                                         const int32_t* __restrict__ qlabel,
@@ -123,23 +125,38 @@ __global__ void __launch_bounds__(256) influence_kernel(const float* __restrict_
                                                         int n_classes, int n_sets, float* __restrict__ out) {
   const int b = blockIdx.y;
   const int g = blockIdx.z;
-  const int qy = qlabel[b];
-  const float p = softmaxes[(long long)b * n_classes + qy];
   const float* w = sweights + (long long)b * n_support;
   const int32_t* sl = slabel + (long long)g * n_support;
   float* o = out + ((long long)b * n_sets + g) * n_support;
   if (VEC) {
-    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (j >= n_support) return;
-    const float4 wv = __ldcs(reinterpret_cast<const float4*>(w + j));
-    const int4 lv = *reinterpret_cast<const int4*>(sl + j);
-    float4 r;
-    r.x = influence_one(p, wv.x, lv.x == qy);
-    r.y = influence_one(p, wv.y, lv.y == qy);
-    r.z = influence_one(p, wv.z, lv.z == qy);
-    r.w = influence_one(p, wv.w, lv.w == qy);
-    __stcs(reinterpret_cast<float4*>(o + j), r);
+    const long long base = ((long long)blockIdx.x * blockDim.x * INFL_VEC_PER_THREAD + threadIdx.x) * 4;
+    float4 wv[INFL_VEC_PER_THREAD];
+    int4 lv[INFL_VEC_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < INFL_VEC_PER_THREAD; ++k) {  // all streaming loads first
+      const long long j = base + (long long)k * blockDim.x * 4;
+      if (j < n_support) {
+        wv[k] = __ldcs(reinterpret_cast<const float4*>(w + j));
+        lv[k] = __ldg(reinterpret_cast<const int4*>(sl + j));
+      }
+    }
+    const int qy = qlabel[b];
+    const float p = softmaxes[(long long)b * n_classes + qy];
+#pragma unroll
+    for (int k = 0; k < INFL_VEC_PER_THREAD; ++k) {
+      const long long j = base + (long long)k * blockDim.x * 4;
+      if (j < n_support) {
+        float4 r;
+        r.x = influence_one(p, wv[k].x, lv[k].x == qy);
+        r.y = influence_one(p, wv[k].y, lv[k].y == qy);
+        r.z = influence_one(p, wv[k].z, lv[k].z == qy);
+        r.w = influence_one(p, wv[k].w, lv[k].w == qy);
+        __stcs(reinterpret_cast<float4*>(o + j), r);
+      }
+    }
   } else {
+    const int qy = qlabel[b];
+    const float p = softmaxes[(long long)b * n_classes + qy];
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_support) return;
     o[j] = influence_one(p, w[j], sl[j] == qy);
@@ -285,7 +302,7 @@ extern "C" int nw_support_influence(const float* softmaxes, const int32_t* qlabe
   const bool vec = (n_support % 4 == 0) && ((reinterpret_cast<uintptr_t>(sweights) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(slabel) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (vec) {
-    dim3 grid(unsigned(ceil_div_ll(n_support, 1024)), n_query, n_label_sets);
+    dim3 grid(unsigned(ceil_div_ll(n_support, 1024 * aux::INFL_VEC_PER_THREAD)), n_query, n_label_sets);
     aux::influence_kernel<true><<<grid, 256, 0, stream>>>(softmaxes, qlabel, sweights, slabel, n_support, n_classes,
                                                           n_label_sets, out);
   } else {

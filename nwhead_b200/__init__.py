@@ -8,7 +8,8 @@ from .bank import SupportBank, logp_from_class_lse
 from .kernel import get_kernel
 from .metric import support_influence
 from .nw import NWHead, NWNet
+from .serving import FullModePredictor
 from .utils import compute_clusters
 
 __all__ = ["NWHead", "NWNet", "SupportBank", "get_kernel", "support_influence", "compute_clusters",
-           "logp_from_class_lse", "_abi"]
+           "logp_from_class_lse", "FullModePredictor", "_abi"]

@@ -205,10 +205,13 @@ class SupportBank:
         return logp_from_class_lse(self.class_lse(q, scale))
 
 
-def logp_from_class_lse(class_lse: torch.Tensor) -> torch.Tensor:
+def logp_from_class_lse(class_lse: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = load()
     b, c = class_lse.shape
-    out = torch.empty_like(class_lse)
+    if not class_lse.is_contiguous():
+        class_lse = class_lse.contiguous()
+    if out is None:
+        out = torch.empty_like(class_lse)
     check(lib.nw_logp_from_class_lse(ptr(class_lse), b, c, ptr(out), stream_of(class_lse.device)),
           "nw_logp_from_class_lse")
     return out

@@ -115,7 +115,7 @@ __device__ __forceinline__ float influence_one(float p, float w, bool same) {
   return logf((p - p * w) / den);
 }
 
-constexpr int INFL_VEC_PER_THREAD = 4;  // 16-byte vectors per thread: 4 independent loads in flight
+constexpr int INFL_VEC_PER_THREAD = 2;  // 16-byte vectors per thread: independent loads in flight
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) influence_kernel(const float* __restrict__ softmaxes,

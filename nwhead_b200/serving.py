@@ -1,0 +1,87 @@
+"""Pipelined full-mode predict from host memory (the end-to-end serving path).
+
+`FullModePredictor` takes query features that live in (pinned) HOST memory and returns log-probabilities
+in host memory.  Host<->device copies run on their own CUDA streams and are double-buffered, so the copy of
+batch i+1 and the read-back of batch i-1 overlap the fused forward of batch i.
+
+With a process group (one rank per GPU, class-aligned bank shards — nwhead_b200/dist.py) the host I/O is
+sharded too: rank r uploads only rows [r*B/R, (r+1)*B/R) of the batch, the ranks all-gather the queries over
+NVLink, run the fused forward on their bank shard, merge with ONE all-reduce(MAX), and each rank finalises and
+returns only its own rows.  PCIe traffic per rank drops by R while every query still sees the whole bank.
+"""
+import torch
+import torch.distributed as dist
+
+from .bank import SupportBank, logp_from_class_lse
+from .dist import merge_class_lse
+
+
+class _Slot:
+    def __init__(self, rows, rows_total, d, c, device, sharded):
+        self.q_slice = torch.empty((rows, d), dtype=torch.float32, device=device)
+        self.q_full = torch.empty((rows_total, d), dtype=torch.float32, device=device) if sharded else self.q_slice
+        self.logp = torch.empty((rows, c), dtype=torch.float32, device=device)
+        self.out_host = torch.empty((rows, c), dtype=torch.float32).pin_memory()
+        self.h2d_done = torch.cuda.Event()
+        self.compute_done = torch.cuda.Event()
+        self.d2h_done = torch.cuda.Event()
+        self.busy = False
+
+
+class FullModePredictor:
+    """predict(mode='full') for feature batches in host memory.
+
+    bank : SupportBank (whole bank, world size 1) or this rank's class-aligned shard.
+    rows : rows of the query batch THIS rank uploads / returns per call (B, or B / world_size).
+    """
+
+    def __init__(self, bank: SupportBank, rows: int, group=None, depth: int = 2, scale: float = 1.0):
+        self.bank, self.group, self.scale = bank, group, scale
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rows = rows
+        dev = bank.device
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.out_stream = torch.cuda.Stream(dev)
+        self.slots = [_Slot(rows, rows * self.world, bank.d, bank.n_classes, dev, self.world > 1)
+                      for _ in range(depth)]
+        self.next = 0
+
+    def submit(self, q_host: torch.Tensor) -> int:
+        """Enqueue one batch (this rank's rows, pinned fp32 host tensor).  Returns a ticket for result()."""
+        if q_host.is_cuda or q_host.shape != (self.rows, self.bank.d) or q_host.dtype != torch.float32:
+            raise ValueError(f"expected a host float32 tensor of shape ({self.rows}, {self.bank.d})")
+        ticket = self.next
+        slot = self.slots[ticket % len(self.slots)]
+        if slot.busy:
+            raise RuntimeError("pipeline full: call result() on the oldest ticket first")
+        slot.busy = True
+        self.next += 1
+        compute = torch.cuda.current_stream(self.bank.device)
+        self.copy_stream.wait_stream(compute)  # the slot's device buffers may still be read by older work
+        with torch.cuda.stream(self.copy_stream):
+            slot.q_slice.copy_(q_host, non_blocking=True)
+            slot.h2d_done.record(self.copy_stream)
+        compute.wait_event(slot.h2d_done)
+        if self.world > 1:
+            dist.all_gather_into_tensor(slot.q_full, slot.q_slice, group=self.group)
+        lse = merge_class_lse(self.bank.class_lse(slot.q_full, self.scale), self.group)
+        mine = lse[self.rank * self.rows:(self.rank + 1) * self.rows] if self.world > 1 else lse
+        logp_from_class_lse(mine, out=slot.logp)
+        slot.compute_done.record(compute)
+        self.out_stream.wait_event(slot.compute_done)
+        with torch.cuda.stream(self.out_stream):
+            slot.out_host.copy_(slot.logp, non_blocking=True)
+            slot.d2h_done.record(self.out_stream)
+        return ticket
+
+    def result(self, ticket: int) -> torch.Tensor:
+        """Blocks until the batch of `ticket` is back in host memory; returns the pinned (rows, C) tensor
+        (valid until the slot is reused `depth` submits later)."""
+        slot = self.slots[ticket % len(self.slots)]
+        slot.d2h_done.synchronize()
+        slot.busy = False
+        return slot.out_host
+
+    def __call__(self, q_host: torch.Tensor) -> torch.Tensor:
+        return self.result(self.submit(q_host))

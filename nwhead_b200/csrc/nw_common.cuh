@@ -120,6 +120,10 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c
                "r"(c0), "r"(c1)
                : "memory");
 }
+// Linear variant: pull `bytes` (multiple of 16) of contiguous global memory into L2.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));

@@ -71,6 +71,7 @@ struct Params {
   const float* q_sqnorm;
   const float* s_sqnorm;
   const int32_t* labels;
+  const uint8_t* bank;  // bf16 bank base (for linear L2 prefetch); row pitch = kblocks * 128 bytes
   float* class_lse;
   float* side;
   int n_query;
@@ -82,6 +83,7 @@ struct Params {
   int chunks;
   int tiles_per_chunk;
   float scale_log2;  // LINEAR: scale * log2(e)
+  int l2_prefetch;   // 1: pull the next support tile into L2 one tile ahead
 };
 
 struct Flusher {
@@ -221,9 +223,19 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
               const int un = u + n_workers;
               pt = un < n_units ? (un / p.q_groups) * p.tiles_per_chunk : -1;
             }
-            if (pt >= 0) {
-              const int p_row0 = pt * BN + int(cta_rank) * C::B_ROWS;
-              for (int kb = qg % p.kblocks; kb < p.kblocks; kb += p.q_groups) tma_prefetch_l2_2d(&map_s, kb * BK, p_row0);
+            if (pt >= 0 && p.l2_prefetch) {
+              // a tile's rows are contiguous in HBM (it spans every column), so prefetch it as one linear range
+              // in 32 KB pieces: sequential DRAM pages instead of 128-byte column slices
+              const long long row_bytes = (long long)p.kblocks * (BK * 2);
+              const long long r0 = (long long)pt * BN + (long long)cta_rank * C::B_ROWS;
+              long long r1 = r0 + C::B_ROWS;
+              if (r1 > p.n_support) r1 = p.n_support;
+              const long long beg = r0 * row_bytes, end = r1 * row_bytes;
+              constexpr long long PIECE = 32768;
+              for (long long off = beg + (long long)qg * PIECE; off < end; off += (long long)p.q_groups * PIECE) {
+                const long long len = end - off < PIECE ? end - off : PIECE;
+                bulk_prefetch_l2(p.bank + off, uint32_t(len));
+              }
             }
           }
           for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
@@ -392,29 +404,47 @@ __device__ __forceinline__ float logaddexp_f(float a, float b) {
 }
 
 // Apply the chunk-boundary partials in chunk order (fixed order => bitwise reproducible).
-__global__ void merge_side_kernel(float* __restrict__ class_lse, const float* __restrict__ side,
-                                  const int32_t* __restrict__ labels, int n_query, int n_support, int n_classes,
-                                  int chunks, int tiles_per_chunk, int s_tiles) {
+// A class that is cut by a chunk boundary receives ALL of its mass through `side` (never a direct store), and
+// the cut classes appear in non-decreasing order along the chunks, so one thread per query row run-length
+// merges the (class, value) pairs in registers and writes each class once: no read-modify-write chain through
+// global memory, and the loads of different chunks are independent (software pipelined by the unroll).
+__global__ void __launch_bounds__(32) merge_side_kernel(float* __restrict__ class_lse, const float* __restrict__ side,
+                                                        const int32_t* __restrict__ labels, int n_query,
+                                                        int n_support, int n_classes, int chunks,
+                                                        int tiles_per_chunk, int s_tiles) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_query) return;
   float* row = class_lse + size_t(b) * n_classes;
   const float neg_inf = __int_as_float(0xff800000);
+  int cur = -1;
+  float acc = neg_inf;
+#pragma unroll 4
   for (int g = 0; g < chunks; ++g) {
     const int t0 = g * tiles_per_chunk;
     const int t1 = min(t0 + tiles_per_chunk, s_tiles);
     const int n0 = t0 * BN;
     const int n1 = min(t1 * BN, n_support);
-    const float v0 = side[(size_t(g) * n_query + b) * 2 + 0];
-    const float v1 = side[(size_t(g) * n_query + b) * 2 + 1];
-    if (v0 != neg_inf) {
-      const int c = labels[n0];
-      row[c] = logaddexp_f(row[c], v0);
+    const float2 v = *reinterpret_cast<const float2*>(side + (size_t(g) * n_query + b) * 2);
+    const int c0 = __ldg(labels + n0);
+    const int c1 = __ldg(labels + n1 - 1);
+    if (v.x != neg_inf) {
+      if (c0 != cur) {
+        if (cur >= 0) row[cur] = acc;
+        cur = c0;
+        acc = neg_inf;
+      }
+      acc = logaddexp_f(acc, v.x);
     }
-    if (v1 != neg_inf) {
-      const int c = labels[n1 - 1];
-      row[c] = logaddexp_f(row[c], v1);
+    if (v.y != neg_inf) {
+      if (c1 != cur) {
+        if (cur >= 0) row[cur] = acc;
+        cur = c1;
+        acc = neg_inf;
+      }
+      acc = logaddexp_f(acc, v.y);
     }
   }
+  if (cur >= 0) row[cur] = acc;
 }
 
 // logp[b,c] = log(exp(L[b,c] - logsumexp_c L[b,:]) + 1e-12)   (reference nwhead/nw.py:285-289)
@@ -608,6 +638,7 @@ extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf1
   p.q_sqnorm = q_sqnorm;
   p.s_sqnorm = s_sqnorm;
   p.labels = labels;
+  p.bank = static_cast<const uint8_t*>(bank_bf16);
   p.class_lse = class_lse;
   p.side = side;
   p.n_query = n_query;
@@ -619,6 +650,13 @@ extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf1
   p.chunks = plan.chunks;
   p.tiles_per_chunk = plan.tiles_per_chunk;
   p.scale_log2 = scale * kLog2e;
+  {
+    // One-tile-ahead L2 prefetch only pays when few distinct support streams are live (many query groups share
+    // each stream); with one stream per worker the prefetched tiles (148 MB) exceed L2 and the bank would be read
+    // from HBM twice (measured: 9.4 GB instead of 5.0 GB of DRAM reads at B=8).
+    const char* e = getenv("NW_B200_NO_PREFETCH");
+    p.l2_prefetch = (plan.q_tiles >= 8 && !(e && e[0] == '1')) ? 1 : 0;
+  }
 
   if (epilogue == NW_EPI_EUCLID) {
     rc = ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2>(map_q, map_s, p, plan.grid, stream)
@@ -630,7 +668,7 @@ extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf1
   if (rc != NW_OK) return rc;
 
   if (plan.chunks > 1) {
-    k1::merge_side_kernel<<<ceil_div(n_query, 128), 128, 0, stream>>>(class_lse, side, labels, n_query,
+    k1::merge_side_kernel<<<ceil_div(n_query, 32), 32, 0, stream>>>(class_lse, side, labels, n_query,
                                                                       int(n_support), n_classes, plan.chunks,
                                                                       plan.tiles_per_chunk, plan.s_tiles);
     NW_CUDA_OK(cudaGetLastError());

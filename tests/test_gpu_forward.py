@@ -110,3 +110,34 @@ def test_label_errors_raise(cuda_lib):
         SupportBank.build(s, torch.full((40,), 7, device=DEV, dtype=torch.int64), 5)
     with pytest.raises(RuntimeError, match="LongTensor"):
         SupportBank.build(s, torch.zeros(40, device=DEV, dtype=torch.int32), 5)
+
+
+def test_config1_shape(cuda_lib):
+    """BASELINE config 1 head shapes: bank 5800 x 512 (29 per class, 200 classes), batch 8."""
+    q, s, y, _ = clustered_features(200, 29, 512, 8, seed=1)
+    for precision in ("auto", "bf16"):
+        out = run_bank(q, s, y, 200, "euclidean", precision)
+        assert_head_parity(out, O.nw_forward(q, s, y, 200, "euclidean"))
+
+
+def test_random_shapes_against_oracle(cuda_lib):
+    """Seeded sweep over ragged shapes: B around the 128/256-row tile edges (single CTA and CTA pair), N from a
+    handful of rows to several chunks, uneven class sizes with empty classes, d not a multiple of 64."""
+    rng = np.random.default_rng(2026)
+    for trial in range(24):
+        B = int(rng.choice([1, 7, 127, 128, 129, 255, 257, 300, 513]))
+        C = int(rng.integers(2, 60))
+        sizes = rng.integers(0, int(rng.choice([3, 40, 400])) + 1, C)
+        sizes[rng.integers(0, C)] += 26  # at least one non-empty class, N > 25
+        d = int(rng.choice([8, 48, 64, 100, 192, 520]))
+        kind = str(rng.choice(["euclidean", "cosine", "hypersphere_euclidean"]))
+        y = np.repeat(np.arange(C), sizes).astype(np.int64)
+        mu = rng.normal(size=(C, d)) * 1.5
+        s = (mu[y] + rng.normal(size=(len(y), d))).astype(np.float32)
+        q = (mu[rng.integers(0, C, B)] + rng.normal(size=(B, d))).astype(np.float32)
+        out = run_bank(q, s, y, C, kind, "bf16x3").cpu().numpy()
+        ref = O.nw_forward(q, s, y, C, kind)
+        perr = np.abs(np.exp(out) - np.exp(ref)).max()
+        assert perr < 5e-5, (trial, B, len(y), d, C, kind, perr)
+        empty = np.flatnonzero(sizes == 0)
+        assert np.array_equal(out[:, empty], np.full((B, len(empty)), np.log(np.float32(1e-12)), np.float32))

@@ -70,13 +70,11 @@ class SupportSetEval(SupportSet):
         self.full_bank = SupportBank.build(sfeat, sy, self.n_classes, self.kernel_type, self.precision)
 
         # Cluster: n_shot_cluster == 1 -> class means reduced on the GPU from the fp32 features
-        if self.n_shot_cluster == 1:
-            self.cluster_feat, self.cluster_y = class_centroids(
-                sfeat if sfeat.stride(1) == 1 else sfeat.contiguous(), self.full_bank.perm, self.full_bank.offsets,
-                self.n_classes)
-        else:
-            from .utils import compute_clusters
-            self.cluster_feat, self.cluster_y = compute_clusters(sfeat, sy, self.n_shot_cluster)
+        if self.n_shot_cluster != 1:
+            raise NotImplementedError("n_shot_cluster > 1 (host-side KMeans in the reference) is outside the B200 path")
+        self.cluster_feat, self.cluster_y = class_centroids(
+            sfeat if sfeat.stride(1) == 1 else sfeat.contiguous(), self.full_bank.perm, self.full_bank.offsets,
+            self.n_classes)
         self.cluster_bank = SupportBank.build(self.cluster_feat, self.cluster_y, self.n_classes, self.kernel_type,
                                               self.precision)
 

@@ -115,11 +115,14 @@ def compute_clusters(embeddings, labels, n_clusters, closest=False):
     """Cluster-mode support (reference nwhead/utils.py:218-246).
 
     n_clusters == 1 (the NWNet default, nwhead/nw.py:24): KMeans with one cluster is the class mean,
-    computed on the GPU by nw_class_centroids.  n_clusters > 1 keeps scikit-learn on the host, as the
-    reference does (k-means++ / Lloyd parity is unpinned).
+    computed on the GPU by nw_class_centroids.  n_clusters > 1 (k-means++ / Lloyd on the host in the
+    reference, parity unpinned) is not provided.
     Returns (centroids (U*k, d) fp32, labels (U*k,) int64) over the sorted unique labels."""
     if n_clusters != 1 or closest:
-        return _compute_clusters_sklearn(embeddings, labels, n_clusters, closest)
+        raise NotImplementedError(
+            "only n_clusters=1 (the NWNet default: class means, nw_class_centroids) runs on the B200 path; the "
+            "reference's k>1 / closest=True variants are host-side scikit-learn KMeans (nwhead/utils.py:227-241) "
+            "and there is no CPU fallback here")
     dev = _abi.require_cuda(embeddings, labels)
     lib = load()
     feats = embeddings.detach()
@@ -158,29 +161,6 @@ def class_centroids(feats, perm, offsets, n_classes):
     if present.numel() != n_classes:
         out = out.index_select(0, present)
     return out, present.to(torch.int64)
-
-
-def _compute_clusters_sklearn(embeddings, labels, n_clusters, closest):
-    from sklearn.cluster import KMeans
-
-    emb = embeddings.detach().cpu()
-    lab = labels.detach().cpu()
-    ids = np.arange(len(emb))
-    feats, out_labels = [], []
-    for c in np.unique(lab):
-        sel = lab == c
-        emb_c = emb[sel]
-        km = KMeans(n_clusters=n_clusters, random_state=0).fit(emb_c)
-        cent = torch.tensor(km.cluster_centers_).float()
-        out_labels += [c] * n_clusters
-        if closest:
-            nearest = torch.cdist(cent, emb_c).argmin(dim=-1)
-            pick = ids[sel][nearest]
-            feats.append(emb[[pick] if n_clusters == 1 else pick])
-        else:
-            feats.append(cent)
-    return (torch.cat(feats, dim=0).to(embeddings.device),
-            torch.tensor(out_labels).to(embeddings.device))
 
 
 def rank_rows(scores: torch.Tensor, k=None) -> torch.Tensor:

@@ -167,7 +167,8 @@ def nwnet_flow(ref):
     out["ds_x"], out["ds_y"] = ds.x, torch.tensor(ds.targets)
     for kind in ("euclidean", "cosine"):
         net = ref.NWNet(feat, C, support_dataset=ds, feat_dim=16, kernel_type=kind, n_shot=2, n_way=4,
-                        n_shot_random=2, n_shot_full=5, n_shot_cluster=1, device="cpu")
+                        n_shot_random=2, n_shot_full=5, n_shot_cluster=1, n_neighbors=3, device="cpu",
+                        return_mask=False)
         net.eval()
         with torch.no_grad():
             net.precompute()
@@ -183,6 +184,7 @@ def nwnet_flow(ref):
             out[f"{kind}/pred_cluster"] = net.predict(xq, mode="cluster")
             np.random.seed(123)
             out[f"{kind}/pred_random"] = net.predict(xq, mode="random")
+            out[f"{kind}/pred_knn"] = net.predict(xq, mode="knn")   # k nearest of every query, one shared support
             if kind == "euclidean":
                 out[f"{kind}/neighbors"] = net.get_neighbors(xq)
         net.train()

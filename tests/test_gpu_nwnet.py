@@ -28,7 +28,7 @@ def make_net(g, kind):
         feat[1].bias.copy_(torch.from_numpy(g["b"]))
     ds = TinyDataset(g["ds_x"], g["ds_y"])
     net = nwhead_b200.NWNet(feat, 6, support_dataset=ds, feat_dim=16, kernel_type=kind, n_shot=2, n_way=4,
-                            n_shot_random=2, n_shot_full=5, n_shot_cluster=1, device=DEV)
+                            n_shot_random=2, n_shot_full=5, n_shot_cluster=1, n_neighbors=3, device=DEV)
     return net.to(DEV), feat
 
 
@@ -54,8 +54,14 @@ def test_precompute_predict_neighbors(cuda_lib, golden_flow, kind):
         np.random.seed(123)  # same numpy stream as the reference run -> same sampled support
         out = net.predict(xq, mode="random").cpu().numpy()
         assert np.abs(np.exp(out) - np.exp(g[f"{kind}/pred_random"])).max() < 1e-3
+        # knn mode: k nearest bank rows of every query, concatenated into one shared support
+        out = net.predict(xq, mode="knn").cpu().numpy()
+        assert np.abs(np.exp(out) - np.exp(g[f"{kind}/pred_knn"])).max() < 1e-3
         with pytest.raises(NotImplementedError):
             net.predict(xq, mode="bogus")
+        for mode in ("ensemble", "hnsw"):
+            with pytest.raises(NotImplementedError):
+                net.predict(xq, mode=mode)
         if kind == "euclidean":
             nb = net.get_neighbors(xq).cpu().numpy()
             assert nb.shape == g[f"{kind}/neighbors"].shape and nb.dtype == np.int64
@@ -75,3 +81,30 @@ def test_training_step(cuda_lib, golden_flow, kind):
     assert np.abs(logp.detach().cpu().numpy() - g[f"{kind}/train_logp"]).max() < 1e-4
     gw = g[f"{kind}/train_gW"]
     assert np.abs(feat[1].weight.grad.cpu().numpy() - gw).max() < 1e-6 + 2e-4 * np.abs(gw).max()
+
+
+def test_return_mask_and_functional_support(cuda_lib, golden_flow):
+    import nwhead_b200
+
+    g = golden_flow
+    net, feat = make_net(g, "euclidean")
+    net.return_mask = True
+    net.train()
+    x, y = torch.from_numpy(g["xq"][:4]).to(DEV), torch.from_numpy(g["yq"][:4]).to(DEV)
+    sx = torch.from_numpy(g["ds_x"][:12]).to(DEV)
+    sy = torch.from_numpy(g["ds_y"][:12]).to(DEV)
+    logp, mask = net(x, y, support_data=(sx, sy, None))
+    assert logp.shape == (4, 6) and mask.dtype == torch.bool
+    assert torch.equal(mask, torch.isin(y, sy))
+    logp.sum().backward()
+    assert feat[1].weight.grad is not None and torch.isfinite(feat[1].weight.grad).all()
+    # the same support through the plain head gives the same numbers
+    with torch.no_grad():
+        f = feat(torch.cat((x, sx)))
+        ref = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), 6)(f[:4], f[4:], sy)
+    assert torch.allclose(ref, logp.detach(), atol=1e-6)
+    net.eval()
+    with torch.no_grad():
+        net.precompute()
+        out, m = net.predict(x, mode="full")
+    assert m.all() and out.shape == (4, 6)

@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: in-kernel NVLink peer stores + signal barrier, or one NCCL all-reduce(MAX)")
     return ap.parse_args()
 
 
@@ -223,7 +225,7 @@ def main():
     import nwhead_b200
     from nwhead_b200 import SupportBank, _abi
     from nwhead_b200.bank import logp_from_class_lse
-    from nwhead_b200.dist import class_range, merge_class_lse
+    from nwhead_b200.dist import ShardedBank, class_range
 
     _abi.check(_abi.load().nw_device_check(), "nw_device_check")
     B, N, d, C = args.batch, args.n_support, args.dim, args.classes
@@ -240,20 +242,29 @@ def main():
     center = (center / N).float().contiguous()  # global centre: every shard rounds exactly like the 1-GPU bank
     bank = SupportBank.build(feats, labels, C, "euclidean", args.precision, center=center)
     del feats
-    head = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), C)
+    sharded = ShardedBank(bank, exchange=args.exchange, max_batch=B)
     q_dev, qy = synth_queries(mu, B, dev)
     q_host = q_dev.cpu().pin_memory()
     torch.cuda.synchronize()
     plan = _abi.forward_plan(B, len(bank))
+
+    from nwhead_b200.dist import merge_class_lse as sharded_merge
 
     def step_resident():
         qb, qs = bank.prepare_queries(q_dev)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        lse = bank.class_lse_prepared(qb, qs)
-        e1.record()
-        lse = merge_class_lse(lse)
+        if sharded.peer is None:
+            lse = bank.class_lse_prepared(qb, qs)
+            e1.record()
+            lse = sharded_merge(lse)
+        else:
+            table, hdl, ptrs, ch = sharded.peer.next()
+            bank.class_lse_prepared(qb, qs, tables=ptrs)
+            e1.record()
+            hdl.barrier(channel=ch)
+            lse = table[:B]
         return logp_from_class_lse(lse), (e0, e1)
 
     # end-to-end arm: the public serving API.  Every step uploads the step's queries from pinned host memory
@@ -261,7 +272,7 @@ def main():
     # ranks all-gather the queries over NVLink.  Copies are double-buffered against the fused forward.
     rows = B // world
     assert rows * world == B
-    predictor = nwhead_b200.FullModePredictor(bank, rows)
+    predictor = nwhead_b200.FullModePredictor(sharded, rows)
     q_host_slice = q_host[rank * rows:(rank + 1) * rows].clone().pin_memory()
 
     def run_e2e(n_steps):
@@ -345,6 +356,8 @@ def main():
                 "workload": f"NWHead full-mode inference: support N={N} d={d} C={C}, query batch B={B}, euclidean, "
                             f"bank sharded class-aligned over {world} GPU(s)",
                 "precision": args.precision, "parallelism": f"bank-shard x{world}" if world > 1 else "single",
+                "exchange": ("none" if world == 1 else "in-kernel NVLink peer stores + signal barrier"
+                             if sharded.peer is not None else "one NCCL all-reduce(MAX)"),
                 "l2": "inputs larger than L2: the bf16 bank shard streamed every step is "
                       f"{bank.feats_bf16.numel() * 2 / 1e9:.2f} GB",
                 "plan": {"chunks": plan.chunks, "tiles_per_chunk": plan.tiles_per_chunk, "grid": plan.grid},

@@ -183,15 +183,26 @@ class SupportBank:
         q_bf16, q_sq = self.prepare_queries(q)
         return self.class_lse_prepared(q_bf16, q_sq, scale)
 
-    def class_lse_prepared(self, q_bf16: torch.Tensor, q_sq: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    def class_lse_prepared(self, q_bf16: torch.Tensor, q_sq: torch.Tensor, scale: float = 1.0, tables=None):
+        """tables=None: returns a fresh (B, C) table.  tables=ctypes array of device pointers ([0] local, then
+        the peer GPUs' tables): results are stored into all of them (nw_forward_class_lse_peers), returns None."""
         lib = load()
         b = q_bf16.shape[0]
         n = len(self)
         plan = _abi.forward_plan(b, n)
         dev = self.device
-        out = torch.empty((b, self.n_classes), dtype=torch.float32, device=dev)
         side = torch.empty((max(int(plan.side_elems), 1),), dtype=torch.float32, device=dev)
         epi = _abi.EPI_EUCLID if self.kind in EUCLID_KINDS else _abi.EPI_LINEAR
+        if tables is not None:
+            check(
+                lib.nw_forward_class_lse_peers(epi, float(scale), ptr(q_bf16), ptr(q_sq), b, ptr(self.feats_bf16),
+                                               ptr(self.sqnorm), ptr(self.labels), n, self.row_elems,
+                                               self.n_classes, tables, len(tables), ptr(side), side.numel(),
+                                               stream_of(dev)),
+                "nw_forward_class_lse_peers",
+            )
+            return None
+        out = torch.empty((b, self.n_classes), dtype=torch.float32, device=dev)
         check(
             lib.nw_forward_class_lse(epi, float(scale), ptr(q_bf16), ptr(q_sq), b, ptr(self.feats_bf16),
                                      ptr(self.sqnorm), ptr(self.labels), n, self.row_elems, self.n_classes,

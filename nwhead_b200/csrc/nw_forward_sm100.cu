@@ -35,6 +35,7 @@ constexpr int A_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 128;
+constexpr int NW_MAX_PEERS = 16;
 
 // NCTA = 1: one CTA computes a 128 x 256 tile (UMMA M=128).
 // NCTA = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x 256 tile (UMMA M=256); each CTA stages
@@ -72,7 +73,8 @@ struct Params {
   const float* s_sqnorm;
   const int32_t* labels;
   const uint8_t* bank;  // bf16 bank base (for linear L2 prefetch); row pitch = kblocks * 128 bytes
-  float* class_lse;
+  float* lse[NW_MAX_PEERS];  // class-LSE tables the results are stored to: [0] local, [1..] peer GPUs (NVLink P2P)
+  int n_tables;
   float* side;
   int n_query;
   int n_support;
@@ -87,16 +89,23 @@ struct Params {
 };
 
 struct Flusher {
-  float* class_lse_row;  // class_lse + row * C
-  float* side_row;       // side + (chunk * B + row) * 2
+  const Params* p;
+  size_t row_off;   // row * C
+  float* side_row;  // side + (chunk * B + row) * 2
   int cf, cl;
   bool head_cut, tail_cut, row_valid;
+  // Rare path (once per class per row), kept out of line so the unrolled column loop stays compact.
+  // A class that lies completely inside this unit is final: store it to the local table AND to every peer
+  // GPU's table (bank-sharded predict: the all-gather of class columns happens here, tile by tile, as NVLink
+  // peer stores that overlap the MMAs).  Classes cut by a chunk boundary go through `side`.
   __device__ __noinline__ void operator()(int cls, float m, float l) const {
     const float v = (m + lg2_approx(l)) * kLn2;
     if (!row_valid) return;
     if (cls == cf && head_cut) side_row[0] = v;
     else if (cls == cl && tail_cut) side_row[1] = v;
-    else class_lse_row[cls] = v;
+    else {
+      for (int r = 0; r < p->n_tables; ++r) p->lse[r][row_off + cls] = v;
+    }
   }
 };
 
@@ -152,7 +161,7 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
 template <int EPI, int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_s,
-                  const Params p) {
+                  const __grid_constant__ Params p) {
   using C = Cfg<NCTA>;
   constexpr int STAGES = C::STAGES;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
@@ -324,7 +333,8 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       flush.head_cut = n0 > 0 && __ldg(p.labels + n0 - 1) == flush.cf;
       flush.tail_cut = n1 < p.n_support && __ldg(p.labels + n1) == flush.cl;
       const int srow = flush.row_valid ? row : 0;
-      flush.class_lse_row = p.class_lse + size_t(srow) * p.n_classes;
+      flush.p = &p;
+      flush.row_off = size_t(srow) * p.n_classes;
       flush.side_row = p.side + (size_t(g) * p.n_query + srow) * 2;
       const float qn = (EPI == NW_EPI_EUCLID && flush.row_valid) ? __ldg(p.q_sqnorm + row) : 0.0f;
 
@@ -408,16 +418,24 @@ __device__ __forceinline__ float logaddexp_f(float a, float b) {
 // the cut classes appear in non-decreasing order along the chunks, so one thread per query row run-length
 // merges the (class, value) pairs in registers and writes each class once: no read-modify-write chain through
 // global memory, and the loads of different chunks are independent (software pipelined by the unroll).
-__global__ void __launch_bounds__(32) merge_side_kernel(float* __restrict__ class_lse, const float* __restrict__ side,
+struct TableList {
+  float* t[NW_MAX_PEERS];
+  int n;
+};
+
+__global__ void __launch_bounds__(32) merge_side_kernel(const TableList tables, const float* __restrict__ side,
                                                         const int32_t* __restrict__ labels, int n_query,
                                                         int n_support, int n_classes, int chunks,
                                                         int tiles_per_chunk, int s_tiles) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_query) return;
-  float* row = class_lse + size_t(b) * n_classes;
+  const size_t row_off = size_t(b) * n_classes;
   const float neg_inf = __int_as_float(0xff800000);
   int cur = -1;
   float acc = neg_inf;
+  auto put = [&](int cls, float v) {
+    for (int r = 0; r < tables.n; ++r) tables.t[r][row_off + cls] = v;
+  };
 #pragma unroll 4
   for (int g = 0; g < chunks; ++g) {
     const int t0 = g * tiles_per_chunk;
@@ -429,7 +447,7 @@ __global__ void __launch_bounds__(32) merge_side_kernel(float* __restrict__ clas
     const int c1 = __ldg(labels + n1 - 1);
     if (v.x != neg_inf) {
       if (c0 != cur) {
-        if (cur >= 0) row[cur] = acc;
+        if (cur >= 0) put(cur, acc);
         cur = c0;
         acc = neg_inf;
       }
@@ -437,14 +455,14 @@ __global__ void __launch_bounds__(32) merge_side_kernel(float* __restrict__ clas
     }
     if (v.y != neg_inf) {
       if (c1 != cur) {
-        if (cur >= 0) row[cur] = acc;
+        if (cur >= 0) put(cur, acc);
         cur = c1;
         acc = neg_inf;
       }
       acc = logaddexp_f(acc, v.y);
     }
   }
-  if (cur >= 0) row[cur] = acc;
+  if (cur >= 0) put(cur, acc);
 }
 
 // logp[b,c] = log(exp(L[b,c] - logsumexp_c L[b,:]) + 1e-12)   (reference nwhead/nw.py:285-289)
@@ -602,13 +620,15 @@ static int launch_forward(const CUtensorMap& map_q, const CUtensorMap& map_s, co
 }  // namespace k1
 }  // namespace nw
 
-extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm,
-                                    int n_query, const void* bank_bf16, const float* s_sqnorm,
-                                    const int32_t* labels, int64_t n_support, int row_elems, int n_classes,
-                                    float* class_lse, float* side, int64_t side_elems, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int forward_impl(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
+                        const void* bank_bf16, const float* s_sqnorm, const int32_t* labels, int64_t n_support,
+                        int row_elems, int n_classes, float* const* tables, int n_tables, bool fill_local,
+                        float* side, int64_t side_elems, cudaStream_t stream) {
   NW_REQUIRE(epilogue == NW_EPI_EUCLID || epilogue == NW_EPI_LINEAR, NW_ERR_INVALID, "unknown epilogue %d", epilogue);
-  NW_REQUIRE(q_bf16 && bank_bf16 && labels && class_lse && side, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(q_bf16 && bank_bf16 && labels && tables && side, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n_tables >= 1 && n_tables <= k1::NW_MAX_PEERS, NW_ERR_INVALID, "n_tables must be in [1, %d]",
+             k1::NW_MAX_PEERS);
+  for (int r = 0; r < n_tables; ++r) NW_REQUIRE(tables[r] != nullptr, NW_ERR_INVALID, "NULL class-LSE table %d", r);
   NW_REQUIRE(epilogue != NW_EPI_EUCLID || (q_sqnorm && s_sqnorm), NW_ERR_INVALID,
              "the euclidean epilogue needs q_sqnorm and s_sqnorm");
   NW_REQUIRE(row_elems > 0 && row_elems % k1::BK == 0, NW_ERR_INVALID, "row_elems must be a positive multiple of 64");
@@ -630,7 +650,7 @@ extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf1
   rc = k1::make_map(&map_s, bank_bf16, uint64_t(n_support), uint64_t(row_elems), k1::BN / ncta);
   if (rc != NW_OK) return rc;
 
-  k1::fill_kernel<<<sm_count() * 4, 256, 0, stream>>>(class_lse, (long long)n_query * n_classes, side,
+  k1::fill_kernel<<<sm_count() * 4, 256, 0, stream>>>(tables[0], fill_local ? (long long)n_query * n_classes : 0, side,
                                                       (long long)plan.side_elems, -INFINITY);
   NW_CUDA_OK(cudaGetLastError());
 
@@ -639,7 +659,9 @@ extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf1
   p.s_sqnorm = s_sqnorm;
   p.labels = labels;
   p.bank = static_cast<const uint8_t*>(bank_bf16);
-  p.class_lse = class_lse;
+  k1::TableList tl;
+  for (int r = 0; r < k1::NW_MAX_PEERS; ++r) p.lse[r] = tl.t[r] = (r < n_tables ? tables[r] : nullptr);
+  p.n_tables = tl.n = n_tables;
   p.side = side;
   p.n_query = n_query;
   p.n_support = int(n_support);
@@ -668,12 +690,32 @@ extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf1
   if (rc != NW_OK) return rc;
 
   if (plan.chunks > 1) {
-    k1::merge_side_kernel<<<ceil_div(n_query, 32), 32, 0, stream>>>(class_lse, side, labels, n_query,
-                                                                      int(n_support), n_classes, plan.chunks,
-                                                                      plan.tiles_per_chunk, plan.s_tiles);
+    k1::merge_side_kernel<<<ceil_div(n_query, 32), 32, 0, stream>>>(tl, side, labels, n_query, int(n_support),
+                                                                    n_classes, plan.chunks, plan.tiles_per_chunk,
+                                                                    plan.s_tiles);
     NW_CUDA_OK(cudaGetLastError());
   }
   return NW_OK;
+}
+
+extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm,
+                                    int n_query, const void* bank_bf16, const float* s_sqnorm,
+                                    const int32_t* labels, int64_t n_support, int row_elems, int n_classes,
+                                    float* class_lse, float* side, int64_t side_elems, void* stream_) {
+  NW_REQUIRE(class_lse != nullptr, NW_ERR_INVALID, "NULL pointer argument");
+  float* tables[1] = {class_lse};
+  return forward_impl(epilogue, scale, q_bf16, q_sqnorm, n_query, bank_bf16, s_sqnorm, labels, n_support, row_elems,
+                      n_classes, tables, 1, /*fill_local=*/true, side, side_elems, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int nw_forward_class_lse_peers(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm,
+                                          int n_query, const void* bank_bf16, const float* s_sqnorm,
+                                          const int32_t* labels, int64_t n_support, int row_elems, int n_classes,
+                                          float* const* tables_host, int n_tables, float* side, int64_t side_elems,
+                                          void* stream_) {
+  return forward_impl(epilogue, scale, q_bf16, q_sqnorm, n_query, bank_bf16, s_sqnorm, labels, n_support, row_elems,
+                      n_classes, tables_host, n_tables, /*fill_local=*/false, side, side_elems,
+                      static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int nw_logp_from_class_lse(const float* class_lse, int n_query, int n_classes, float* logp,

@@ -9,6 +9,8 @@ then finalises log(P + 1e-12) locally.
 
 `merge_class_lse` is backend-agnostic (NCCL on GPUs, gloo in the CPU tests of the host logic).
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -38,21 +40,77 @@ def merge_class_lse(partial: torch.Tensor, group=None, class_aligned: bool = Tru
     return partial
 
 
-class ShardedBank:
-    """This rank's class-aligned shard of a support bank + the merged forward."""
+class PeerTables:
+    """Double-buffered (max_batch, C) class-LSE tables in symmetric memory (one per rank, peer-mapped over
+    NVLink).  The fused forward stores every class-LSE entry its shard owns into ALL ranks' tables from the
+    epilogue (nw_forward_class_lse_peers), so the exchange overlaps the MMAs and no all-reduce is launched; a
+    signal-pad barrier on the stream separates the writes from the local finalise.
 
-    def __init__(self, shard, group=None):
+    Hazards: step i writes table i%2 everywhere, then barrier_i, then every rank reads only its own table i%2.
+    Table i%2 is written again at step i+2, which a rank can only start after barrier_{i+1} — and every rank
+    enqueues barrier_{i+1} after its finalise of step i.  Entries of classes no shard owns keep the -inf the
+    tables are created with; every owned entry is overwritten on each step."""
+
+    def __init__(self, max_batch: int, n_classes: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.max_batch, self.n_classes = max_batch, n_classes
+        self.tables, self.handles, self.ptr_arrays = [], [], []
+        rank = dist.get_rank(self.group)
+        for _ in range(2):
+            t = symm_mem.empty((max_batch, n_classes), dtype=torch.float32, device=device)
+            t.fill_(float("-inf"))
+            hdl = symm_mem.rendezvous(t, self.group.group_name)
+            ptrs = list(hdl.buffer_ptrs)
+            order = [ptrs[rank]] + [p for r, p in enumerate(ptrs) if r != rank]  # [0] must be the local table
+            self.tables.append(t)
+            self.handles.append(hdl)
+            self.ptr_arrays.append((ctypes.c_void_p * len(order))(*order))
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)  # every table is -inf before any peer may store into it
+        self.step = 0
+
+    def next(self):
+        i = self.step % 2
+        self.step += 1
+        return self.tables[i], self.handles[i], self.ptr_arrays[i], i
+
+
+class ShardedBank:
+    """This rank's class-aligned shard of a support bank + the merged forward.
+
+    exchange='nccl'  : local table + ONE all-reduce(MAX) (works everywhere).
+    exchange='peer'  : in-kernel NVLink peer stores into every rank's table + a signal barrier (PeerTables)."""
+
+    def __init__(self, shard, group=None, exchange="nccl", max_batch=0):
         self.shard = shard
         self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.peer = None
+        if exchange == "peer" and self.world > 1:
+            self.peer = PeerTables(max_batch, shard.n_classes, shard.device, group)
+        elif exchange not in ("nccl", "peer"):
+            raise ValueError(f"unknown exchange {exchange!r}")
 
     @staticmethod
-    def from_full(bank, group=None):
+    def from_full(bank, group=None, exchange="nccl", max_batch=0):
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         world = dist.get_world_size(group) if dist.is_initialized() else 1
-        return ShardedBank(bank.class_shard(rank, world) if world > 1 else bank, group)
+        return ShardedBank(bank.class_shard(rank, world) if world > 1 else bank, group, exchange, max_batch)
 
     def class_lse(self, q, scale: float = 1.0):
-        return merge_class_lse(self.shard.class_lse(q, scale), self.group)
+        """(B, C) class log-sum-exp over the WHOLE bank, identical on every rank."""
+        if self.peer is None:
+            return merge_class_lse(self.shard.class_lse(q, scale), self.group)
+        b = q.shape[0]
+        if b > self.peer.max_batch:
+            raise ValueError(f"batch {b} exceeds the peer tables' max_batch {self.peer.max_batch}")
+        table, hdl, ptrs, ch = self.peer.next()
+        q_bf16, q_sq = self.shard.prepare_queries(q)
+        self.shard.class_lse_prepared(q_bf16, q_sq, scale, tables=ptrs)
+        hdl.barrier(channel=ch)  # all ranks' peer stores have landed (kernel completion + signal exchange)
+        return table[:b]
 
     def forward(self, q, scale: float = 1.0):
         from .bank import logp_from_class_lse

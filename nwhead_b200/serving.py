@@ -31,11 +31,16 @@ class _Slot:
 class FullModePredictor:
     """predict(mode='full') for feature batches in host memory.
 
-    bank : SupportBank (whole bank, world size 1) or this rank's class-aligned shard.
+    bank : SupportBank (whole bank, world size 1), this rank's class-aligned shard, or a dist.ShardedBank
+           (which also selects the exchange: NCCL all-reduce or in-kernel NVLink peer stores).
     rows : rows of the query batch THIS rank uploads / returns per call (B, or B / world_size).
     """
 
-    def __init__(self, bank: SupportBank, rows: int, group=None, depth: int = 2, scale: float = 1.0):
+    def __init__(self, bank, rows: int, group=None, depth: int = 2, scale: float = 1.0):
+        from .dist import ShardedBank
+
+        self.sharded = bank if isinstance(bank, ShardedBank) else ShardedBank(bank, group)
+        bank = self.sharded.shard
         self.bank, self.group, self.scale = bank, group, scale
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -65,7 +70,7 @@ class FullModePredictor:
         compute.wait_event(slot.h2d_done)
         if self.world > 1:
             dist.all_gather_into_tensor(slot.q_full, slot.q_slice, group=self.group)
-        lse = merge_class_lse(self.bank.class_lse(slot.q_full, self.scale), self.group)
+        lse = self.sharded.class_lse(slot.q_full, self.scale)
         mine = lse[self.rank * self.rows:(self.rank + 1) * self.rows] if self.world > 1 else lse
         logp_from_class_lse(mine, out=slot.logp)
         slot.compute_done.record(compute)

@@ -53,13 +53,17 @@ def _worker(rank, world, port, ret):
     q, s, y, _ = clustered_features(30, 100, 128, 256, seed=3)
     full = nwhead_b200.SupportBank.build(torch.from_numpy(s).to(dev), torch.from_numpy(y).to(dev), 30, "euclidean", "bf16")
     want = full.forward(torch.from_numpy(q).to(dev))
-    sharded = ShardedBank.from_full(full)
-    got = sharded.forward(torch.from_numpy(q).to(dev))
-    ok = (got - want).abs().max().item() < 2e-5
+    ok = True
     rows = 256 // world
-    pred = nwhead_b200.FullModePredictor(sharded.shard, rows=rows)
-    mine = pred(torch.from_numpy(q[rank * rows:(rank + 1) * rows]).pin_memory())
-    ok = ok and (mine.to(dev) - want[rank * rows:(rank + 1) * rows]).abs().max().item() < 2e-5
+    for exchange in ("nccl", "peer"):  # one all-reduce(MAX) vs in-kernel NVLink peer stores + signal barrier
+        sharded = ShardedBank.from_full(full, exchange=exchange, max_batch=256)
+        for _ in range(3):  # several steps: exercises the double-buffered peer tables
+            got = sharded.forward(torch.from_numpy(q).to(dev))
+            ok = ok and (got - want).abs().max().item() < 2e-5
+        pred = nwhead_b200.FullModePredictor(sharded, rows=rows)
+        for _ in range(3):
+            mine = pred(torch.from_numpy(q[rank * rows:(rank + 1) * rows]).pin_memory())
+            ok = ok and (mine.to(dev) - want[rank * rows:(rank + 1) * rows]).abs().max().item() < 2e-5
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -242,7 +242,12 @@ def main():
     center = (center / N).float().contiguous()  # global centre: every shard rounds exactly like the 1-GPU bank
     bank = SupportBank.build(feats, labels, C, "euclidean", args.precision, center=center)
     del feats
-    sharded = ShardedBank(bank, exchange=args.exchange, max_batch=B)
+    try:
+        sharded = ShardedBank(bank, exchange=args.exchange, max_batch=B)
+    except Exception as e:  # symmetric memory unavailable on this box: fall back to the NCCL all-reduce
+        if rank == 0:
+            print(f"bench: peer exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+        sharded = ShardedBank(bank, exchange="nccl")
     q_dev, qy = synth_queries(mu, B, dev)
     q_host = q_dev.cpu().pin_memory()
     torch.cuda.synchronize()
@@ -250,28 +255,30 @@ def main():
 
     from nwhead_b200.dist import merge_class_lse as sharded_merge
 
+    rows = B // world
+    assert rows * world == B, "batch must be a multiple of the number of GPUs"
+
     def step_resident():
         qb, qs = bank.prepare_queries(q_dev)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
+        # every rank finalises its own B/R rows of the merged table (the results stay sharded across ranks)
         if sharded.peer is None:
             lse = bank.class_lse_prepared(qb, qs)
             e1.record()
-            lse = sharded_merge(lse)
+            lse = sharded_merge(lse)[rank * rows:(rank + 1) * rows]
         else:
             table, hdl, ptrs, ch = sharded.peer.next()
-            bank.class_lse_prepared(qb, qs, tables=ptrs)
+            bank.class_lse_prepared(qb, qs, tables=ptrs, rows_per_table=rows)
             e1.record()
             hdl.barrier(channel=ch)
-            lse = table[:B]
+            lse = table[rank * rows:(rank + 1) * rows]
         return logp_from_class_lse(lse), (e0, e1)
 
     # end-to-end arm: the public serving API.  Every step uploads the step's queries from pinned host memory
     # and reads the step's (rows, C) log-probs back; rank r moves rows [r*B/R, (r+1)*B/R) over PCIe and the
     # ranks all-gather the queries over NVLink.  Copies are double-buffered against the fused forward.
-    rows = B // world
-    assert rows * world == B
     predictor = nwhead_b200.FullModePredictor(sharded, rows)
     q_host_slice = q_host[rank * rows:(rank + 1) * rows].clone().pin_memory()
 
@@ -318,7 +325,7 @@ def main():
     windows.append((w0, time.time()))
     total_ms = max_over_ranks(s0.elapsed_time(s1))
     kern_ms = max_over_ranks(statistics.mean(a.elapsed_time(b) for a, b in kernel_events))
-    top1 = (logp.argmax(1) == qy).float().mean().item()
+    top1 = (logp.argmax(1) == qy[rank * rows:(rank + 1) * rows]).float().mean().item()
     psum = logp.exp().sum(1).mean().item()
 
     # ---- end to end through the public API with host buffers
@@ -356,7 +363,7 @@ def main():
                 "workload": f"NWHead full-mode inference: support N={N} d={d} C={C}, query batch B={B}, euclidean, "
                             f"bank sharded class-aligned over {world} GPU(s)",
                 "precision": args.precision, "parallelism": f"bank-shard x{world}" if world > 1 else "single",
-                "exchange": ("none" if world == 1 else "in-kernel NVLink peer stores + signal barrier"
+                "exchange": ("none" if world == 1 else "in-kernel NVLink peer stores (all-to-all by query row) + signal barrier"
                              if sharded.peer is not None else "one NCCL all-reduce(MAX)"),
                 "l2": "inputs larger than L2: the bf16 bank shard streamed every step is "
                       f"{bank.feats_bf16.numel() * 2 / 1e9:.2f} GB",

@@ -127,16 +127,19 @@ NW_API int nw_forward_class_lse(int epilogue, float scale, const void* q_bf16, c
                          void* stream);
 
 /* Bank-sharded variant with the exchange fused into the kernel (new; the reference has no multi-GPU code).
- * tables_host: HOST array of n_tables DEVICE pointers to (B, C) class-LSE tables — [0] this GPU's table, the
- * others the peer GPUs' tables mapped into this process (NVLink P2P / symmetric memory).  Every class-LSE entry
- * this shard owns is stored to ALL tables from the epilogue (peer stores overlap the MMAs), which replaces the
- * all-reduce; the caller only needs a cross-GPU barrier before reading its table.  Tables are NOT cleared by this
- * call: fill them with -inf once; classes owned by no shard then stay -inf, and every class must be owned by
- * exactly one shard (class-aligned sharding). */
+ * tables_host: HOST array of n_tables DEVICE pointers to (B, C) class-LSE tables, one per rank in rank order —
+ * this GPU's own table and the peer GPUs' tables mapped into this process (NVLink P2P / symmetric memory).
+ * Every class-LSE entry this shard owns is stored from the epilogue (peer stores overlap the MMAs):
+ *   rows_per_table == 0 : to ALL tables            (all-gather: every rank ends with the whole table)
+ *   rows_per_table  > 0 : to table[row / rows_per_table] only (all-to-all: rank r ends with complete rows
+ *                         [r*rows_per_table, (r+1)*rows_per_table) and finalises / returns just those).
+ * This replaces the all-reduce; the caller only needs a cross-GPU barrier before reading its table.  Tables are
+ * NOT cleared by this call: fill them with -inf once; classes owned by no shard then stay -inf, and every class
+ * must be owned by exactly one shard (class-aligned sharding). */
 NW_API int nw_forward_class_lse_peers(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm,
                                int n_query, const void* bank_bf16, const float* s_sqnorm, const int32_t* labels,
                                int64_t n_support, int row_elems, int n_classes, float* const* tables_host,
-                               int n_tables, float* side, int64_t side_elems, void* stream);
+                               int n_tables, int rows_per_table, float* side, int64_t side_elems, void* stream);
 
 /* logp[b, c] = log( exp(class_lse[b,c] - logsumexp_c class_lse[b,:]) + 1e-12 )  (nwhead/nw.py:285-289).
  * With a sharded bank, all-reduce class_lse with MAX across ranks first (each class is owned by one

@@ -53,8 +53,8 @@ SIGNATURES = {
     "nw_forward_class_lse": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                      c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "nw_forward_class_lse_peers": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                           c_int64, c_int, c_int, POINTER(c_void_p), c_int, c_void_p, c_int64,
-                                           c_void_p]),
+                                           c_int64, c_int, c_int, POINTER(c_void_p), c_int, c_int, c_void_p,
+                                           c_int64, c_void_p]),
     "nw_logp_from_class_lse": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "nw_class_lse_merge": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "nw_direct_scores": (c_int, [c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p,

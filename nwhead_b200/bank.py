@@ -165,6 +165,32 @@ class SupportBank:
                            self.center, self.kind, self.precision, self.d, self.n_classes)
 
     # ------------------------------------------------------------------------------------------
+    _FIELDS = ("feats_bf16", "sqnorm", "labels", "offsets", "perm", "center")
+
+    def state_dict(self) -> dict:
+        """Everything needed to serve from this bank again without the fp32 features or the featurizer
+        (the reference rebuilds its bank on every precompute(), nwhead/nw.py:118-125)."""
+        d = {k: getattr(self, k) for k in self._FIELDS}
+        d.update(kind=self.kind, precision=self.precision, d=self.d, n_classes=self.n_classes, layout_version=1)
+        return d
+
+    @staticmethod
+    def from_state_dict(state: dict, device=None) -> "SupportBank":
+        if state.get("layout_version") != 1:
+            raise ValueError("unknown SupportBank layout version")
+        t = {k: (None if state[k] is None else state[k].to(device or state[k].device).contiguous())
+             for k in SupportBank._FIELDS}
+        return SupportBank(t["feats_bf16"], t["sqnorm"], t["labels"], t["offsets"], t["perm"], t["center"],
+                           state["kind"], state["precision"], state["d"], state["n_classes"])
+
+    def save(self, path: str) -> None:
+        torch.save({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in self.state_dict().items()}, path)
+
+    @staticmethod
+    def load(path: str, device="cuda:0") -> "SupportBank":
+        return SupportBank.from_state_dict(torch.load(path, map_location="cpu"), device)
+
+    # ------------------------------------------------------------------------------------------
     def prepare_queries(self, q: torch.Tensor):
         """fp32 queries -> (bf16 rows in the query layout, squared norms), centred / normalised like the bank."""
         if q.dtype != torch.float32:
@@ -183,9 +209,11 @@ class SupportBank:
         q_bf16, q_sq = self.prepare_queries(q)
         return self.class_lse_prepared(q_bf16, q_sq, scale)
 
-    def class_lse_prepared(self, q_bf16: torch.Tensor, q_sq: torch.Tensor, scale: float = 1.0, tables=None):
-        """tables=None: returns a fresh (B, C) table.  tables=ctypes array of device pointers ([0] local, then
-        the peer GPUs' tables): results are stored into all of them (nw_forward_class_lse_peers), returns None."""
+    def class_lse_prepared(self, q_bf16: torch.Tensor, q_sq: torch.Tensor, scale: float = 1.0, tables=None,
+                           rows_per_table: int = 0):
+        """tables=None: returns a fresh (B, C) table.  tables=ctypes array of device pointers (one table per
+        rank, in rank order): results are stored into all of them, or with rows_per_table > 0 only into the
+        table that owns the row (nw_forward_class_lse_peers); returns None."""
         lib = load()
         b = q_bf16.shape[0]
         n = len(self)
@@ -197,8 +225,8 @@ class SupportBank:
             check(
                 lib.nw_forward_class_lse_peers(epi, float(scale), ptr(q_bf16), ptr(q_sq), b, ptr(self.feats_bf16),
                                                ptr(self.sqnorm), ptr(self.labels), n, self.row_elems,
-                                               self.n_classes, tables, len(tables), ptr(side), side.numel(),
-                                               stream_of(dev)),
+                                               self.n_classes, tables, len(tables), int(rows_per_table), ptr(side),
+                                               side.numel(), stream_of(dev)),
                 "nw_forward_class_lse_peers",
             )
             return None

@@ -73,8 +73,9 @@ struct Params {
   const float* s_sqnorm;
   const int32_t* labels;
   const uint8_t* bank;  // bf16 bank base (for linear L2 prefetch); row pitch = kblocks * 128 bytes
-  float* lse[NW_MAX_PEERS];  // class-LSE tables the results are stored to: [0] local, [1..] peer GPUs (NVLink P2P)
+  float* lse[NW_MAX_PEERS];  // class-LSE tables the results are stored to (local + peer GPUs over NVLink P2P)
   int n_tables;
+  int rows_per_table;  // 0: store every entry to ALL tables; > 0: only to table[row / rows_per_table]
   float* side;
   int n_query;
   int n_support;
@@ -103,10 +104,12 @@ struct Flusher {
     if (!row_valid) return;
     if (cls == cf && head_cut) side_row[0] = v;
     else if (cls == cl && tail_cut) side_row[1] = v;
+    else if (p->rows_per_table > 0) p->lse[row / p->rows_per_table][row_off + cls] = v;
     else {
       for (int r = 0; r < p->n_tables; ++r) p->lse[r][row_off + cls] = v;
     }
   }
+  int row;
 };
 
 // One 32-column chunk of the accumulator for one query row.
@@ -334,6 +337,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       flush.tail_cut = n1 < p.n_support && __ldg(p.labels + n1) == flush.cl;
       const int srow = flush.row_valid ? row : 0;
       flush.p = &p;
+      flush.row = srow;
       flush.row_off = size_t(srow) * p.n_classes;
       flush.side_row = p.side + (size_t(g) * p.n_query + srow) * 2;
       const float qn = (EPI == NW_EPI_EUCLID && flush.row_valid) ? __ldg(p.q_sqnorm + row) : 0.0f;
@@ -421,6 +425,7 @@ __device__ __forceinline__ float logaddexp_f(float a, float b) {
 struct TableList {
   float* t[NW_MAX_PEERS];
   int n;
+  int rows_per_table;
 };
 
 __global__ void __launch_bounds__(32) merge_side_kernel(const TableList tables, const float* __restrict__ side,
@@ -434,7 +439,9 @@ __global__ void __launch_bounds__(32) merge_side_kernel(const TableList tables, 
   int cur = -1;
   float acc = neg_inf;
   auto put = [&](int cls, float v) {
-    for (int r = 0; r < tables.n; ++r) tables.t[r][row_off + cls] = v;
+    if (tables.rows_per_table > 0) tables.t[b / tables.rows_per_table][row_off + cls] = v;
+    else
+      for (int r = 0; r < tables.n; ++r) tables.t[r][row_off + cls] = v;
   };
 #pragma unroll 4
   for (int g = 0; g < chunks; ++g) {
@@ -622,13 +629,15 @@ static int launch_forward(const CUtensorMap& map_q, const CUtensorMap& map_s, co
 
 static int forward_impl(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
                         const void* bank_bf16, const float* s_sqnorm, const int32_t* labels, int64_t n_support,
-                        int row_elems, int n_classes, float* const* tables, int n_tables, bool fill_local,
-                        float* side, int64_t side_elems, cudaStream_t stream) {
+                        int row_elems, int n_classes, float* const* tables, int n_tables, int rows_per_table,
+                        bool fill_local, float* side, int64_t side_elems, cudaStream_t stream) {
   NW_REQUIRE(epilogue == NW_EPI_EUCLID || epilogue == NW_EPI_LINEAR, NW_ERR_INVALID, "unknown epilogue %d", epilogue);
   NW_REQUIRE(q_bf16 && bank_bf16 && labels && tables && side, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(n_tables >= 1 && n_tables <= k1::NW_MAX_PEERS, NW_ERR_INVALID, "n_tables must be in [1, %d]",
              k1::NW_MAX_PEERS);
   for (int r = 0; r < n_tables; ++r) NW_REQUIRE(tables[r] != nullptr, NW_ERR_INVALID, "NULL class-LSE table %d", r);
+  NW_REQUIRE(rows_per_table >= 0 && (rows_per_table == 0 || (long long)rows_per_table * n_tables >= n_query),
+             NW_ERR_INVALID, "rows_per_table * n_tables must cover n_query");
   NW_REQUIRE(epilogue != NW_EPI_EUCLID || (q_sqnorm && s_sqnorm), NW_ERR_INVALID,
              "the euclidean epilogue needs q_sqnorm and s_sqnorm");
   NW_REQUIRE(row_elems > 0 && row_elems % k1::BK == 0, NW_ERR_INVALID, "row_elems must be a positive multiple of 64");
@@ -662,6 +671,7 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   k1::TableList tl;
   for (int r = 0; r < k1::NW_MAX_PEERS; ++r) p.lse[r] = tl.t[r] = (r < n_tables ? tables[r] : nullptr);
   p.n_tables = tl.n = n_tables;
+  p.rows_per_table = tl.rows_per_table = rows_per_table;
   p.side = side;
   p.n_query = n_query;
   p.n_support = int(n_support);
@@ -705,16 +715,16 @@ extern "C" int nw_forward_class_lse(int epilogue, float scale, const void* q_bf1
   NW_REQUIRE(class_lse != nullptr, NW_ERR_INVALID, "NULL pointer argument");
   float* tables[1] = {class_lse};
   return forward_impl(epilogue, scale, q_bf16, q_sqnorm, n_query, bank_bf16, s_sqnorm, labels, n_support, row_elems,
-                      n_classes, tables, 1, /*fill_local=*/true, side, side_elems, static_cast<cudaStream_t>(stream_));
+                      n_classes, tables, 1, 0, /*fill_local=*/true, side, side_elems, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int nw_forward_class_lse_peers(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm,
                                           int n_query, const void* bank_bf16, const float* s_sqnorm,
                                           const int32_t* labels, int64_t n_support, int row_elems, int n_classes,
-                                          float* const* tables_host, int n_tables, float* side, int64_t side_elems,
-                                          void* stream_) {
+                                          float* const* tables_host, int n_tables, int rows_per_table, float* side,
+                                          int64_t side_elems, void* stream_) {
   return forward_impl(epilogue, scale, q_bf16, q_sqnorm, n_query, bank_bf16, s_sqnorm, labels, n_support, row_elems,
-                      n_classes, tables_host, n_tables, /*fill_local=*/false, side, side_elems,
+                      n_classes, tables_host, n_tables, rows_per_table, /*fill_local=*/false, side, side_elems,
                       static_cast<cudaStream_t>(stream_));
 }
 

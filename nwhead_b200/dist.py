@@ -62,11 +62,10 @@ class PeerTables:
             t = symm_mem.empty((max_batch, n_classes), dtype=torch.float32, device=device)
             t.fill_(float("-inf"))
             hdl = symm_mem.rendezvous(t, self.group.group_name)
-            ptrs = list(hdl.buffer_ptrs)
-            order = [ptrs[rank]] + [p for r, p in enumerate(ptrs) if r != rank]  # [0] must be the local table
+            ptrs = list(hdl.buffer_ptrs)  # one table per rank, in rank order
             self.tables.append(t)
             self.handles.append(hdl)
-            self.ptr_arrays.append((ctypes.c_void_p * len(order))(*order))
+            self.ptr_arrays.append((ctypes.c_void_p * len(ptrs))(*ptrs))
         torch.cuda.synchronize(device)
         dist.barrier(self.group)  # every table is -inf before any peer may store into it
         self.step = 0
@@ -112,7 +111,31 @@ class ShardedBank:
         hdl.barrier(channel=ch)  # all ranks' peer stores have landed (kernel completion + signal exchange)
         return table[:b]
 
+    def class_lse_rows(self, q, scale: float = 1.0):
+        """This rank's rows [rank*B/R, (rank+1)*B/R) of the merged table, shape (B/R, C).  With the peer exchange
+        each class-LSE entry crosses NVLink once (all-to-all) instead of being replicated to every rank."""
+        b = q.shape[0]
+        rank = dist.get_rank(self.group) if self.world > 1 else 0
+        if b % self.world:
+            raise ValueError(f"batch {b} is not a multiple of the world size {self.world}")
+        rows = b // self.world
+        if self.peer is None:
+            return self.class_lse(q, scale)[rank * rows:(rank + 1) * rows]
+        if b > self.peer.max_batch:
+            raise ValueError(f"batch {b} exceeds the peer tables' max_batch {self.peer.max_batch}")
+        table, hdl, ptrs, ch = self.peer.next()
+        q_bf16, q_sq = self.shard.prepare_queries(q)
+        self.shard.class_lse_prepared(q_bf16, q_sq, scale, tables=ptrs, rows_per_table=rows)
+        hdl.barrier(channel=ch)
+        return table[rank * rows:(rank + 1) * rows]
+
     def forward(self, q, scale: float = 1.0):
         from .bank import logp_from_class_lse
 
         return logp_from_class_lse(self.class_lse(q, scale))
+
+    def forward_rows(self, q, scale: float = 1.0):
+        """log-probs of this rank's rows only (each rank finalises B/R rows)."""
+        from .bank import logp_from_class_lse
+
+        return logp_from_class_lse(self.class_lse_rows(q, scale))

@@ -70,8 +70,7 @@ class FullModePredictor:
         compute.wait_event(slot.h2d_done)
         if self.world > 1:
             dist.all_gather_into_tensor(slot.q_full, slot.q_slice, group=self.group)
-        lse = self.sharded.class_lse(slot.q_full, self.scale)
-        mine = lse[self.rank * self.rows:(self.rank + 1) * self.rows] if self.world > 1 else lse
+        mine = self.sharded.class_lse_rows(slot.q_full, self.scale)  # this rank's rows of the merged table
         logp_from_class_lse(mine, out=slot.logp)
         slot.compute_done.record(compute)
         self.out_stream.wait_event(slot.compute_done)

@@ -115,3 +115,19 @@ def test_rank_rows_bit_exact(cuda_lib, n):
     assert np.array_equal(got, np.argsort(-sc, axis=1, kind="stable"))
     k = min(7, n)
     assert np.array_equal(rank_rows(torch.from_numpy(sc).to(DEV), k).cpu().numpy(), got[:, :k])
+
+
+def test_bank_save_load_roundtrip(cuda_lib, tmp_path):
+    from nwhead_b200 import SupportBank
+
+    q, s, y, _ = clustered_features(9, 40, 96, 20, seed=4)
+    rng = np.random.default_rng(0)
+    order = rng.permutation(len(y))  # unsorted input -> the bank carries a permutation
+    bank = SupportBank.build(torch.from_numpy(s[order]).to(DEV), torch.from_numpy(y[order]).to(DEV), 9, "euclidean", "bf16x3")
+    want = bank.forward(torch.from_numpy(q).to(DEV))
+    path = str(tmp_path / "bank.pt")
+    bank.save(path)
+    again = SupportBank.load(path, DEV)
+    assert again.kind == "euclidean" and again.precision == bank.precision and len(again) == len(bank)
+    assert torch.equal(again.perm, bank.perm) and torch.equal(again.feats_bf16, bank.feats_bf16)
+    assert torch.equal(again.forward(torch.from_numpy(q).to(DEV)), want)

@@ -60,6 +60,8 @@ def _worker(rank, world, port, ret):
         for _ in range(3):  # several steps: exercises the double-buffered peer tables
             got = sharded.forward(torch.from_numpy(q).to(dev))
             ok = ok and (got - want).abs().max().item() < 2e-5
+            part = sharded.forward_rows(torch.from_numpy(q).to(dev))  # all-to-all: only this rank's rows
+            ok = ok and (part - want[rank * rows:(rank + 1) * rows]).abs().max().item() < 2e-5
         pred = nwhead_b200.FullModePredictor(sharded, rows=rows)
         for _ in range(3):
             mine = pred(torch.from_numpy(q[rank * rows:(rank + 1) * rows]).pin_memory())

@@ -147,8 +147,75 @@ def cfg3_torch_gpu_unfused(feats, labels, n_classes):
         emit(config="cfg3 torch-gpu-unfused", error=str(e)[:120])
 
 
+class SynthImages(torch.utils.data.Dataset):
+    """CUB-shaped synthetic dataset: 5994 images of 3x224x224, labels i % 200."""
+
+    def __init__(self, n=5994, n_classes=200):
+        self.targets = [i % n_classes for i in range(n)]
+
+    def __len__(self):
+        return len(self.targets)
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(int(i))
+        return torch.randn(3, 224, 224, generator=g), self.targets[i]
+
+
+def cfg1_cfg2_with_resnet18():
+    """Whole NWNet calls with a ResNet-18 backbone (torchvision, fc removed -> 512 features): config 1
+    precompute + predict(mode) at batch 8, and the config 2 episodic training step (B=8, n_way=10, n_shot=1)."""
+    try:
+        import torchvision
+    except ImportError:
+        emit(config="cfg1/cfg2 with ResNet-18", error="torchvision not available")
+        return
+    import numpy as np
+
+    feat = torchvision.models.resnet18(weights=None)
+    feat.fc = torch.nn.Identity()
+    ds = SynthImages()
+    net = nwhead_b200.NWNet(feat, 200, support_dataset=ds, feat_dim=512, kernel_type="euclidean", n_shot=1, n_way=10,
+                            device="cuda:0").to(DEV)
+    net.eval()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        net.precompute()
+    torch.cuda.synchronize()
+    emit(config="cfg1 NWNet.precompute() ResNet-18, 5994 synthetic 224x224 images, 200 classes", seconds=time.perf_counter() - t0,
+         bank_rows=len(net.support_eval.full_bank), note="includes the host-side synthetic image generation")
+    x = torch.randn(8, 3, 224, 224, device=DEV)
+    with torch.no_grad():
+        f = net.featurizer(x)
+        t_feat = timed(lambda: net.featurizer(x), 20, 5)
+        for mode in ("full", "cluster", "random"):
+            ms = timed(lambda: net.predict(x, mode=mode), 20, 5)
+            emit(config=f"cfg1 NWNet.predict(mode='{mode}') batch 8, ResNet-18 on the B200", ms=ms, queries_per_s=8e3 / ms,
+                 featurizer_ms=t_feat, head_ms=ms - t_feat)
+        bank = net.support_eval.full_bank
+        ms = timed(lambda: bank.forward(f), 50, 10)
+        emit(config="cfg1 head only: bank 5800x512, batch 8 (fused forward + finalise)", ms=ms)
+    net.train()
+    opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.9, nesterov=True)
+    y = torch.tensor([3, 17, 17, 42, 99, 150, 199, 0], device=DEV)
+    np.random.seed(0)
+    sup = net.support_train.get_support(y)  # sample once: the timing excludes host-side image generation
+    sup = tuple(t.to(DEV) for t in sup)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.nll_loss(net(x, y, support_data=sup), y)
+        loss.backward()
+        opt.step()
+
+    ms = timed(step, 20, 5)
+    emit(config="cfg2 whole episodic training step (ResNet-18 fwd+bwd on 18 images, NW head fwd+bwd, SGD) B=8 n_way=10",
+         ms=ms, note="backbone-dominated; head GPU time is 23 us of it (profiles/r1_episodic_launches_ours.txt)")
+
+
 def main():
     _abi.check(_abi.load().nw_device_check(), "nw_device_check")
+    if "--resnet" in sys.argv:
+        cfg1_cfg2_with_resnet18()
     cfg2_episodic()
     cfg5_influence()
     torch.cuda.empty_cache()

@@ -73,7 +73,11 @@ NW_API int nw_device_check(void);
  * and the per-call `.to(device)` of the whole bank in NWNet.predict (nwhead/nw.py:156).
  * ------------------------------------------------------------------------------------------ */
 
-/* bf16 elements per stored row for feature width d: precision*d rounded up to a multiple of 64. */
+/* bf16 elements per stored row for feature width d: precision*d rounded up to a multiple of 64.
+ * bf16 operands (bank and prepared queries) are stored K-BLOCK-MAJOR: a matrix of n rows is the 3-D array
+ * [row_elems / 64][n][64], element (row, col) at ((col / 64) * n + row) * 64 + col % 64.  Every 64-element
+ * k-block of a row is one 128-byte TMA swizzle row and every (row tile, k-block) box the fused forward loads
+ * is contiguous in HBM. */
 NW_API int nw_row_elems(int d, int precision);
 
 /* labels_i64[perm[i]] -> int32, validating 0 <= label < C (F.one_hot would raise, nwhead/nw.py:276)
@@ -94,7 +98,8 @@ NW_API int nw_column_mean(const float* rows, int64_t n, int d, int64_t ld, float
 /* out[i, :] = bf16 layout of f(rows[perm[i], :]) with f = optional centring (x - center) followed by
  * optional L2 normalisation x / max(|x|, 1e-12) (F.normalize, nwhead/kernel.py:19-20,25-26,41-42);
  * sqnorm_out[i] = squared norm of the values the tensor cores will see.
- * out has row stride row_elems = nw_row_elems(d, precision); padding columns are zero. */
+ * out holds n * row_elems bf16 values, row_elems = nw_row_elems(d, precision), in the k-block-major layout
+ * described above; padding columns are zero. */
 NW_API int nw_rows_to_bf16(const float* rows, int64_t n, int d, int64_t ld, const int64_t* perm, const float* center,
                     int normalize, int layout, int precision, void* out_bf16, int row_elems,
                     float* sqnorm_out, void* stream);

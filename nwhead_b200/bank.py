@@ -4,7 +4,8 @@ Replaces the CPU fp32 bank of the reference (nwhead/nw.py:118-125, 213-243; nwhe
 and the per-call whole-bank host->device copy in NWNet.predict (nwhead/nw.py:156).
 
 HBM layout (all contiguous, 16-byte aligned):
-    feats_bf16 (N, row_elems) bf16   row_elems = precision*d rounded up to 64 (one 128-B TMA row per k-block)
+    feats_bf16 (row_elems/64, N, 64) bf16   K-BLOCK-MAJOR; row_elems = precision*d rounded up to 64.  Each k-block
+                                     of a row is one 128-B TMA swizzle row, each (row tile, k-block) box is contiguous
     sqnorm     (N,)          fp32    squared norms of the ROUNDED rows (euclidean kinds)
     labels     (N,)          int32   class-sorted
     offsets    (C+1,)        int32   first row of every class
@@ -38,12 +39,12 @@ def resolve_precision(precision: str, n: int, d: int) -> int:
 
 
 def rows_to_bf16(rows: torch.Tensor, *, perm, center, normalize: bool, layout: int, precision: int):
-    """nw_rows_to_bf16: fp32 (R, d) -> (bf16 (R, row_elems), sqnorm (R,))."""
+    """nw_rows_to_bf16: fp32 (R, d) -> (bf16 k-block-major (row_elems/64, R, 64), sqnorm (R,))."""
     lib = load()
     assert rows.dim() == 2 and rows.dtype == torch.float32 and rows.stride(1) == 1
     n, d = rows.shape
     row_elems = lib.nw_row_elems(d, precision)
-    out = torch.empty((n, row_elems), dtype=torch.bfloat16, device=rows.device)
+    out = torch.empty((row_elems // 64, n, 64), dtype=torch.bfloat16, device=rows.device)
     sq = torch.empty((n,), dtype=torch.float32, device=rows.device)
     check(
         lib.nw_rows_to_bf16(ptr(rows), n, d, rows.stride(0), ptr(perm), ptr(center), int(normalize), layout,
@@ -69,7 +70,7 @@ class SupportBank:
         self.n_classes = n_classes
 
     def __len__(self):
-        return self.feats_bf16.shape[0]
+        return self.feats_bf16.shape[1]
 
     @property
     def device(self):
@@ -77,7 +78,12 @@ class SupportBank:
 
     @property
     def row_elems(self):
-        return self.feats_bf16.shape[1]
+        return self.feats_bf16.shape[0] * 64
+
+    def rows_as_matrix(self, rows=None) -> torch.Tensor:
+        """(n, row_elems) row-major fp32 view of the stored bf16 rows (inspection / tests)."""
+        t = self.feats_bf16 if rows is None else self.feats_bf16[:, rows]
+        return t.permute(1, 0, 2).reshape(t.shape[1], -1).float()
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.feats_bf16, self.sqnorm, self.labels, self.offsets))
@@ -143,7 +149,7 @@ class SupportBank:
         check(lib.nw_class_offsets(ptr(labels), labels.numel(), self.n_classes, ptr(offsets), stream_of(self.device)),
               "nw_class_offsets")
         perm = idx if self.perm is None else self.perm.index_select(0, idx)
-        return SupportBank(self.feats_bf16.index_select(0, idx).contiguous(), self.sqnorm.index_select(0, idx).contiguous(),
+        return SupportBank(self.feats_bf16.index_select(1, idx).contiguous(), self.sqnorm.index_select(0, idx).contiguous(),
                            labels, offsets, perm, self.center, self.kind, self.precision, self.d, self.n_classes)
 
     def class_shard(self, rank: int, world: int) -> "SupportBank":
@@ -161,7 +167,7 @@ class SupportBank:
         check(lib.nw_class_offsets(ptr(labels), labels.numel(), self.n_classes, ptr(offsets), stream_of(self.device)),
               "nw_class_offsets")
         perm = (torch.arange(r0, r1, device=self.device) if self.perm is None else self.perm[sl]).contiguous()
-        return SupportBank(self.feats_bf16[sl].contiguous(), self.sqnorm[sl].contiguous(), labels, offsets, perm,
+        return SupportBank(self.feats_bf16[:, sl].contiguous(), self.sqnorm[sl].contiguous(), labels, offsets, perm,
                            self.center, self.kind, self.precision, self.d, self.n_classes)
 
     # ------------------------------------------------------------------------------------------
@@ -215,7 +221,7 @@ class SupportBank:
         rank, in rank order): results are stored into all of them, or with rows_per_table > 0 only into the
         table that owns the row (nw_forward_class_lse_peers); returns None."""
         lib = load()
-        b = q_bf16.shape[0]
+        b = q_bf16.shape[1]
         n = len(self)
         plan = _abi.forward_plan(b, n)
         dev = self.device

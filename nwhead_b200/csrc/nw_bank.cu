@@ -3,8 +3,9 @@
 //
 // Replaces the CPU fp32 bank of the reference (nwhead/nw.py:213-243, nwhead/support.py:113-120) and
 // the per-call whole-bank host->device copy (nwhead/nw.py:156) by a device-resident, class-sorted
-// layout: bf16 features (row stride a multiple of 64 elements = 128 B, so every k-block is one TMA
-// swizzle row), fp32 squared norms of the ROUNDED values, int32 labels, int32 class offsets.
+// layout: bf16 features stored k-block-major [row_elems/64][N][64] (every 64-element k-block of a row is one
+// 128-byte TMA swizzle row and every (row tile, k-block) box is contiguous in HBM), fp32 squared norms of the
+// ROUNDED values, int32 labels, int32 class offsets.
 
 #include <stdarg.h>
 #include <string.h>
@@ -116,7 +117,9 @@ __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restri
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const float* src = rows + (perm ? perm[row] : row) * ld;
-  __nv_bfloat16* dst = out + row * (long long)row_elems;
+  // k-block-major output: element (row, col) lives at ((col / 64) * n + row) * 64 + col % 64, so that every
+  // (row tile, k-block) box the fused forward loads with TMA is one contiguous run of 128-byte rows in HBM
+  auto at = [&](int col) -> __nv_bfloat16* { return out + ((long long)(col >> 6) * n + row) * 64 + (col & 63); };
 
   float inv = 1.0f;
   if (normalize) {
@@ -166,10 +169,10 @@ __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restri
         }
       }
       const uint2 ph = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]));
-      *reinterpret_cast<uint2*>(dst + c) = ph;
+      *reinterpret_cast<uint2*>(at(c)) = ph;
       if (precision == NW_PREC_BF16X3) {
-        *reinterpret_cast<uint2*>(dst + seg_hi2 + c) = ph;
-        *reinterpret_cast<uint2*>(dst + seg_lo + c) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+        *reinterpret_cast<uint2*>(at(seg_hi2 + c)) = ph;
+        *reinterpret_cast<uint2*>(at(seg_lo + c)) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
       }
     }
   } else {
@@ -177,19 +180,19 @@ __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restri
       const float x = (src[c] - (center ? center[c] : 0.f)) * inv;
       const __nv_bfloat16 hi = __float2bfloat16_rn(x);
       const float h = __bfloat162float(hi);
-      dst[c] = hi;
+      *at(c) = hi;
       if (precision == NW_PREC_BF16X3) {
         const __nv_bfloat16 lo = __float2bfloat16_rn(x - h);
         const float l = __bfloat162float(lo);
-        dst[seg_hi2 + c] = hi;
-        dst[seg_lo + c] = lo;
+        *at(seg_hi2 + c) = hi;
+        *at(seg_lo + c) = lo;
         sq += h * h + 2.0f * h * l;
       } else {
         sq += h * h;
       }
     }
   }
-  for (int c = precision * d + lane; c < row_elems; c += 32) dst[c] = __float2bfloat16_rn(0.f);
+  for (int c = precision * d + lane; c < row_elems; c += 32) *at(c) = __float2bfloat16_rn(0.f);
   sq = warp_sum(sq);
   if (lane == 0 && sqnorm_out) sqnorm_out[row] = sq;
 }

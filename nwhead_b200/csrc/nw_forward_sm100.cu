@@ -72,7 +72,7 @@ struct Params {
   const float* q_sqnorm;
   const float* s_sqnorm;
   const int32_t* labels;
-  const uint8_t* bank;  // bf16 bank base (for linear L2 prefetch); row pitch = kblocks * 128 bytes
+  const uint8_t* bank;  // bf16 bank base (for linear L2 prefetch), k-block-major [kblocks][N][64]
   float* lse[NW_MAX_PEERS];  // class-LSE tables the results are stored to (local + peer GPUs over NVLink P2P)
   int n_tables;
   int rows_per_table;  // 0: store every entry to ALL tables; > 0: only to table[row / rows_per_table]
@@ -236,17 +236,15 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
               pt = un < n_units ? (un / p.q_groups) * p.tiles_per_chunk : -1;
             }
             if (pt >= 0 && p.l2_prefetch) {
-              // a tile's rows are contiguous in HBM (it spans every column), so prefetch it as one linear range
-              // in 32 KB pieces: sequential DRAM pages instead of 128-byte column slices
-              const long long row_bytes = (long long)p.kblocks * (BK * 2);
+              // the bank is k-block-major, so each (tile, k-block) box of this CTA is one contiguous run of
+              // 128-byte rows: prefetch those runs, split over the query groups that share the chunk
               const long long r0 = (long long)pt * BN + (long long)cta_rank * C::B_ROWS;
               long long r1 = r0 + C::B_ROWS;
               if (r1 > p.n_support) r1 = p.n_support;
-              const long long beg = r0 * row_bytes, end = r1 * row_bytes;
-              constexpr long long PIECE = 32768;
-              for (long long off = beg + (long long)qg * PIECE; off < end; off += (long long)p.q_groups * PIECE) {
-                const long long len = end - off < PIECE ? end - off : PIECE;
-                bulk_prefetch_l2(p.bank + off, uint32_t(len));
+              if (r1 > r0) {
+                const uint32_t len = uint32_t((r1 - r0) * (BK * 2));
+                for (int kb = qg % p.kblocks; kb < p.kblocks; kb += p.q_groups)
+                  bulk_prefetch_l2(p.bank + ((long long)kb * p.n_support + r0) * (BK * 2), len);
               }
             }
           }
@@ -259,13 +257,13 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
               // both CTAs' bytes are accounted on the LEADER's full barrier (the MMA issuer waits there)
               const uint32_t bar = mapa_u32(smem_u32(&tail->full[s]), 0);
               if (leader) mbar_arrive_expect_tx(smem_u32(&tail->full[s]), 2 * STAGE_BYTES);
-              tma_load_2d_pair(a_dst, &map_q, bar, kb * BK, q_row0, pol_q);
-              tma_load_2d_pair(a_dst + A_BYTES, &map_s, bar, kb * BK, s_row0, pol_s);
+              tma_load_3d_pair(a_dst, &map_q, bar, 0, q_row0, kb, pol_q);
+              tma_load_3d_pair(a_dst + A_BYTES, &map_s, bar, 0, s_row0, kb, pol_s);
             } else {
               const uint32_t bar = smem_u32(&tail->full[s]);
               mbar_arrive_expect_tx(bar, STAGE_BYTES);
-              tma_load_2d(a_dst, &map_q, bar, kb * BK, q_row0, pol_q);
-              tma_load_2d(a_dst + A_BYTES, &map_s, bar, kb * BK, s_row0, pol_s);
+              tma_load_3d(a_dst, &map_q, bar, 0, q_row0, kb, pol_q);
+              tma_load_3d(a_dst + A_BYTES, &map_s, bar, 0, s_row0, kb, pol_s);
             }
           }
         }
@@ -533,15 +531,16 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-B swizzle, zero OOB fill.
+// k-block-major bf16 operand [cols/64][rows][64] seen as a 3-D tensor {64, rows, cols/64}; box = one k-block of
+// box_rows rows (box_rows x 128 B, contiguous in HBM), 128-B swizzle, zero fill for rows past the end.
 static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   NW_REQUIRE(fn != nullptr, NW_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * 2};
-  cuuint32_t box[2] = {BK, box_rows};
-  cuuint32_t estride[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+  cuuint64_t gdim[3] = {BK, rows, cols / BK};
+  cuuint64_t gstride[2] = {BK * 2, rows * BK * 2};
+  cuuint32_t box[3] = {BK, box_rows, 1};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NW_REQUIRE(r == CUDA_SUCCESS, NW_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));

@@ -27,7 +27,8 @@ def test_bank_layout_bit_exact(cuda_lib):
     center = bank.center.cpu().numpy()
     assert np.abs(center - s.mean(0, dtype=np.float64)).max() < 1e-5
     expect = O.quantize_bf16(s[perm] - center)
-    got = bank.feats_bf16.float().cpu().numpy()
+    assert tuple(bank.feats_bf16.shape) == (2, N, 64)  # k-block-major: [row_elems / 64][N][64]
+    got = bank.rows_as_matrix().cpu().numpy()
     assert got.shape == (N, 128)
     assert np.array_equal(got[:, :d], expect) and not got[:, d:].any()
     sq = (expect.astype(np.float64) ** 2).sum(1)
@@ -35,7 +36,7 @@ def test_bank_layout_bit_exact(cuda_lib):
     # 3-product split: [hi | hi | lo] with lo = bf16(x - hi)
     b3 = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, "cosine", "bf16x3")
     sn = (s[perm] / np.maximum(np.sqrt((s[perm].astype(np.float64) ** 2).sum(1, keepdims=True)), 1e-12)).astype(np.float32)
-    g3 = b3.feats_bf16.float().cpu().numpy()
+    g3 = b3.rows_as_matrix().cpu().numpy()
     hi = g3[:, :d]
     assert np.abs(hi - sn).max() < 2 ** -8 and np.array_equal(g3[:, d:2 * d], hi)
     assert np.abs(hi + g3[:, 2 * d:3 * d] - sn).max() < 2 ** -15

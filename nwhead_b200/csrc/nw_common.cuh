@@ -104,27 +104,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-// 2-D tiled load global -> shared, completion on an mbarrier (bytes), with an L2 cache policy.
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                            uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      :
-      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
-// Ask L2 to fetch a tile from HBM ahead of time (no shared-memory destination, no completion tracking).
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
-// Linear variant: pull `bytes` (multiple of 16) of contiguous global memory into L2.
+// Pull `bytes` (multiple of 16) of contiguous global memory into L2 (no shared-memory destination).
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
-// 3-D variants (k-block-major operands: coordinates are {element in k-block, row, k-block})
+// 3-D tiled load global -> shared (k-block-major operands: coordinates are {element in k-block, row, k-block}),
+// completion on an mbarrier (bytes), with an L2 cache policy.  The _pair variant signals an mbarrier that may
+// live in the peer CTA of a cta_group::2 pair.
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             uint64_t policy) {
   asm volatile(
@@ -214,16 +200,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load whose completion bytes are signalled on an mbarrier that may live in the peer CTA of the pair
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
-                                                 int c0, int c1, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      :
-      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)

@@ -104,10 +104,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-// Pull `bytes` (multiple of 16) of contiguous global memory into L2 (no shared-memory destination).
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
 // 3-D tiled load global -> shared (k-block-major operands: coordinates are {element in k-block, row, k-block}),
 // completion on an mbarrier (bytes), with an L2 cache policy.  The _pair variant signals an mbarrier that may
 // live in the peer CTA of a cta_group::2 pair.

@@ -72,7 +72,6 @@ struct Params {
   const float* q_sqnorm;
   const float* s_sqnorm;
   const int32_t* labels;
-  const uint8_t* bank;  // bf16 bank base (for linear L2 prefetch), k-block-major [kblocks][N][64]
   float* lse[NW_MAX_PEERS];  // class-LSE tables the results are stored to (local + peer GPUs over NVLink P2P)
   int n_tables;
   int rows_per_table;  // 0: store every entry to ALL tables; > 0: only to table[row / rows_per_table]
@@ -86,7 +85,6 @@ struct Params {
   int chunks;
   int tiles_per_chunk;
   float scale_log2;  // LINEAR: scale * log2(e)
-  int l2_prefetch;   // 1: pull the next support tile into L2 one tile ahead
 };
 
 struct Flusher {
@@ -226,28 +224,6 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int q_row0 = (qg * NCTA + int(cta_rank)) * BM;
         for (int t = t0; t < t1; ++t) {
           const int s_row0 = t * BN + int(cta_rank) * C::B_ROWS;
-          {
-            // The workers that share this chunk reach every new support tile at the same time, so its first
-            // touch would expose HBM latency to all of them at once.  Pull the NEXT tile into L2 one tile
-            // (~10 us) ahead; the k-blocks are split over the query groups that share the chunk.
-            int pt = t + 1;
-            if (pt >= t1) {
-              const int un = u + n_workers;
-              pt = un < n_units ? (un / p.q_groups) * p.tiles_per_chunk : -1;
-            }
-            if (pt >= 0 && p.l2_prefetch) {
-              // the bank is k-block-major, so each (tile, k-block) box of this CTA is one contiguous run of
-              // 128-byte rows: prefetch those runs, split over the query groups that share the chunk
-              const long long r0 = (long long)pt * BN + (long long)cta_rank * C::B_ROWS;
-              long long r1 = r0 + C::B_ROWS;
-              if (r1 > p.n_support) r1 = p.n_support;
-              if (r1 > r0) {
-                const uint32_t len = uint32_t((r1 - r0) * (BK * 2));
-                for (int kb = qg % p.kblocks; kb < p.kblocks; kb += p.q_groups)
-                  bulk_prefetch_l2(p.bank + ((long long)kb * p.n_support + r0) * (BK * 2), len);
-              }
-            }
-          }
           for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
             const uint32_t s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
@@ -666,7 +642,6 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.q_sqnorm = q_sqnorm;
   p.s_sqnorm = s_sqnorm;
   p.labels = labels;
-  p.bank = static_cast<const uint8_t*>(bank_bf16);
   k1::TableList tl;
   for (int r = 0; r < k1::NW_MAX_PEERS; ++r) p.lse[r] = tl.t[r] = (r < n_tables ? tables[r] : nullptr);
   p.n_tables = tl.n = n_tables;
@@ -681,14 +656,6 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.chunks = plan.chunks;
   p.tiles_per_chunk = plan.tiles_per_chunk;
   p.scale_log2 = scale * kLog2e;
-  {
-    // One-tile-ahead L2 prefetch only pays when few distinct support streams are live (many query groups share
-    // each stream); with one stream per worker the prefetched tiles (148 MB) exceed L2 and the bank would be read
-    // from HBM twice (measured: 9.4 GB instead of 5.0 GB of DRAM reads at B=8).
-    const char* e = getenv("NW_B200_NO_PREFETCH");
-    p.l2_prefetch = (plan.q_tiles >= 8 && !(e && e[0] == '1')) ? 1 : 0;
-  }
-
   if (epilogue == NW_EPI_EUCLID) {
     rc = ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2>(map_q, map_s, p, plan.grid, stream)
                    : k1::launch_forward<NW_EPI_EUCLID, 1>(map_q, map_s, p, plan.grid, stream);

@@ -137,13 +137,15 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
     m = mx;
   }
   if (emask == 0u) {  // warp-uniform fast path: no class ends inside this chunk
+    float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // four independent partial sums: no 32-long FADD chain
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       float e;
       if (EPI == NW_EPI_EUCLID) e = ex2_approx(fmaf(sqrt_approx(fmaxf(acc[i], 0.0f)), -kLog2e, -m));
       else e = ex2_approx(acc[i] - m);
-      l += e;
+      part[i & 3] += e;
     }
+    l += (part[0] + part[1]) + (part[2] + part[3]);
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -316,31 +318,46 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       flush.side_row = p.side + (size_t(g) * p.n_query + srow) * 2;
       const float qn = (EPI == NW_EPI_EUCLID && flush.row_valid) ? __ldg(p.q_sqnorm + row) : 0.0f;
 
+      // column metadata of a tile: additive term (|s|^2, or 0; +inf / -inf on padding columns) and labels
+      float pre_cadd[BN / EPI_THREADS];
+      int pre_lab[BN / EPI_THREADS];
+      int pre_lab_next = -1;
+      auto load_meta = [&](int t) {
+        const int j0 = t * BN;
+#pragma unroll
+        for (int r = 0; r < BN / EPI_THREADS; ++r) {
+          const int j = j0 + et + r * EPI_THREADS;
+          if (EPI == NW_EPI_EUCLID) pre_cadd[r] = j < n1 ? __ldg(p.s_sqnorm + j) : pos_inf;
+          else pre_cadd[r] = j < n1 ? 0.0f : neg_inf;
+          pre_lab[r] = j < p.n_support ? __ldg(p.labels + j) : -1;
+        }
+        if (et == 0) pre_lab_next = (j0 + BN) < p.n_support ? __ldg(p.labels + j0 + BN) : -1;
+      };
+      load_meta(t0);
+
       float m = neg_inf, l = 0.0f;
       for (int t = t0; t < t1; ++t, ++tc) {
         const uint32_t as = tc & 1u;
         const uint32_t aph = (tc >> 1) & 1u;
         TileMeta& meta = tail->meta[as];
         const int j0 = t * BN;
-        // stage this tile's column metadata while the MMAs of the tile are still running
+        // publish this tile's column metadata (fetched into registers one tile ahead, so the global-load
+        // latency is hidden behind the previous tile's epilogue math)
 #pragma unroll
         for (int r = 0; r < BN / EPI_THREADS; ++r) {
-          const int i = et + r * EPI_THREADS;
-          const int j = j0 + i;
-          float ca;
-          if (EPI == NW_EPI_EUCLID) ca = j < n1 ? __ldg(p.s_sqnorm + j) : pos_inf;
-          else ca = j < n1 ? 0.0f : neg_inf;
-          meta.cadd[i] = ca;
-          meta.lab[i] = j < p.n_support ? __ldg(p.labels + j) : -1;
+          meta.cadd[et + r * EPI_THREADS] = pre_cadd[r];
+          meta.lab[et + r * EPI_THREADS] = pre_lab[r];
         }
-        if (et == 0) meta.lab[BN] = (j0 + BN) < p.n_support ? __ldg(p.labels + j0 + BN) : -1;
+        if (et == 0) meta.lab[BN] = pre_lab_next;
         named_bar_sync(1, EPI_THREADS);
+        if (t + 1 < t1) load_meta(t + 1);
 
         mbar_wait(smem_u32(&tail->tfull[as]), aph);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + as * BN + (uint32_t(ew * 32) << 16);
         // Two 32-column chunks per iteration, NOT unrolled further: the epilogue body is ~1.5k instructions and
         // a fully unrolled tile (8 chunks x 2 paths) overflows the instruction cache (stall_no_inst in ncu).
+        // (Software-pipelining the TMEM loads one chunk ahead was measured: no gain, +40 registers.)
 #pragma unroll 1
         for (int c = 0; c < BN / 32; c += 2) {
           float acc0[32], acc1[32];

@@ -594,12 +594,14 @@ namespace k1 {
 template <int EPI, int NCTA>
 static int launch_forward(const CUtensorMap& map_q, const CUtensorMap& map_s, const Params& p, int grid,
                           cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set[64] = {false};  // function attributes are per device
   auto kern = nw_forward_kernel<EPI, NCTA>;
   constexpr size_t smem = smem_bytes<NCTA>();
-  if (!attr_set) {
+  int dev = 0;
+  NW_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     NW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

@@ -99,7 +99,8 @@ class ShardedBank:
         return ShardedBank(bank.class_shard(rank, world) if world > 1 else bank, group, exchange, max_batch)
 
     def class_lse(self, q, scale: float = 1.0):
-        """(B, C) class log-sum-exp over the WHOLE bank, identical on every rank."""
+        """(B, C) class log-sum-exp over the WHOLE bank, identical on every rank.  With the peer exchange the
+        result is a view of a double-buffered symmetric table: consume it before the call after next."""
         if self.peer is None:
             return merge_class_lse(self.shard.class_lse(q, scale), self.group)
         b = q.shape[0]

@@ -143,6 +143,8 @@ class NWHead(nn.Module):
         """
         kind = self._kind()
         if isinstance(sx, SupportBank):
+            # inference-only (the reference's eval step runs predict() with gradients disabled, train.py:408):
+            # the result carries no grad_fn even if x does
             return sx.forward(x, self.kernel.scale_value())
         _abi.require_cuda(x, sx, sy)
         if x.dtype != torch.float32 or sx.dtype != torch.float32:

@@ -58,6 +58,10 @@ extern "C" {
 #define NW_PREC_BF16 1   /* one bf16 value per feature */
 #define NW_PREC_BF16X3 3 /* hi/lo bf16 split, 3 products: ~fp32 accuracy at 3x the FLOPs */
 
+/* per-pair outputs of nw_forward_emit */
+#define NW_EMIT_SCORES 0    /* out[b, j] = score(b, j)  (the kernel(x, y) matrix, nwhead/kernel.py:13-44) */
+#define NW_EMIT_INFLUENCE 1 /* out[b, j] = support influence (util/metric.py:47) with w = softmax_j score */
+
 /* row layouts written by nw_rows_to_bf16 */
 #define NW_ROWS_BANK 0  /* support rows:  [hi]  or [hi | hi | lo] */
 #define NW_ROWS_QUERY 1 /* query rows:    [hi]  or [hi | lo | hi] */
@@ -145,6 +149,20 @@ NW_API int nw_forward_class_lse_peers(int epilogue, float scale, const void* q_b
                                int n_query, const void* bank_bf16, const float* s_sqnorm, const int32_t* labels,
                                int64_t n_support, int row_elems, int n_classes, float* const* tables_host,
                                int n_tables, int rows_per_table, float* side, int64_t side_elems, void* stream);
+
+/* Dense per-pair output through the same TMA + tcgen05 mainloop (tensor-core replacement of the (B, N) matrices
+ * the reference materialises): out[b, j] for every query b and bank row j, row stride ld_out floats.
+ *   NW_EMIT_SCORES    : the similarity kernel itself — `kernel(x, y)` of nwhead/kernel.py:13-44 as used by
+ *                       NWNet.get_neighbors (nwhead/nw.py:248) and KNN (nwhead/utils.py:187), bf16-operand accuracy.
+ *   NW_EMIT_INFLUENCE : support_influence (util/metric.py:23-50) computed FROM FEATURES: w[b,j] = exp(score -
+ *                       row_lse[b]) is formed in registers and never written; needs row_lse (B) = logsumexp_j
+ *                       score(b, :), p_query (B) = softmax mass of the query's own class, qlabel (B) and the bank
+ *                       labels.  4 bytes per pair of HBM traffic instead of 8 + the weight matrix.
+ * labels may be NULL for NW_EMIT_SCORES. */
+NW_API int nw_forward_emit(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
+                    const void* bank_bf16, const float* s_sqnorm, const int32_t* labels, int64_t n_support,
+                    int row_elems, int emit_kind, const float* row_lse, const float* p_query,
+                    const int32_t* qlabel, float* out, int64_t ld_out, void* stream);
 
 /* logp[b, c] = log( exp(class_lse[b,c] - logsumexp_c class_lse[b,:]) + 1e-12 )  (nwhead/nw.py:285-289).
  * With a sharded bank, all-reduce class_lse with MAX across ranks first (each class is owned by one

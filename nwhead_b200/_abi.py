@@ -17,6 +17,7 @@ KIND = {"euclidean": 0, "hypersphere_euclidean": 1, "cosine": 2, "dotproduct": 3
 EPI_EUCLID, EPI_LINEAR = 0, 1
 PREC_BF16, PREC_BF16X3 = 1, 3
 ROWS_BANK, ROWS_QUERY = 0, 1
+EMIT_SCORES, EMIT_INFLUENCE = 0, 1
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnw_sm100.so")
 
@@ -55,6 +56,8 @@ SIGNATURES = {
     "nw_forward_class_lse_peers": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                            c_int64, c_int, c_int, POINTER(c_void_p), c_int, c_int, c_void_p,
                                            c_int64, c_void_p]),
+    "nw_forward_emit": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
+                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "nw_logp_from_class_lse": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "nw_class_lse_merge": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "nw_direct_scores": (c_int, [c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p,

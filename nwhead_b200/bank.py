@@ -245,6 +245,46 @@ class SupportBank:
         )
         return out
 
+    def _emit(self, q, scale, kind, row_lse=None, p_query=None, qlabel=None, source_order=False):
+        lib = load()
+        _abi.require_cuda(q, self.feats_bf16)
+        q_bf16, q_sq = self.prepare_queries(q)
+        b, n, dev = q.shape[0], len(self), self.device
+        ld = (n + 3) // 4 * 4  # 16-byte aligned rows
+        out = torch.empty((b, ld), dtype=torch.float32, device=dev)
+        epi = _abi.EPI_EUCLID if self.kind in EUCLID_KINDS else _abi.EPI_LINEAR
+        check(
+            lib.nw_forward_emit(epi, float(scale), ptr(q_bf16), ptr(q_sq), b, ptr(self.feats_bf16), ptr(self.sqnorm),
+                                ptr(self.labels), n, self.row_elems, kind, ptr(row_lse), ptr(p_query), ptr(qlabel),
+                                ptr(out), ld, stream_of(dev)),
+            "nw_forward_emit",
+        )
+        out = out[:, :n]
+        if source_order and self.perm is not None:  # column j of the result <-> row j of the tensor the bank was built from
+            res = torch.empty((b, n), dtype=torch.float32, device=dev)
+            res[:, self.perm] = out
+            return res
+        return out
+
+    def scores(self, q: torch.Tensor, scale: float = 1.0, source_order: bool = True) -> torch.Tensor:
+        """Dense (B, N) similarity matrix on the tensor cores (bf16-operand accuracy; use precision='bf16x3'
+        banks for near-fp32 scores).  Columns follow the bank's class-sorted rows, or with source_order the
+        rows of the tensor the bank was built from."""
+        return self._emit(q, scale, _abi.EMIT_SCORES, source_order=source_order)
+
+    def support_influence(self, q: torch.Tensor, qlabel: torch.Tensor, scale: float = 1.0,
+                          source_order: bool = True) -> torch.Tensor:
+        """support_influence (reference util/metric.py:23-50) computed from FEATURES in two tensor-core passes:
+        pass 1 = the fused forward (class log-sum-exp -> softmax mass of each query's class and the softmax
+        normaliser), pass 2 = scores again with the influence formula in the epilogue.  The (B, N) weight matrix
+        the reference takes as an input is never materialised."""
+        lse = self.class_lse(q, scale)
+        z = torch.logsumexp(lse, dim=1).contiguous()
+        qy = qlabel.to(self.device, torch.int64)
+        p = torch.exp(lse.gather(1, qy[:, None])[:, 0] - z).contiguous()
+        return self._emit(q, scale, _abi.EMIT_INFLUENCE, row_lse=z, p_query=p, qlabel=qy.to(torch.int32).contiguous(),
+                          source_order=source_order)
+
     def forward(self, q: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
         """log(softmax-weighted label aggregation + 1e-12): NWHead.forward (nwhead/nw.py:266-289)."""
         return logp_from_class_lse(self.class_lse(q, scale))

@@ -103,18 +103,6 @@ __global__ void onehot_argmax_kernel(const float* __restrict__ onehot, long long
   if (lane == 0) out[r] = bi;
 }
 
-__device__ __forceinline__ float influence_one(float p, float w, bool same) {
-  // reference: log((p - p*w) / (p - w*indicator))   (util/metric.py:47), IEEE division, +inf / nan preserved.
-  // The ratio is 1 + x with x = w*(indicator - p) / (p - w*indicator); for the usual |x| << 1 (w ~ 1/N) the
-  // log1p series below is MORE accurate than rounding the ratio to fp32 first (whose ulp near 1 is 1.2e-7, the
-  // reference's own error floor) and costs a third of the instructions of division + logf.
-  const float ind = same ? 1.0f : 0.0f;
-  const float den = p - ind * w;
-  const float x = __fdividef(w * (ind - p), den);
-  if (fabsf(x) < 0.015625f) return x * (1.0f + x * (-0.5f + x * (0.33333334f - 0.25f * x)));  // |err| < x^5/5
-  return logf((p - p * w) / den);
-}
-
 constexpr int INFL_VEC_PER_THREAD = 2;  // 16-byte vectors per thread: independent loads in flight
 
 template <bool VEC>

@@ -274,6 +274,20 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// support influence of one (query, support) pair — reference util/metric.py:47:
+//   log((p - p*w) / (p - w*indicator)), IEEE division, +inf / nan preserved.
+// The ratio is 1 + x with x = w*(indicator - p) / (p - w*indicator); for the usual |x| << 1 (w ~ 1/N) the log1p
+// series is MORE accurate than rounding the ratio to fp32 first (whose ulp near 1 is 1.2e-7, the reference's own
+// error floor) and costs a third of the instructions of division + logf.
+static __device__ __noinline__ float influence_exact(float p, float w, float den) { return logf((p - p * w) / den); }
+__device__ __forceinline__ float influence_one(float p, float w, bool same) {
+  const float ind = same ? 1.0f : 0.0f;
+  const float den = p - ind * w;
+  const float x = __fdividef(w * (ind - p), den);
+  if (fabsf(x) < 0.015625f) return x * (1.0f + x * (-0.5f + x * (0.33333334f - 0.25f * x)));  // |err| < x^5/5
+  return influence_exact(p, w, den);  // rare, out of line: keeps unrolled callers small (instruction cache)
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -32,18 +32,23 @@ constexpr int MAX_STAGES = 6;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 = all of TMEM
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 128;
+constexpr int MAX_EPI_WARPS = 8;
+constexpr int MAX_THREADS = (EPI_WARP0 + MAX_EPI_WARPS) * 32;
+// Epilogue warps: the class-LSE epilogue carries a running (max, sum) per query row along the columns, so one
+// thread owns a row (4 warps = 128 TMEM lanes).  The emit epilogues have no state across columns, so a second
+// set of 4 warps (same lane quarters, the other column chunks) doubles their throughput.
+constexpr int epi_warps(int mode) { return mode == 0 ? 4 : 8; }
 constexpr int NW_MAX_PEERS = 16;
 
 // NCTA = 1: one CTA computes a 128 x 256 tile (UMMA M=128).
 // NCTA = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x 256 tile (UMMA M=256); each CTA stages
 //           its own 128 query rows and HALF of the support tile, so L2->SM traffic and shared-memory operand
 //           reads per FLOP drop by a third and the smaller stages allow a 6-deep TMA ring.
-template <int NCTA>
+template <int NCTA, int MODE = 0>
 struct Cfg {
-  static constexpr int STAGES = NCTA == 1 ? 4 : 6;
+  // the emit modes give one ring stage up for the per-warp transpose buffers of their epilogue
+  static constexpr int STAGES = (NCTA == 1 ? 4 : 6) - (MODE == 0 ? 0 : 1);
   static constexpr int B_ROWS = BN / NCTA;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -54,8 +59,10 @@ struct TileMeta {
   int lab[BN + 8];   // labels of the tile's columns plus one look-ahead entry
 };
 
+template <int MODE>
 struct SmemTail {
   TileMeta meta[ACC_STAGES];
+  float stage[MODE == 0 ? 1 : MAX_EPI_WARPS][32][33];  // emit modes: per-warp 32x32 transpose buffers
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
   uint64_t tfull[ACC_STAGES];
@@ -63,9 +70,10 @@ struct SmemTail {
   uint32_t tmem_base;
 };
 
-template <int NCTA>
+template <int NCTA, int MODE>
 constexpr size_t smem_bytes() {
-  return 1024 /*align slack*/ + size_t(Cfg<NCTA>::STAGES) * Cfg<NCTA>::STAGE_BYTES + sizeof(SmemTail);
+  return 1024 /*align slack*/ + size_t(Cfg<NCTA, MODE>::STAGES) * Cfg<NCTA, MODE>::STAGE_BYTES +
+         sizeof(SmemTail<MODE>);
 }
 
 struct Params {
@@ -85,7 +93,21 @@ struct Params {
   int chunks;
   int tiles_per_chunk;
   float scale_log2;  // LINEAR: scale * log2(e)
+  // ---- MODE_EMIT only: one output value per (query, support) pair
+  float* emit_out;           // (B, ld_out)
+  long long emit_ld;
+  int emit_kind;             // NW_EMIT_SCORES | NW_EMIT_INFLUENCE
+  int emit_vec;              // 1: 16-byte stores are aligned
+  const float* row_lse;      // (B) logsumexp_j score(b, j)          [influence]
+  const float* p_query;      // (B) softmax mass of the query's class [influence]
+  const int32_t* qlabel;     // (B) query labels                      [influence]
 };
+
+constexpr int MODE_CLASS_LSE = 0;       // online softmax + per-class sums (the NW head)
+constexpr int MODE_EMIT_SCORES = 1;     // dense per-pair output: the similarity scores
+constexpr int MODE_EMIT_INFLUENCE = 2;  // dense per-pair output: support influence
+// (the emit kind is a template parameter: one kernel with a runtime switch and logf inlined 64 times was > 64 KB
+//  of SASS and ran 4x slower on instruction fetch)
 
 struct Flusher {
   const Params* p;
@@ -161,18 +183,80 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
   }
 }
 
-template <int EPI, int NCTA>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// MODE_EMIT: one 32-column chunk.  Every thread turns the 32 accumulators of ITS query row into output values,
+// the warp transposes the 32x32 block through shared memory, and each store instruction then writes four rows x
+// 128 contiguous bytes (full cache lines) instead of 32 scattered 16-byte pieces.
+template <int EPI, bool INFLUENCE>
+__device__ __forceinline__ void emit_chunk(float (&acc)[32], const float* __restrict__ cadd,
+                                           const int* __restrict__ lab, float qn, float scale, float z,
+                                           float pq, int qy, float (*stage)[33], int lane, float* __restrict__ out,
+                                           long long ld, int row0, int n_rows, int col0, int n_valid, bool vec) {
+  // phase 1: scores of this thread's query row -> staging tile
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float sc;
+    if (EPI == NW_EPI_EUCLID) sc = -sqrt_approx(fmaxf(fmaf(-2.0f, acc[i], qn + cadd[i]), 0.0f));
+    else sc = acc[i] * scale;
+    stage[lane][i] = sc;
+  }
+  __syncwarp();
+  // phase 2: transposed read-out.  The influence transform runs here, in a rolled loop (4 inline copies instead
+  // of 64: the unrolled form was > 64 KB of SASS and instruction-fetch bound); lane rr holds row rr's parameters.
+  const int c4 = (lane & 7) * 4;
+#pragma unroll 2
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3);
+    float v[4] = {stage[rr][c4], stage[rr][c4 + 1], stage[rr][c4 + 2], stage[rr][c4 + 3]};
+    if (INFLUENCE) {
+      const float rz = __shfl_sync(0xffffffffu, z, rr);
+      const float rp = __shfl_sync(0xffffffffu, pq, rr);
+      const int ry = __shfl_sync(0xffffffffu, qy, rr);
+      // Branch-free fast path for all four values first (one epilogue warp per scheduler: the per-element branch of
+      // influence_one serialised the four dependency chains, 900 cycles per iteration), exact formula afterwards
+      // only where |x| is not small.
+      float w[4], den[4], x[4];
+      bool slow = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float ind = lab[c4 + k] == ry ? 1.0f : 0.0f;
+        w[k] = __expf(v[k] - rz);
+        den[k] = rp - ind * w[k];
+        x[k] = __fdividef(w[k] * (ind - rp), den[k]);
+        v[k] = x[k] * (1.0f + x[k] * (-0.5f + x[k] * (0.33333334f - 0.25f * x[k])));
+        slow |= !(fabsf(x[k]) < 0.015625f);
+      }
+      if (slow) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (!(fabsf(x[k]) < 0.015625f)) v[k] = influence_exact(rp, w[k], den[k]);
+      }
+    }
+    if (row0 + rr < n_rows) {
+      float* dst = out + (long long)(row0 + rr) * ld + col0 + c4;
+      if (vec && c4 + 4 <= n_valid) {
+        __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c4 + k < n_valid) dst[k] = v[k];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int EPI, int NCTA, int MODE>
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_s,
                   const __grid_constant__ Params p) {
-  using C = Cfg<NCTA>;
+  using C = Cfg<NCTA, MODE>;
   constexpr int STAGES = C::STAGES;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;  // 1024-B aligned (swizzle-128B atoms); same offset in both CTAs of a pair
-  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + size_t(STAGES) * STAGE_BYTES);
+  SmemTail<MODE>* tail = reinterpret_cast<SmemTail<MODE>*>(smem + size_t(STAGES) * STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -193,7 +277,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(smem_u32(&tail->tfull[i]), 1);
-      mbar_init(smem_u32(&tail->tempty[i]), NCTA * EPI_THREADS / 32);
+      mbar_init(smem_u32(&tail->tempty[i]), NCTA * epi_warps(MODE));
     }
     fence_mbar_init();
   }
@@ -288,9 +372,11 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
     }
     __syncwarp();
-  } else if (warp >= EPI_WARP0) {
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + epi_warps(MODE)) {
     // ===================================== epilogue ==========================================
-    const int ew = warp - EPI_WARP0;  // == warp % 4: TMEM lane quarter this warp may read
+    constexpr int EPI_THREADS = epi_warps(MODE) * 32;
+    const int ew = (warp - EPI_WARP0) & 3;   // == warp % 4: TMEM lane quarter this warp may read
+    const int eg = (warp - EPI_WARP0) >> 2;  // emit modes: which half of the column chunks this warp handles
     const int et = threadIdx.x - EPI_WARP0 * 32;
     const float scale2 = p.scale_log2;
     const float neg_inf = __int_as_float(0xff800000);
@@ -307,16 +393,27 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
       Flusher flush;
       flush.row_valid = row < p.n_query;
-      flush.cf = __ldg(p.labels + n0);
-      flush.cl = __ldg(p.labels + n1 - 1);
-      flush.head_cut = n0 > 0 && __ldg(p.labels + n0 - 1) == flush.cf;
-      flush.tail_cut = n1 < p.n_support && __ldg(p.labels + n1) == flush.cl;
+      flush.cf = flush.cl = -1;
+      flush.head_cut = flush.tail_cut = false;
+      if (MODE == MODE_CLASS_LSE) {
+        flush.cf = __ldg(p.labels + n0);
+        flush.cl = __ldg(p.labels + n1 - 1);
+        flush.head_cut = n0 > 0 && __ldg(p.labels + n0 - 1) == flush.cf;
+        flush.tail_cut = n1 < p.n_support && __ldg(p.labels + n1) == flush.cl;
+      }
       const int srow = flush.row_valid ? row : 0;
       flush.p = &p;
       flush.row = srow;
       flush.row_off = size_t(srow) * p.n_classes;
       flush.side_row = p.side + (size_t(g) * p.n_query + srow) * 2;
       const float qn = (EPI == NW_EPI_EUCLID && flush.row_valid) ? __ldg(p.q_sqnorm + row) : 0.0f;
+      float e_z = 0.0f, e_p = 0.0f;
+      int e_qy = -1;
+      if (MODE == MODE_EMIT_INFLUENCE && flush.row_valid) {
+        e_z = __ldg(p.row_lse + row);
+        e_p = __ldg(p.p_query + row);
+        e_qy = __ldg(p.qlabel + row);
+      }
 
       // column metadata of a tile: additive term (|s|^2, or 0; +inf / -inf on padding columns) and labels
       float pre_cadd[BN / EPI_THREADS];
@@ -329,9 +426,9 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           const int j = j0 + et + r * EPI_THREADS;
           if (EPI == NW_EPI_EUCLID) pre_cadd[r] = j < n1 ? __ldg(p.s_sqnorm + j) : pos_inf;
           else pre_cadd[r] = j < n1 ? 0.0f : neg_inf;
-          pre_lab[r] = j < p.n_support ? __ldg(p.labels + j) : -1;
+          pre_lab[r] = (p.labels != nullptr && j < p.n_support) ? __ldg(p.labels + j) : -1;
         }
-        if (et == 0) pre_lab_next = (j0 + BN) < p.n_support ? __ldg(p.labels + j0 + BN) : -1;
+        if (et == 0) pre_lab_next = (p.labels != nullptr && (j0 + BN) < p.n_support) ? __ldg(p.labels + j0 + BN) : -1;
       };
       load_meta(t0);
 
@@ -360,6 +457,23 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // (Software-pipelining the TMEM loads one chunk ahead was measured: no gain, +40 registers.)
 #pragma unroll 1
         for (int c = 0; c < BN / 32; c += 2) {
+          if (MODE != MODE_CLASS_LSE) {
+            constexpr bool INFL = MODE == MODE_EMIT_INFLUENCE;
+            if (((c >> 1) & 1) != eg) continue;  // chunk pairs alternate between the two epilogue warp sets
+            float acc0[32], acc1[32];
+            tmem_ld_32x32(t_addr + c * 32, acc0);
+            tmem_ld_32x32(t_addr + (c + 1) * 32, acc1);
+            tmem_ld_wait();
+            const int row0 = (qg * NCTA + int(cta_rank)) * BM + ew * 32;
+            float(*stg)[33] = tail->stage[warp - EPI_WARP0];
+            emit_chunk<EPI, INFL>(acc0, meta.cadd + c * 32, meta.lab + c * 32, qn, p.scale_log2 * kLn2, e_z, e_p, e_qy,
+                                  stg, lane, p.emit_out, p.emit_ld, row0, p.n_query, j0 + c * 32, n1 - (j0 + c * 32),
+                                  p.emit_vec != 0);
+            emit_chunk<EPI, INFL>(acc1, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, qn, p.scale_log2 * kLn2, e_z,
+                                  e_p, e_qy, stg, lane, p.emit_out, p.emit_ld, row0, p.n_query, j0 + (c + 1) * 32,
+                                  n1 - (j0 + (c + 1) * 32), p.emit_vec != 0);
+            continue;
+          }
           float acc0[32], acc1[32];
           tmem_ld_32x32(t_addr + c * 32, acc0);
           tmem_ld_32x32(t_addr + (c + 1) * 32, acc1);
@@ -591,12 +705,13 @@ extern "C" int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t
 
 namespace nw {
 namespace k1 {
-template <int EPI, int NCTA>
+template <int EPI, int NCTA, int MODE = MODE_CLASS_LSE>
 static int launch_forward(const CUtensorMap& map_q, const CUtensorMap& map_s, const Params& p, int grid,
                           cudaStream_t stream) {
   static bool attr_set[64] = {false};  // function attributes are per device
-  auto kern = nw_forward_kernel<EPI, NCTA>;
-  constexpr size_t smem = smem_bytes<NCTA>();
+  auto kern = nw_forward_kernel<EPI, NCTA, MODE>;
+  constexpr size_t smem = smem_bytes<NCTA, MODE>();
+  static_assert(smem <= 232448, "shared memory budget exceeded");
   int dev = 0;
   NW_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -605,7 +720,7 @@ static int launch_forward(const CUtensorMap& map_q, const CUtensorMap& map_s, co
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3((EPI_WARP0 + epi_warps(MODE)) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -675,6 +790,12 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.chunks = plan.chunks;
   p.tiles_per_chunk = plan.tiles_per_chunk;
   p.scale_log2 = scale * kLog2e;
+  p.emit_out = nullptr;
+  p.emit_ld = 0;
+  p.emit_kind = 0;
+  p.emit_vec = 0;
+  p.row_lse = p.p_query = nullptr;
+  p.qlabel = nullptr;
   if (epilogue == NW_EPI_EUCLID) {
     rc = ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2>(map_q, map_s, p, plan.grid, stream)
                    : k1::launch_forward<NW_EPI_EUCLID, 1>(map_q, map_s, p, plan.grid, stream);
@@ -711,6 +832,71 @@ extern "C" int nw_forward_class_lse_peers(int epilogue, float scale, const void*
   return forward_impl(epilogue, scale, q_bf16, q_sqnorm, n_query, bank_bf16, s_sqnorm, labels, n_support, row_elems,
                       n_classes, tables_host, n_tables, rows_per_table, /*fill_local=*/false, side, side_elems,
                       static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
+                               const void* bank_bf16, const float* s_sqnorm, const int32_t* labels,
+                               int64_t n_support, int row_elems, int emit_kind, const float* row_lse,
+                               const float* p_query, const int32_t* qlabel, float* out, int64_t ld_out,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(epilogue == NW_EPI_EUCLID || epilogue == NW_EPI_LINEAR, NW_ERR_INVALID, "unknown epilogue %d", epilogue);
+  NW_REQUIRE(emit_kind == NW_EMIT_SCORES || emit_kind == NW_EMIT_INFLUENCE, NW_ERR_INVALID, "unknown emit kind %d",
+             emit_kind);
+  NW_REQUIRE(q_bf16 && bank_bf16 && out, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(epilogue != NW_EPI_EUCLID || (q_sqnorm && s_sqnorm), NW_ERR_INVALID,
+             "the euclidean epilogue needs q_sqnorm and s_sqnorm");
+  NW_REQUIRE(emit_kind != NW_EMIT_INFLUENCE || (labels && row_lse && p_query && qlabel), NW_ERR_INVALID,
+             "influence needs labels, row_lse, p_query and qlabel");
+  NW_REQUIRE(row_elems > 0 && row_elems % k1::BK == 0, NW_ERR_INVALID, "row_elems must be a positive multiple of 64");
+  NW_REQUIRE(ld_out >= n_support, NW_ERR_INVALID, "ld_out must be >= n_support");
+  NW_REQUIRE((reinterpret_cast<uintptr_t>(q_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(bank_bf16) & 15) == 0,
+             NW_ERR_INVALID, "bf16 operands must be 16-byte aligned");
+  int rc = nw_device_check();
+  if (rc != NW_OK) return rc;
+  nw_forward_plan_t plan;
+  rc = nw_forward_plan(n_query, n_support, &plan);
+  if (rc != NW_OK) return rc;
+  const int ncta = plan.cta_pair ? 2 : 1;
+  CUtensorMap map_q, map_s;
+  rc = k1::make_map(&map_q, q_bf16, uint64_t(n_query), uint64_t(row_elems), k1::BM);
+  if (rc != NW_OK) return rc;
+  rc = k1::make_map(&map_s, bank_bf16, uint64_t(n_support), uint64_t(row_elems), k1::BN / ncta);
+  if (rc != NW_OK) return rc;
+
+  k1::Params p = {};
+  p.q_sqnorm = q_sqnorm;
+  p.s_sqnorm = s_sqnorm;
+  p.labels = labels;
+  p.n_tables = 0;
+  p.n_query = n_query;
+  p.n_support = int(n_support);
+  p.n_classes = 1;
+  p.kblocks = row_elems / k1::BK;
+  p.q_groups = plan.q_tiles;
+  p.s_tiles = plan.s_tiles;
+  p.chunks = plan.chunks;
+  p.tiles_per_chunk = plan.tiles_per_chunk;
+  p.scale_log2 = scale * kLog2e;
+  p.emit_out = out;
+  p.emit_ld = ld_out;
+  p.emit_kind = emit_kind;
+  p.emit_vec = (ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+  p.row_lse = row_lse;
+  p.p_query = p_query;
+  p.qlabel = qlabel;
+  const int key = (epilogue == NW_EPI_EUCLID ? 0 : 4) + (ncta == 2 ? 2 : 0) + (emit_kind == NW_EMIT_INFLUENCE ? 1 : 0);
+  switch (key) {
+    case 0: rc = k1::launch_forward<NW_EPI_EUCLID, 1, k1::MODE_EMIT_SCORES>(map_q, map_s, p, plan.grid, stream); break;
+    case 1: rc = k1::launch_forward<NW_EPI_EUCLID, 1, k1::MODE_EMIT_INFLUENCE>(map_q, map_s, p, plan.grid, stream); break;
+    case 2: rc = k1::launch_forward<NW_EPI_EUCLID, 2, k1::MODE_EMIT_SCORES>(map_q, map_s, p, plan.grid, stream); break;
+    case 3: rc = k1::launch_forward<NW_EPI_EUCLID, 2, k1::MODE_EMIT_INFLUENCE>(map_q, map_s, p, plan.grid, stream); break;
+    case 4: rc = k1::launch_forward<NW_EPI_LINEAR, 1, k1::MODE_EMIT_SCORES>(map_q, map_s, p, plan.grid, stream); break;
+    case 5: rc = k1::launch_forward<NW_EPI_LINEAR, 1, k1::MODE_EMIT_INFLUENCE>(map_q, map_s, p, plan.grid, stream); break;
+    case 6: rc = k1::launch_forward<NW_EPI_LINEAR, 2, k1::MODE_EMIT_SCORES>(map_q, map_s, p, plan.grid, stream); break;
+    default: rc = k1::launch_forward<NW_EPI_LINEAR, 2, k1::MODE_EMIT_INFLUENCE>(map_q, map_s, p, plan.grid, stream); break;
+  }
+  return rc;
 }
 
 extern "C" int nw_logp_from_class_lse(const float* class_lse, int n_query, int n_classes, float* logp,

@@ -59,3 +59,9 @@ def support_influence_from_labels(softmaxes, qlabel_idx, sweights, slabel_idx):
     check(lib.nw_support_influence(ptr(P), ptr(qy), ptr(w), ptr(sy), b, 1, n, c, ptr(out), stream_of(dev)),
           "nw_support_influence")
     return out[:, 0, :]
+
+
+def support_influence_from_features(qfeat, bank, qlabel_idx, scale: float = 1.0, source_order: bool = True):
+    """Influence of every bank row on every query computed directly from the query features and a SupportBank
+    (two tensor-core passes, SupportBank.support_influence): no (bs, num_support) weight matrix is needed."""
+    return bank.support_influence(qfeat, qlabel_idx, scale, source_order)

@@ -141,3 +141,44 @@ def test_random_shapes_against_oracle(cuda_lib):
         assert perr < 5e-5, (trial, B, len(y), d, C, kind, perr)
         empty = np.flatnonzero(sizes == 0)
         assert np.array_equal(out[:, empty], np.full((B, len(empty)), np.log(np.float32(1e-12)), np.float32))
+
+
+@pytest.mark.parametrize("kind", ["euclidean", "cosine", "dotproduct", "hypersphere_euclidean"])
+def test_dense_scores_on_tensor_cores(cuda_lib, kind):
+    """SupportBank.scores: the kernel(x, y) matrix through the TMA + tcgen05 mainloop (emit epilogue), on an
+    UNSORTED support (columns must come back in the caller's order), ragged N, B across a tile edge."""
+    from nwhead_b200 import SupportBank
+
+    rng = np.random.default_rng(8)
+    B, N, d, C = 150, 1001, 72, 11
+    y = rng.integers(0, C, N).astype(np.int64)
+    s = rng.normal(size=(N, d)).astype(np.float32)
+    q = rng.normal(size=(B, d)).astype(np.float32)
+    bank = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, kind, "bf16x3")
+    got = bank.scores(torch.from_numpy(q).to(DEV)).cpu().numpy()
+    ref = O.pairwise_scores(q, s, kind)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 5e-4 * max(1.0, np.abs(ref).max())
+    plain = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, kind, "bf16")
+    got1 = plain.scores(torch.from_numpy(q).to(DEV)).cpu().numpy()
+    assert np.abs(got1 - ref).max() < 0.08 * max(1.0, np.abs(ref).max() / 8)
+
+
+def test_support_influence_from_features(cuda_lib):
+    """Influence computed from features (two tensor-core passes) == the reference formula fed with the exact
+    softmax weights (oracle), BASELINE config 5 shapes scaled down."""
+    from nwhead_b200 import SupportBank
+
+    C, per, d, B = 20, 50, 512, 96
+    q, s, y, qy = clustered_features(C, per, d, B, seed=21)
+    bank = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, "euclidean", "bf16x3")
+    got = bank.support_influence(torch.from_numpy(q).to(DEV), torch.from_numpy(qy).to(DEV)).cpu().numpy()
+    sc = O.pairwise_scores(q, s, "euclidean")
+    w = np.exp(sc - sc.max(1, keepdims=True))
+    w /= w.sum(1, keepdims=True)
+    P = np.zeros((B, C))
+    np.add.at(P.T, y, w.T)
+    ref = O.support_influence(P, qy, w, y)
+    ok = np.isfinite(ref) & (np.abs(ref) > 1e-12)
+    assert np.array_equal(np.sign(got[ok]), np.sign(ref[ok]))
+    assert np.allclose(got[ok], ref[ok], rtol=5e-3, atol=1e-7)

@@ -135,6 +135,26 @@ def cfg5_influence():
          cores=os.cpu_count(), kind="port")
 
 
+def cfg5_from_features():
+    """support_influence computed FROM FEATURES (d=512) on the tensor cores: fused forward + emit pass."""
+    B, N, C, d = 10000, 50000, 200, 512
+    feats, labels, mu = synth(N, d, C, 55)
+    g = torch.Generator(device=DEV).manual_seed(56)
+    qy = torch.randint(0, C, (B,), generator=g, device=DEV)
+    q = torch.relu(mu[qy] + torch.randn(B, d, generator=g, device=DEV) + 0.5)
+    for prec in ("bf16x3", "bf16"):
+        bank = SupportBank.build(feats, labels, C, "euclidean", prec)
+        ms = timed(lambda: bank.support_influence(q, qy, source_order=False), iters=5, warm=2)
+        k = 3 if prec == "bf16x3" else 1
+        flops = 2 * 2.0 * B * N * d * k  # two GEMM passes
+        emit(config=f"cfg5 support_influence from features B={B} N={N} d={d} C={C} ({prec})", ms=ms,
+             pairs_per_s=B * N / ms * 1e3, tflops=flops / ms / 1e9, out_GB=B * N * 4 / 1e9,
+             note="class-LSE pass + emit pass; the (B,N) weight matrix is never written; 4 B/pair of HBM output")
+        ms = timed(lambda: bank.scores(q, source_order=False), iters=5, warm=2)
+        emit(config=f"dense scores B={B} N={N} d={d} ({prec}) via nw_forward_emit", ms=ms,
+             tflops=2.0 * B * N * d * k / ms / 1e9, out_GBs=B * N * 4 / ms / 1e6)
+
+
 def cfg3_torch_gpu_unfused(feats, labels, n_classes):
     """The reference's own op sequence on the B200 through stock PyTorch (cuBLAS cdist + softmax + one-hot bmm).
     It materialises (B,N,d), so only B=1 fits comfortably."""
@@ -218,6 +238,7 @@ def main():
         cfg1_cfg2_with_resnet18()
     cfg2_episodic()
     cfg5_influence()
+    cfg5_from_features()
     torch.cuda.empty_cache()
     feats, labels, _ = synth(1280000, 2048, 1000, 1234)
     bank_build(feats, labels, 1000)

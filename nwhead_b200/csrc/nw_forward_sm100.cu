@@ -7,15 +7,22 @@
 // The (B, N) score matrix never leaves the SM.  Output is the per-class log-sum-exp table
 // class_lse (B, C); nw_logp_from_class_lse turns it into log(P + 1e-12).
 //
-// Work decomposition: the bank is cut into `chunks` contiguous ranges of 256-row support tiles; a work
-// unit is (chunk, 128-query tile).  Units of one chunk are adjacent in the unit order, so the persistent
-// CTAs of one wave sweep the same support tiles at the same time and the bank is read from HBM once
-// (L2 hits for the other query tiles).  Inside a unit the epilogue carries (running max, class sum)
-// in registers across tiles; classes cut by a chunk boundary go to `side` and are merged in fixed order
-// by merge_side_kernel (deterministic, no atomics).
+// Operands are k-block-major bf16 ([row_elems/64][rows][64], see nw_bank.cu): every TMA box is one contiguous
+// run of 128-byte swizzle rows.  Two tile shapes: a single CTA computes 128 queries x 256 supports (UMMA
+// M=128), a CTA pair (cluster of 2, cta_group::2) 256 x 256 (UMMA M=256) with each CTA staging half of the
+// support tile.  TMEM holds two 256-column accumulators so the epilogue of one tile overlaps the MMAs of the next.
 //
-// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-7 epilogue (one thread per query row = TMEM lane).
+// Work decomposition (persistent): the bank is cut into `chunks` contiguous ranges of 256-row support tiles; a
+// work unit is (chunk, query group of 128 or 256 rows).  Units of one chunk are adjacent in the unit order, so
+// the workers of a wave sweep the same support tiles at the same time and the bank is read from HBM ~once (L2
+// hits for the other query groups).  Inside a unit the epilogue carries (running max, class sum) in registers
+// across tiles; classes cut by a chunk boundary go to `side` and are merged in fixed order by merge_side_kernel
+// (deterministic, no atomics).  Results can be stored to several tables (peer GPUs over NVLink) for the
+// bank-sharded multi-GPU path.
+//
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator, warps 4-7 epilogue
+// (one thread per query row = TMEM lane); the emit modes (dense scores / support influence, no state along
+// the columns) add warps 8-11 as a second epilogue set.
 
 #include <stdlib.h>
 

@@ -272,6 +272,23 @@ class SupportBank:
         rows of the tensor the bank was built from."""
         return self._emit(q, scale, _abi.EMIT_SCORES, source_order=source_order)
 
+    def topk(self, q: torch.Tensor, k: int, scale: float = 1.0, source_order: bool = True,
+             query_chunk: int = 512) -> torch.Tensor:
+        """Indices (B, k) of the k best-scoring support rows per query, best first: tensor-core dense scores
+        (nw_forward_emit) + the bitonic ranking (nw_rank_rows), chunked over queries to bound memory.  The
+        ranking has the accuracy of the bank's operands: near-fp32 for 'bf16x3' banks, ~1e-2 in score for
+        'bf16' (NWNet.get_neighbors keeps the exact fp32 path by default)."""
+        from .utils import rank_rows
+
+        out = []
+        for i in range(0, q.shape[0], query_chunk):
+            sc = self._emit(q[i:i + query_chunk], scale, _abi.EMIT_SCORES)
+            idx = rank_rows(sc.contiguous(), k)
+            if source_order and self.perm is not None:
+                idx = self.perm[idx]
+            out.append(idx)
+        return torch.cat(out, dim=0)
+
     def support_influence(self, q: torch.Tensor, qlabel: torch.Tensor, scale: float = 1.0,
                           source_order: bool = True) -> torch.Tensor:
         """support_influence (reference util/metric.py:23-50) computed from FEATURES in two tensor-core passes:

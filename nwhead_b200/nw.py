@@ -316,11 +316,18 @@ class NWNet(nn.Module):
         return (torch.cat(feats, dim=0), torch.cat(labels, dim=0), torch.cat(meta, dim=0), sep_feats, sep_labels,
                 sep_meta)
 
-    def get_neighbors(self, x, k=None):
+    def get_neighbors(self, x, k=None, exact=True):
         '''Returns indices of nearest neighbors of x in the support set, nearest first
-        (reference nwhead/nw.py:245-249: the full ranking; pass k to keep only the first k).'''
+        (reference nwhead/nw.py:245-249: the full ranking; pass k to keep only the first k).
+        exact=True  : fp32 exact-difference scores (nw_direct_scores) + full ranking, bit-exact with the
+                      reference on ties-free data.
+        exact=False : tensor-core scores against the precomputed bank (SupportBank.topk) for large banks /
+                      batches; ranking accuracy is that of the bank's operand precision.'''
         from .utils import rank_rows
 
         qfeat = self.featurizer(x).detach()
+        if not exact:
+            bank = self.support_eval.full_bank
+            return bank.topk(qfeat, len(bank) if k is None else k, self.kernel.scale_value())
         distances = self.kernel(qfeat, self.full_feat)
         return rank_rows(distances, k)

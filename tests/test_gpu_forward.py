@@ -182,3 +182,23 @@ def test_support_influence_from_features(cuda_lib):
     ok = np.isfinite(ref) & (np.abs(ref) > 1e-12)
     assert np.array_equal(np.sign(got[ok]), np.sign(ref[ok]))
     assert np.allclose(got[ok], ref[ok], rtol=5e-3, atol=1e-7)
+
+
+def test_tensor_core_topk_matches_exact_ranking(cuda_lib):
+    """SupportBank.topk (emit scores + bitonic ranking) on a shuffled support: with the 3-product operands the
+    ranking equals the exact float64 ranking on data whose score gaps exceed the operand rounding."""
+    from nwhead_b200 import SupportBank
+
+    rng = np.random.default_rng(12)
+    B, N, d, C, k = 70, 3000, 64, 30, 10
+    y = rng.integers(0, C, N).astype(np.int64)
+    s = rng.normal(size=(N, d)).astype(np.float32)
+    q = rng.normal(size=(B, d)).astype(np.float32)
+    bank = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, "euclidean", "bf16x3")
+    got = bank.topk(torch.from_numpy(q).to(DEV), k, query_chunk=32).cpu().numpy()
+    sc = O.pairwise_scores(q, s, "euclidean")
+    ref = np.argsort(-sc, axis=1, kind="stable")[:, :k + 1]
+    gaps = -np.diff(np.take_along_axis(sc, ref, 1), axis=1)
+    clear = (gaps > 1e-3).all(axis=1)  # rows whose first k+1 neighbours are separated by more than the rounding
+    assert clear.mean() > 0.5
+    assert np.array_equal(got[clear], ref[clear, :k])

@@ -302,9 +302,40 @@ class SupportBank:
         return self._emit(q, scale, _abi.EMIT_INFLUENCE, row_lse=z, p_query=p, qlabel=qy.to(torch.int32).contiguous(),
                           source_order=source_order)
 
+    def graphed(self, batch: int, scale: float = 1.0) -> "GraphedForward":
+        """CUDA-graph replay of forward() for a fixed batch size (see GraphedForward)."""
+        return GraphedForward(self, batch, scale)
+
     def forward(self, q: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
         """log(softmax-weighted label aggregation + 1e-12): NWHead.forward (nwhead/nw.py:266-289)."""
         return logp_from_class_lse(self.class_lse(q, scale))
+
+
+class GraphedForward:
+    """SupportBank.forward for a fixed batch size captured in a CUDA graph: query prep, -inf fill, fused forward,
+    chunk merge and finalise replay as ONE graph launch (small-batch predict is launch-latency bound: five
+    kernel launches + four ctypes calls per step otherwise).  The result tensor is reused by the next call."""
+
+    def __init__(self, bank: "SupportBank", batch: int, scale: float = 1.0):
+        self.bank, self.batch = bank, batch
+        dev = bank.device
+        self.q = torch.zeros((batch, bank.d), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up outside capture (kernel attributes, allocator pools)
+                bank.forward(self.q, scale)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = bank.forward(self.q, scale)
+
+    def __call__(self, q: torch.Tensor) -> torch.Tensor:
+        if q.shape != self.q.shape:
+            raise ValueError(f"graphed forward was captured for {tuple(self.q.shape)}, got {tuple(q.shape)}")
+        self.q.copy_(q, non_blocking=True)
+        self.graph.replay()
+        return self.out
 
 
 def logp_from_class_lse(class_lse: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

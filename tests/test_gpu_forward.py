@@ -202,3 +202,18 @@ def test_tensor_core_topk_matches_exact_ranking(cuda_lib):
     clear = (gaps > 1e-3).all(axis=1)  # rows whose first k+1 neighbours are separated by more than the rounding
     assert clear.mean() > 0.5
     assert np.array_equal(got[clear], ref[clear, :k])
+
+
+def test_cuda_graph_replay_matches_eager(cuda_lib):
+    from nwhead_b200 import SupportBank
+
+    q, s, y, _ = clustered_features(200, 29, 512, 8, seed=1)  # BASELINE config 1 head shape
+    bank = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), 200, "euclidean", "bf16")
+    qd = torch.from_numpy(q).to(DEV)
+    eager = bank.forward(qd)
+    fwd = bank.graphed(8)
+    assert torch.equal(fwd(qd), eager)
+    q2 = torch.roll(qd, 3, dims=0)
+    assert torch.equal(fwd(q2), torch.roll(eager, 3, dims=0))
+    with pytest.raises(ValueError):
+        fwd(qd[:4])

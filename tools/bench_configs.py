@@ -214,6 +214,9 @@ def cfg1_cfg2_with_resnet18():
         bank = net.support_eval.full_bank
         ms = timed(lambda: bank.forward(f), 50, 10)
         emit(config="cfg1 head only: bank 5800x512, batch 8 (fused forward + finalise)", ms=ms)
+        fwd = bank.graphed(8)
+        ms = timed(lambda: fwd(f), 50, 10)
+        emit(config="cfg1 head only, CUDA-graph replay (SupportBank.graphed)", ms=ms)
     net.train()
     opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.9, nesterov=True)
     y = torch.tensor([3, 17, 17, 42, 99, 150, 199, 0], device=DEV)

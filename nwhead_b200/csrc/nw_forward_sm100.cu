@@ -131,10 +131,16 @@ struct Flusher {
     if (!row_valid) return;
     if (cls == cf && head_cut) side_row[0] = v;
     else if (cls == cl && tail_cut) side_row[1] = v;
-    else if (p->rows_per_table > 0) p->lse[row / p->rows_per_table][row_off + cls] = v;
-    else {
+    else store(cls, v);
+  }
+  // single-row class that lies inside the unit: its class log-sum-exp is the score itself
+  __device__ __forceinline__ void single(int cls, float v) const {
+    if (row_valid) store(cls, v);
+  }
+  __device__ __noinline__ void store(int cls, float v) const {
+    if (p->rows_per_table > 0) p->lse[row / p->rows_per_table][row_off + cls] = v;
+    else
       for (int r = 0; r < p->n_tables; ++r) p->lse[r][row_off + cls] = v;
-    }
   }
   int row;
 };
@@ -178,21 +184,24 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      float e;
-      if (EPI == NW_EPI_EUCLID) e = ex2_approx(fmaf(sqrt_approx(fmaxf(acc[i], 0.0f)), -kLog2e, -m));
-      else e = ex2_approx(acc[i] - m);
-      l += e;
+      float arg;  // score * log2(e) - m
+      if (EPI == NW_EPI_EUCLID) arg = fmaf(sqrt_approx(fmaxf(acc[i], 0.0f)), -kLog2e, -m);
+      else arg = acc[i] - m;
+      l += ex2_approx(arg);
       if (emask & (1u << i)) {  // warp-uniform: column i is the last row of its class (in this unit)
-        flush(lab[i], m, l);
+        if (i > 0 && (emask & (1u << (i - 1))) && !(flush.tail_cut && lab[i] == flush.cl)) {
+          // the previous column closed its class too, so this class has ONE row here (cluster / random mode
+          // banks: one support per class): its log-sum-exp is simply its score; stored inline, no call
+          flush.single(lab[i], (arg + m) * kLn2);
+        } else {
+          flush(lab[i], m, l);
+        }
         l = 0.0f;
       }
     }
   }
 }
 
-// MODE_EMIT: one 32-column chunk.  Every thread turns the 32 accumulators of ITS query row into output values,
-// the warp transposes the 32x32 block through shared memory, and each store instruction then writes four rows x
-// 128 contiguous bytes (full cache lines) instead of 32 scattered 16-byte pieces.
 template <int EPI, bool INFLUENCE>
 __device__ __forceinline__ void emit_chunk(float (&acc)[32], const float* __restrict__ cadd,
                                            const int* __restrict__ lab, float qn, float scale, float z,

@@ -63,7 +63,8 @@ class FullModePredictor:
         slot.busy = True
         self.next += 1
         compute = torch.cuda.current_stream(self.bank.device)
-        self.copy_stream.wait_stream(compute)  # the slot's device buffers may still be read by older work
+        # The slot's previous use was retired by result() (d2h_done implies its compute finished), so the upload
+        # may start right away and overlap the forward of the batch submitted before this one.
         with torch.cuda.stream(self.copy_stream):
             slot.q_slice.copy_(q_host, non_blocking=True)
             slot.h2d_done.record(self.copy_stream)

@@ -67,10 +67,10 @@ class FullModePredictor:
         # may start right away and overlap the forward of the batch submitted before this one.
         with torch.cuda.stream(self.copy_stream):
             slot.q_slice.copy_(q_host, non_blocking=True)
+            if self.world > 1:  # replicate the queries over NVLink on the copy stream too (overlaps the forward)
+                dist.all_gather_into_tensor(slot.q_full, slot.q_slice, group=self.group)
             slot.h2d_done.record(self.copy_stream)
         compute.wait_event(slot.h2d_done)
-        if self.world > 1:
-            dist.all_gather_into_tensor(slot.q_full, slot.q_slice, group=self.group)
         mine = self.sharded.class_lse_rows(slot.q_full, self.scale)  # this rank's rows of the merged table
         logp_from_class_lse(mine, out=slot.logp)
         slot.compute_done.record(compute)

@@ -212,6 +212,8 @@ class SupportBank:
     def class_lse(self, q: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
         """(B, C) per-class log-sum-exp of the scores against this bank (−inf for absent classes)."""
         _abi.require_cuda(q, self.feats_bf16)
+        if q.shape[0] == 0:  # empty batch: nothing to launch
+            return torch.empty((0, self.n_classes), dtype=torch.float32, device=self.device)
         q_bf16, q_sq = self.prepare_queries(q)
         return self.class_lse_prepared(q_bf16, q_sq, scale)
 
@@ -341,6 +343,8 @@ class GraphedForward:
 def logp_from_class_lse(class_lse: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = load()
     b, c = class_lse.shape
+    if b == 0:
+        return class_lse.clone() if out is None else out
     if not class_lse.is_contiguous():
         class_lse = class_lse.contiguous()
     if out is None:

@@ -155,6 +155,10 @@ class NWHead(nn.Module):
         needs_grad = torch.is_grad_enabled() and (
             x.requires_grad or sx.requires_grad or (logit_scale is not None and logit_scale.requires_grad))
         n = sx.shape[-2]
+        if x.shape[0] == 0:  # empty query batch, as the reference: an empty (0, n_classes) result
+            return x.new_empty((0, self.n_classes))
+        if n == 0:
+            raise ValueError("NWHead needs at least one support row")
         if needs_grad or sx.dim() == 3 or n < MM_PATH_MIN_ROWS:
             return _NWDirectFunction.apply(x, sx, sy, logit_scale, kind, self.n_classes)
         bank = SupportBank.build(sx, sy, self.n_classes, kind, self.precision)

@@ -217,3 +217,26 @@ def test_cuda_graph_replay_matches_eager(cuda_lib):
     assert torch.equal(fwd(q2), torch.roll(eager, 3, dims=0))
     with pytest.raises(ValueError):
         fwd(qd[:4])
+
+
+def test_empty_and_degenerate_inputs(cuda_lib):
+    import nwhead_b200
+    from nwhead_b200 import SupportBank
+
+    q, s, y, _ = clustered_features(5, 10, 32, 4, seed=2)
+    bank = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), 5, "euclidean", "bf16")
+    empty = bank.forward(torch.empty((0, 32), device=DEV))
+    assert tuple(empty.shape) == (0, 5)
+    head = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), 5)
+    out = head(torch.empty((0, 32), device=DEV), torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV))
+    assert tuple(out.shape) == (0, 5)
+    with pytest.raises(ValueError):
+        head(torch.from_numpy(q).to(DEV), torch.empty((0, 32), device=DEV), torch.empty((0,), dtype=torch.int64, device=DEV))
+    # a single query against a single support row: P = 1 for its class, log(1e-12) elsewhere
+    one = head(torch.from_numpy(q[:1]).to(DEV), torch.from_numpy(s[:1]).to(DEV), torch.from_numpy(y[:1]).to(DEV)).cpu().numpy()
+    assert abs(one[0, y[0]]) < 1e-6 and np.allclose(np.delete(one[0], y[0]), np.log(np.float32(1e-12)))
+    # one query, one class in the bank (tensor-core path, N > 25)
+    yy = np.zeros(40, np.int64)
+    b1 = SupportBank.build(torch.from_numpy(s[:40]).to(DEV), torch.from_numpy(yy).to(DEV), 3, "cosine", "bf16")
+    o1 = b1.forward(torch.from_numpy(q[:1]).to(DEV)).cpu().numpy()
+    assert abs(o1[0, 0]) < 1e-6 and np.allclose(o1[0, 1:], np.log(np.float32(1e-12)))

@@ -195,7 +195,7 @@ class NWNet(nn.Module):
         :param feat_dim: Output dimension of featurizer
         :param proj_dim: If > 0, adds a linear projection down to proj_dim after featurizer
         :param kernel_type: Type of kernel to use
-        :param train_type: 'random' ('irm' is outside the accelerated path)
+        :param train_type: Type of training strategy, choose from ['random', 'irm']
         :param n_way: Number of classes to put in support during training
         :param n_shot: Number of datapoints per class to sample for support during training
         :param n_shot_random / n_shot_full / n_shot_cluster: per-class support sizes of the eval modes
@@ -255,13 +255,19 @@ class NWNet(nn.Module):
         Perform prediction given test images.
 
         :param x: Input datapoints (bs, nch, l, w)
-        :param mode: Inference mode. One of ['random', 'full', 'cluster', 'knn']
+        :param mode: Inference mode. One of ['random', 'full', 'cluster', 'ensemble', 'knn']
         '''
         qfeat = self.featurizer(x)
         support = self.support_eval.get_support(mode, x=qfeat)
         if self.debug_mode:
             print('qx shape:', x.shape)
-        if isinstance(support, SupportBank):
+        if mode == 'ensemble':
+            # mean over environments of the per-environment class probabilities (reference nwhead/nw.py:143-154)
+            probs = 0
+            for bank in support:
+                probs = probs + self.nwhead(qfeat, bank).exp()
+            out = torch.log(probs / len(support))
+        elif isinstance(support, SupportBank):
             out = self.nwhead(qfeat, support)
         else:
             sfeat, sy = support

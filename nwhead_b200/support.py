@@ -13,21 +13,32 @@ from .utils import (DatasetMetadata, FeatureDataset, FullDataset, InfiniteUnifor
 
 
 class SupportSet:
-    '''Support set base class for NW (reference nwhead/support.py:7-56).  Environment / IRM splitting
-    (env_array, lists of datasets) is outside the accelerated path and is not provided.'''
+    '''Support set base class for NW (reference nwhead/support.py:7-56).
+
+    env_array: optional array with one integer environment indicator per support item (IRM training and
+    mode='ensemble').  Without it the whole dataset is a single environment.  (The reference's third form, a
+    list of datasets, reads `.targets` of the list itself and cannot be constructed; it is not provided.)'''
 
     def __init__(self, support_set, n_classes, env_array=None):
-        if env_array is not None or isinstance(support_set, (list, tuple)):
-            raise NotImplementedError(
-                'environment-split supports (IRM training, mode="ensemble") are outside the B200 hot path')
+        if isinstance(support_set, (list, tuple)):
+            raise NotImplementedError('pass one dataset plus env_array; lists of datasets are not supported')
         self.y_array = np.array(support_set.targets)
         self.n_classes = n_classes
-        self.env_array = np.zeros(len(support_set))
+        self.env_array = np.zeros(len(support_set)) if env_array is None else np.asarray(env_array)
         self.combined_dataset = DatasetMetadata(support_set, self.env_array)
-        self.env_map = {0.0: 0}
-        env = torch.utils.data.Subset(self.combined_dataset, np.arange(len(support_set)))
-        env.targets = self.y_array
-        self.env_datasets = [env]
+        self.env_datasets = self._separate_env_datasets(self.combined_dataset)
+
+    def _separate_env_datasets(self, combined_dataset):
+        '''One Subset per environment value, in sorted order of the values (reference nwhead/support.py:47-56).'''
+        env_datasets = []
+        self.env_map = {}
+        for i, attr in enumerate(np.unique(self.env_array)):
+            self.env_map[attr] = i
+            indices = (self.env_array == attr).nonzero()[0]
+            env = torch.utils.data.Subset(combined_dataset, indices)
+            env.targets = self.y_array[indices]
+            env_datasets.append(env)
+        return env_datasets
 
 
 class SupportSetTrain(SupportSet):
@@ -35,16 +46,21 @@ class SupportSetTrain(SupportSet):
 
     def __init__(self, support_set, n_classes, train_type, n_shot, n_way=None, env_array=None):
         super().__init__(support_set, n_classes, env_array)
-        if train_type != 'random':
-            raise NotImplementedError('train_type="irm" is outside the B200 hot path')
         self.train_type = train_type
         self.n_shot = n_shot
         self.n_way = n_way
-        self.train_iter = InfiniteUniformClassLoader(self.combined_dataset, self.n_shot, self.n_way)
+        if train_type == 'random':
+            self.train_iter = InfiniteUniformClassLoader(self.combined_dataset, self.n_shot, self.n_way)
+        else:  # 'irm': one sampler per environment, every class of the environment, n_shot each
+            self.train_iter = [iter(InfiniteUniformClassLoader(env, self.n_shot)) for env in self.env_datasets]
 
     def get_support(self, y):
-        '''Samples a support for training: n_way classes that include every query class, n_shot items
-        each (host numpy sampling in the reference's call order).'''
+        '''Samples a support for training (host numpy sampling in the reference's call order).
+        'random': n_way classes that include every query class, n_shot items each.
+        'irm'   : a random environment, then n_shot items of each of its classes.'''
+        if self.train_type == 'irm':
+            train_iter = np.random.choice(self.train_iter)
+            return train_iter.next()
         return self.train_iter.next(y)
 
 
@@ -68,6 +84,11 @@ class SupportSetEval(SupportSet):
         self.full_feat, self.full_y, self.full_meta = sfeat, sy, smeta
         self.full_feat_sep, self.full_y_sep, self.full_meta_sep = sfeat_env, sy_env, smeta_env
         self.full_bank = SupportBank.build(sfeat, sy, self.n_classes, self.kernel_type, self.precision)
+        # one bank per environment for mode='ensemble' (reference nwhead/nw.py:143-154)
+        self.env_banks = None
+        if sfeat_env is not None and len(sfeat_env) > 1:
+            self.env_banks = [SupportBank.build(f, y, self.n_classes, self.kernel_type, self.precision)
+                              for f, y in zip(sfeat_env, sy_env)]
 
         # Cluster: n_shot_cluster == 1 -> class means reduced on the GPU from the fp32 features
         if self.n_shot_cluster != 1:
@@ -90,8 +111,8 @@ class SupportSetEval(SupportSet):
         self.knn = KNN(self.full_feat, self.full_y, n_neighbors=self.n_neighbors)
 
     def get_support(self, mode, x=None):
-        '''Returns the support for an inference mode: a SupportBank for 'full' / 'cluster' / 'random',
-        a (features, labels) pair for 'knn'.'''
+        '''Returns the support for an inference mode: a SupportBank for 'full' / 'cluster' / 'random', a list of
+        per-environment SupportBanks for 'ensemble', a (features, labels) pair for 'knn'.'''
         try:
             if mode == 'random':
                 idx = torch.as_tensor(self.random_iter.sample_indices(), device=self.full_bank.device)
@@ -104,8 +125,10 @@ class SupportSetEval(SupportSet):
                 return self.cluster_bank
             elif mode == 'knn':
                 return self.knn(x)
-            elif mode in ('ensemble', 'hnsw'):
-                raise NotImplementedError(f'mode={mode!r} is outside the B200 hot path')
+            elif mode == 'ensemble':
+                return self.env_banks if self.env_banks is not None else [self.full_bank]
+            elif mode == 'hnsw':
+                raise NotImplementedError("mode='hnsw' needs hnswlib and is outside the B200 hot path")
             else:
                 raise NotImplementedError
         except AttributeError:

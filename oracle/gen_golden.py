@@ -202,6 +202,37 @@ def nwnet_flow(ref):
     return out
 
 
+def nwnet_env_flow(ref):
+    """Environment-split supports: mode='ensemble' inference and train_type='irm' sampling
+    (nwhead/support.py:17-56, 74-93; nwhead/nw.py:143-154)."""
+    out = {}
+    C = 6
+    ds = TinyDataset(80, C, seed=11)
+    env = np.array([(i // 3) % 2 for i in range(80)])
+    feat = tiny_featurizer()
+    out["env"] = env
+    net = ref.NWNet(feat, C, support_dataset=ds, feat_dim=16, kernel_type="euclidean", n_shot=2, n_way=4,
+                    n_shot_random=2, n_shot_full=5, n_shot_cluster=1, n_neighbors=3, env_array=env, device="cpu")
+    net.eval()
+    g = torch.Generator().manual_seed(99)
+    xq = torch.randn(7, 3, 8, 8, generator=g)
+    with torch.no_grad():
+        net.precompute()
+        out["full_y"] = net.full_y
+        out["env_sizes"] = torch.tensor([len(f) for f in net.support_eval.full_feat_sep])
+        out["pred_full"] = net.predict(xq, mode="full")
+        out["pred_cluster"] = net.predict(xq, mode="cluster")
+        out["pred_ensemble"] = net.predict(xq, mode="ensemble")
+    irm = ref.NWNet(feat, C, support_dataset=ds, feat_dim=16, kernel_type="euclidean", train_type="irm", n_shot=2,
+                    env_array=env, device="cpu")
+    irm.train()
+    np.random.seed(2024)
+    yq = torch.tensor([0, 1, 2, 3])
+    logp = irm(xq[:4].clone(), yq)
+    out["irm_train_logp"] = logp.detach()
+    return out
+
+
 def save(name, d):
     arrs = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
     path = os.path.join(GOLD, name + ".npz")
@@ -218,6 +249,7 @@ def main():
     save("influence", influence_cases(ref))
     save("clusters", cluster_cases(ref))
     save("nwnet_flow", nwnet_flow(ref))
+    save("nwnet_env_flow", nwnet_env_flow(ref))
     print("oracle and torch port agree with the reference on every generated case")
 
 

@@ -50,3 +50,8 @@ def cuda_lib():
     lib = _abi.load()
     _abi.check(lib.nw_device_check(), "nw_device_check")
     return lib
+
+
+@pytest.fixture(scope="session")
+def golden_env_flow():
+    return load_golden("nwnet_env_flow")

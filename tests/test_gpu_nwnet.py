@@ -59,9 +59,11 @@ def test_precompute_predict_neighbors(cuda_lib, golden_flow, kind):
         assert np.abs(np.exp(out) - np.exp(g[f"{kind}/pred_knn"])).max() < 1e-3
         with pytest.raises(NotImplementedError):
             net.predict(xq, mode="bogus")
-        for mode in ("ensemble", "hnsw"):
-            with pytest.raises(NotImplementedError):
-                net.predict(xq, mode=mode)
+        with pytest.raises(NotImplementedError):
+            net.predict(xq, mode="hnsw")
+        # a single environment: the ensemble of one equals full mode (reference nwhead/nw.py:143-154)
+        ens = net.predict(xq, mode="ensemble").cpu().numpy()
+        assert np.abs(np.exp(ens) - np.exp(g[f"{kind}/pred_full"])).max() < 1e-3
         if kind == "euclidean":
             nb = net.get_neighbors(xq).cpu().numpy()
             assert nb.shape == g[f"{kind}/neighbors"].shape and nb.dtype == np.int64
@@ -108,3 +110,36 @@ def test_return_mask_and_functional_support(cuda_lib, golden_flow):
         net.precompute()
         out, m = net.predict(x, mode="full")
     assert m.all() and out.shape == (4, 6)
+
+
+def test_environments_ensemble_and_irm(cuda_lib, golden_flow, golden_env_flow):
+    """env_array supports: per-environment banks, mode='ensemble' (mean of per-environment probabilities) and
+    train_type='irm' sampling, against the reference run in tests/golden/nwnet_env_flow.npz."""
+    import nwhead_b200
+
+    g, e = golden_flow, golden_env_flow
+    feat = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(192, 16), torch.nn.ReLU())
+    with torch.no_grad():
+        feat[1].weight.copy_(torch.from_numpy(g["W"]))
+        feat[1].bias.copy_(torch.from_numpy(g["b"]))
+    ds = TinyDataset(g["ds_x"], g["ds_y"])
+    net = nwhead_b200.NWNet(feat, 6, support_dataset=ds, feat_dim=16, kernel_type="euclidean", n_shot=2, n_way=4,
+                            n_shot_random=2, n_shot_full=5, n_shot_cluster=1, n_neighbors=3, env_array=e["env"],
+                            device=DEV).to(DEV)
+    net.eval()
+    xq = torch.from_numpy(g["xq"]).to(DEV)
+    with torch.no_grad():
+        net.precompute()
+        assert np.array_equal(net.full_y.cpu().numpy(), e["full_y"])
+        assert [len(b) for b in net.support_eval.env_banks] == e["env_sizes"].tolist()
+        for mode in ("full", "cluster", "ensemble"):
+            out = net.predict(xq, mode=mode).cpu().numpy()
+            assert np.abs(np.exp(out) - np.exp(e[f"pred_{mode}"])).max() < 1e-3, mode
+    irm = nwhead_b200.NWNet(feat, 6, support_dataset=ds, feat_dim=16, kernel_type="euclidean", train_type="irm",
+                            n_shot=2, env_array=e["env"], device=DEV).to(DEV)
+    irm.train()
+    np.random.seed(2024)
+    logp = irm(xq[:4].clone(), torch.tensor([0, 1, 2, 3], device=DEV))
+    assert np.abs(logp.detach().cpu().numpy() - e["irm_train_logp"]).max() < 1e-4
+    logp.sum().backward()
+    assert torch.isfinite(feat[1].weight.grad).all()

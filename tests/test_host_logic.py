@@ -86,5 +86,29 @@ def test_unknown_names_raise_like_the_reference():
     with pytest.raises(NotImplementedError):
         nwhead_b200.get_kernel("nope")
     assert nwhead_b200.get_kernel("clip").logit_scale.item() == pytest.approx(np.log(1 / 0.07))
-    with pytest.raises(NotImplementedError):
-        nwhead_b200.NWNet(torch.nn.Identity(), 3, support_dataset=ToyDataset([0, 1, 2]), env_array=np.zeros(3))
+    with pytest.raises(AssertionError):  # as in the reference: the support set must expose .targets
+        nwhead_b200.NWNet(torch.nn.Identity(), 3, support_dataset=[ToyDataset([0, 1, 2])])
+
+
+def test_environment_split_matches_reference_semantics():
+    """env_array -> one Subset per environment value (sorted), targets sliced alike; 'irm' builds one sampler per
+    environment over ALL of its classes (reference nwhead/support.py:47-56, 84-93)."""
+    from nwhead_b200.support import SupportSetEval, SupportSetTrain
+
+    rng = np.random.default_rng(3)
+    targets = rng.integers(0, 5, 60).tolist()
+    env = np.array([(i // 4) % 3 for i in range(60)])
+    ds = ToyDataset(targets)
+    st = SupportSetTrain(ds, 5, 'irm', 2, env_array=env)
+    assert len(st.env_datasets) == 3 and len(st.train_iter) == 3
+    for e, sub in enumerate(st.env_datasets):
+        idx = np.flatnonzero(env == e)
+        assert np.array_equal(sub.indices, idx) and np.array_equal(sub.targets, np.asarray(targets)[idx])
+    np.random.seed(5)
+    sx, sy, sm = st.get_support(torch.tensor([0]))
+    assert len(set(sm.tolist())) == 1                      # one environment per draw
+    e = int(sm[0])
+    assert sorted(set(sy.tolist())) == sorted(set(np.asarray(targets)[env == e].tolist()))
+    assert len(sy) == 2 * len(set(sy.tolist()))             # n_shot items of every class of that environment
+    se = SupportSetEval(ds, 5, 1, 3, env_array=env)
+    assert len(se.support_loaders) == 3

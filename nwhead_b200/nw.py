@@ -255,7 +255,7 @@ class NWNet(nn.Module):
         Perform prediction given test images.
 
         :param x: Input datapoints (bs, nch, l, w)
-        :param mode: Inference mode. One of ['random', 'full', 'cluster', 'ensemble', 'knn']
+        :param mode: Inference mode. One of ['random', 'full', 'cluster', 'ensemble', 'knn', 'hnsw']
         '''
         qfeat = self.featurizer(x)
         support = self.support_eval.get_support(mode, x=qfeat)

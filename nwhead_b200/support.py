@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from .bank import SupportBank
-from .utils import (DatasetMetadata, FeatureDataset, FullDataset, InfiniteUniformClassLoader, KNN,
+from .utils import (DatasetMetadata, FeatureDataset, FullDataset, HNSW, InfiniteUniformClassLoader, KNN,
                     class_centroids)
 
 
@@ -107,8 +107,9 @@ class SupportSetEval(SupportSet):
             inv[self.full_bank.perm] = torch.arange(len(inv), device=inv.device)
         self._source_to_bank_row = inv
 
-        # KNN (exact, on the GPU).  HNSW needs hnswlib and is not provided.
+        # KNN and "HNSW": both exact on the GPU (no hnswlib index to build)
         self.knn = KNN(self.full_feat, self.full_y, n_neighbors=self.n_neighbors)
+        self.hnsw = HNSW(self.full_feat, self.full_y, n_neighbors=self.n_neighbors)
 
     def get_support(self, mode, x=None):
         '''Returns the support for an inference mode: a SupportBank for 'full' / 'cluster' / 'random', a list of
@@ -128,7 +129,7 @@ class SupportSetEval(SupportSet):
             elif mode == 'ensemble':
                 return self.env_banks if self.env_banks is not None else [self.full_bank]
             elif mode == 'hnsw':
-                raise NotImplementedError("mode='hnsw' needs hnswlib and is outside the B200 hot path")
+                return self.hnsw(x)
             else:
                 raise NotImplementedError
         except AttributeError:

@@ -189,3 +189,9 @@ class KNN:
 
         idx = rank_rows(dense_scores("euclidean", x, self.data), self.n_neighbors).flatten()
         return self.data.index_select(0, idx), self.labels.index_select(0, idx)
+
+
+class HNSW(KNN):
+    """mode='hnsw' (reference nwhead/utils.py:195-216 builds an approximate hnswlib index, space='l2').  On the
+    B200 the exact search over the bank (dense scores + ranking) is cheap, so this returns the EXACT k nearest
+    neighbours under the same metric — the result an HNSW index approximates.  hnswlib is not needed."""

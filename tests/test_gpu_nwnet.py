@@ -59,8 +59,8 @@ def test_precompute_predict_neighbors(cuda_lib, golden_flow, kind):
         assert np.abs(np.exp(out) - np.exp(g[f"{kind}/pred_knn"])).max() < 1e-3
         with pytest.raises(NotImplementedError):
             net.predict(xq, mode="bogus")
-        with pytest.raises(NotImplementedError):
-            net.predict(xq, mode="hnsw")
+        # 'hnsw' is served by the exact search: identical to knn mode here
+        assert np.array_equal(net.predict(xq, mode="hnsw").cpu().numpy(), out)
         # a single environment: the ensemble of one equals full mode (reference nwhead/nw.py:143-154)
         ens = net.predict(xq, mode="ensemble").cpu().numpy()
         assert np.abs(np.exp(ens) - np.exp(g[f"{kind}/pred_full"])).max() < 1e-3

@@ -240,3 +240,14 @@ def test_empty_and_degenerate_inputs(cuda_lib):
     b1 = SupportBank.build(torch.from_numpy(s[:40]).to(DEV), torch.from_numpy(yy).to(DEV), 3, "cosine", "bf16")
     o1 = b1.forward(torch.from_numpy(q[:1]).to(DEV)).cpu().numpy()
     assert abs(o1[0, 0]) < 1e-6 and np.allclose(o1[0, 1:], np.log(np.float32(1e-12)))
+
+
+@pytest.mark.parametrize("shape", [(300, 5000, 4, 64), (5000, 40, 80, 32)])
+def test_many_classes_and_many_queries(cuda_lib, shape):
+    """(B, C, per_class, d): a 5000-class table with 4 supports per class (flush-dense), and 5000 queries (40 query
+    groups over few support tiles)."""
+    B, C, per, d = shape
+    q, s, y, _ = clustered_features(C, per, d, B, seed=C + B, spread=0.3)
+    out = run_bank(q, s, y, C, "euclidean", "bf16x3")
+    ref = O.nw_forward(q, s, y, C, "euclidean")
+    assert np.abs(np.exp(out.cpu().numpy()) - np.exp(ref)).max() < 5e-5

@@ -169,6 +169,12 @@ NW_API int nw_forward_emit(int epilogue, float scale, const void* q_bf16, const 
  * rank, so the merge is exact). */
 NW_API int nw_logp_from_class_lse(const float* class_lse, int n_query, int n_classes, float* logp, void* stream);
 
+/* row_lse[b] = logsumexp_c class_lse[b,:] (the softmax normaliser over ALL supports) and, when p_query is not
+ * NULL, p_query[b] = exp(class_lse[b, qlabel[b]] - row_lse[b]) = softmaxes[b, y_b] of util/metric.py:45 — the
+ * per-query inputs of nw_forward_emit(NW_EMIT_INFLUENCE).  qlabel must be in [0, C). */
+NW_API int nw_row_stats(const float* class_lse, int n_query, int n_classes, const int32_t* qlabel, float* row_lse,
+                 float* p_query, void* stream);
+
 /* Exact merge of two class-LSE tables (generic row-sharded banks): a = log(exp(a) + exp(b)). */
 NW_API int nw_class_lse_merge(float* a, const float* b, int64_t n_elems, void* stream);
 

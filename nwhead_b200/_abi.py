@@ -59,6 +59,7 @@ SIGNATURES = {
     "nw_forward_emit": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "nw_logp_from_class_lse": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "nw_row_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nw_class_lse_merge": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "nw_direct_scores": (c_int, [c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p,
                                  c_void_p]),

@@ -297,12 +297,15 @@ class SupportBank:
         pass 1 = the fused forward (class log-sum-exp -> softmax mass of each query's class and the softmax
         normaliser), pass 2 = scores again with the influence formula in the epilogue.  The (B, N) weight matrix
         the reference takes as an input is never materialised."""
+        lib = load()
         lse = self.class_lse(q, scale)
-        z = torch.logsumexp(lse, dim=1).contiguous()
-        qy = qlabel.to(self.device, torch.int64)
-        p = torch.exp(lse.gather(1, qy[:, None])[:, 0] - z).contiguous()
-        return self._emit(q, scale, _abi.EMIT_INFLUENCE, row_lse=z, p_query=p, qlabel=qy.to(torch.int32).contiguous(),
-                          source_order=source_order)
+        b = lse.shape[0]
+        qy = qlabel.to(self.device, torch.int32).contiguous()
+        z = torch.empty((b,), dtype=torch.float32, device=self.device)
+        p = torch.empty((b,), dtype=torch.float32, device=self.device)
+        check(lib.nw_row_stats(ptr(lse), b, self.n_classes, ptr(qy), ptr(z), ptr(p), stream_of(self.device)),
+              "nw_row_stats")
+        return self._emit(q, scale, _abi.EMIT_INFLUENCE, row_lse=z, p_query=p, qlabel=qy, source_order=source_order)
 
     def graphed(self, batch: int, scale: float = 1.0) -> "GraphedForward":
         """CUDA-graph replay of forward() for a fixed batch size (see GraphedForward)."""

@@ -629,6 +629,41 @@ __global__ void __launch_bounds__(256) logp_kernel(const float* __restrict__ cla
   for (int c = threadIdx.x; c < n_classes; c += blockDim.x) out[c] = logf(expf(row[c] - lse) + 1e-12f);
 }
 
+// row_lse[b] = logsumexp_c L[b,:]; p_query[b] = exp(L[b, qlabel[b]] - row_lse[b])   (inputs of the influence emit pass)
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ class_lse, int n_classes,
+                                                        const int32_t* __restrict__ qlabel,
+                                                        float* __restrict__ row_lse, float* __restrict__ p_query) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const float* row = class_lse + size_t(blockIdx.x) * n_classes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = __int_as_float(0xff800000);
+  for (int c = threadIdx.x; c < n_classes; c += blockDim.x) mx = fmaxf(mx, row[c]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = red[0];
+    for (int i = 1; i < 8; ++i) v = fmaxf(v, red[i]);
+    bcast = v;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.0f;
+  for (int c = threadIdx.x; c < n_classes; c += blockDim.x) sum += expf(row[c] - mx);
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.0f;
+    for (int i = 0; i < 8; ++i) v += red[i];
+    const float z = mx + logf(v);
+    row_lse[blockIdx.x] = z;
+    if (p_query) p_query[blockIdx.x] = expf(row[qlabel[blockIdx.x]] - z);
+  }
+}
+
 __global__ void lse_merge_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -921,6 +956,17 @@ extern "C" int nw_logp_from_class_lse(const float* class_lse, int n_query, int n
   NW_REQUIRE(class_lse && logp, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(n_query > 0 && n_classes > 0, NW_ERR_INVALID, "n_query and n_classes must be positive");
   k1::logp_kernel<<<n_query, 256, 0, stream>>>(class_lse, n_classes, logp);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_row_stats(const float* class_lse, int n_query, int n_classes, const int32_t* qlabel, float* row_lse,
+                            float* p_query, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(class_lse && row_lse, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(p_query == nullptr || qlabel != nullptr, NW_ERR_INVALID, "p_query needs qlabel");
+  NW_REQUIRE(n_query > 0 && n_classes > 0, NW_ERR_INVALID, "n_query and n_classes must be positive");
+  k1::row_stats_kernel<<<n_query, 256, 0, stream>>>(class_lse, n_classes, qlabel, row_lse, p_query);
   NW_CUDA_OK(cudaGetLastError());
   return NW_OK;
 }

@@ -121,7 +121,7 @@ typedef struct nw_forward_plan_t {
   int tiles_per_chunk; /* support tiles per chunk */
   int grid;            /* persistent CTAs launched */
   int cta_pair;        /* 1: CTA pairs (cluster of 2, tcgen05 cta_group::2, 256x256 tiles); 0: single CTAs */
-  int64_t side_elems;  /* floats of scratch `side` required: chunks * B * 2 */
+  int64_t side_elems;  /* floats of scratch `side` required: chunks * B * 4 */
 } nw_forward_plan_t;
 
 NW_API int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t* plan_out);
@@ -129,7 +129,9 @@ NW_API int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t* pl
 /* class_lse[b, c] = log sum_{j : labels[j] == c} exp(score(b, j)); -inf for classes with no support
  * row in this bank (or bank shard).  Inputs are the bf16 layouts of nw_rows_to_bf16.
  * labels must be class-sorted int32.  q_sqnorm / s_sqnorm are only read for NW_EPI_EUCLID.
- * side: scratch of plan.side_elems floats. */
+ * side: scratch of at least plan.side_elems floats.  When row_elems <= 1024 and side has room for another
+ * n_query * n_classes floats, the kernel runs two independent epilogue warp sets (each with its own table, the
+ * second one placed in `side`) and combines them afterwards — short GEMMs are otherwise epilogue-bound. */
 NW_API int nw_forward_class_lse(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
                          const void* bank_bf16, const float* s_sqnorm, const int32_t* labels, int64_t n_support,
                          int row_elems, int n_classes, float* class_lse, float* side, int64_t side_elems,

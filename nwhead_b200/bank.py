@@ -227,7 +227,9 @@ class SupportBank:
         n = len(self)
         plan = _abi.forward_plan(b, n)
         dev = self.device
-        side = torch.empty((max(int(plan.side_elems), 1),), dtype=torch.float32, device=dev)
+        # chunk-boundary partials + room for the second epilogue set's table (used for short GEMMs, d <= 1024)
+        extra = b * self.n_classes if (tables is None and self.row_elems <= 1024) else 0
+        side = torch.empty((max(int(plan.side_elems) + extra, 1),), dtype=torch.float32, device=dev)
         epi = _abi.EPI_EUCLID if self.kind in EUCLID_KINDS else _abi.EPI_LINEAR
         if tables is not None:
             check(

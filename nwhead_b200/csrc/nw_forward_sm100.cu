@@ -42,10 +42,11 @@ constexpr int A_BYTES = BM * BK * 2;
 constexpr int EPI_WARP0 = 4;
 constexpr int MAX_EPI_WARPS = 8;
 constexpr int MAX_THREADS = (EPI_WARP0 + MAX_EPI_WARPS) * 32;
-// Epilogue warps: the class-LSE epilogue carries a running (max, sum) per query row along the columns, so one
-// thread owns a row (4 warps = 128 TMEM lanes).  The emit epilogues have no state across columns, so a second
-// set of 4 warps (same lane quarters, the other column chunks) doubles their throughput.
-constexpr int epi_warps(int mode) { return mode == 0 ? 4 : 8; }
+// Epilogue warps: one thread per query row (4 warps = 128 TMEM lanes).  A second set of 4 warps (same lane
+// quarters) takes every other pair of 32-column chunks: always in the emit modes (no state along the columns),
+// and in the class-LSE mode when the GEMM is short (d <= 1024) and the epilogue would otherwise be the
+// bottleneck.  There each set keeps its OWN running (max, sum) per class and stores to its OWN table; the two
+// tables are combined afterwards by one log-add-exp pass, so the sets never synchronise with each other.
 constexpr int NW_MAX_PEERS = 16;
 
 // NCTA = 1: one CTA computes a 128 x 256 tile (UMMA M=128).
@@ -100,6 +101,7 @@ struct Params {
   int chunks;
   int tiles_per_chunk;
   float scale_log2;  // LINEAR: scale * log2(e)
+  int sets;          // epilogue warp sets (1 or 2); class-LSE with 2 sets: set s stores to lse[s]
   // ---- MODE_EMIT only: one output value per (query, support) pair
   float* emit_out;           // (B, ld_out)
   long long emit_ld;
@@ -119,9 +121,10 @@ constexpr int MODE_EMIT_INFLUENCE = 2;  // dense per-pair output: support influe
 struct Flusher {
   const Params* p;
   size_t row_off;   // row * C
-  float* side_row;  // side + (chunk * B + row) * 2
+  float* side_row;  // side + ((chunk * B + row) * 2) * sets: [slot 0 = head-cut class | slot 1 = tail-cut class][set]
   int cf, cl;
   bool head_cut, tail_cut, row_valid;
+  int row, set;
   // Rare path (once per class per row), kept out of line so the unrolled column loop stays compact.
   // A class that lies completely inside this unit is final: store it to the local table AND to every peer
   // GPU's table (bank-sharded predict: the all-gather of class columns happens here, tile by tile, as NVLink
@@ -129,8 +132,8 @@ struct Flusher {
   __device__ __noinline__ void operator()(int cls, float m, float l) const {
     const float v = (m + lg2_approx(l)) * kLn2;
     if (!row_valid) return;
-    if (cls == cf && head_cut) side_row[0] = v;
-    else if (cls == cl && tail_cut) side_row[1] = v;
+    if (cls == cf && head_cut) side_row[set] = v;
+    else if (cls == cl && tail_cut) side_row[p->sets + set] = v;
     else store(cls, v);
   }
   // single-row class that lies inside the unit: its class log-sum-exp is the score itself
@@ -138,11 +141,11 @@ struct Flusher {
     if (row_valid) store(cls, v);
   }
   __device__ __noinline__ void store(int cls, float v) const {
-    if (p->rows_per_table > 0) p->lse[row / p->rows_per_table][row_off + cls] = v;
+    if (p->sets == 2) p->lse[set][row_off + cls] = v;  // two epilogue sets: one table per set, merged afterwards
+    else if (p->rows_per_table > 0) p->lse[row / p->rows_per_table][row_off + cls] = v;
     else
       for (int r = 0; r < p->n_tables; ++r) p->lse[r][row_off + cls] = v;
   }
-  int row;
 };
 
 // One 32-column chunk of the accumulator for one query row.
@@ -293,7 +296,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(smem_u32(&tail->tfull[i]), 1);
-      mbar_init(smem_u32(&tail->tempty[i]), NCTA * epi_warps(MODE));
+      mbar_init(smem_u32(&tail->tempty[i]), NCTA * 4 * p.sets);
     }
     fence_mbar_init();
   }
@@ -388,11 +391,11 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
     }
     __syncwarp();
-  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + epi_warps(MODE)) {
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4 * p.sets) {
     // ===================================== epilogue ==========================================
-    constexpr int EPI_THREADS = epi_warps(MODE) * 32;
+    const int epi_threads = 128 * p.sets;
     const int ew = (warp - EPI_WARP0) & 3;   // == warp % 4: TMEM lane quarter this warp may read
-    const int eg = (warp - EPI_WARP0) >> 2;  // emit modes: which half of the column chunks this warp handles
+    const int eg = (warp - EPI_WARP0) >> 2;  // epilogue set: which pairs of column chunks this warp handles
     const int et = threadIdx.x - EPI_WARP0 * 32;
     const float scale2 = p.scale_log2;
     const float neg_inf = __int_as_float(0xff800000);
@@ -420,8 +423,9 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const int srow = flush.row_valid ? row : 0;
       flush.p = &p;
       flush.row = srow;
+      flush.set = eg;
       flush.row_off = size_t(srow) * p.n_classes;
-      flush.side_row = p.side + (size_t(g) * p.n_query + srow) * 2;
+      flush.side_row = p.side + (size_t(g) * p.n_query + srow) * 2 * p.sets;
       const float qn = (EPI == NW_EPI_EUCLID && flush.row_valid) ? __ldg(p.q_sqnorm + row) : 0.0f;
       float e_z = 0.0f, e_p = 0.0f;
       int e_qy = -1;
@@ -432,23 +436,27 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
 
       // column metadata of a tile: additive term (|s|^2, or 0; +inf / -inf on padding columns) and labels
-      float pre_cadd[BN / EPI_THREADS];
-      int pre_lab[BN / EPI_THREADS];
+      float pre_cadd[2];
+      int pre_lab[2];
       int pre_lab_next = -1;
       auto load_meta = [&](int t) {
         const int j0 = t * BN;
 #pragma unroll
-        for (int r = 0; r < BN / EPI_THREADS; ++r) {
-          const int j = j0 + et + r * EPI_THREADS;
-          if (EPI == NW_EPI_EUCLID) pre_cadd[r] = j < n1 ? __ldg(p.s_sqnorm + j) : pos_inf;
-          else pre_cadd[r] = j < n1 ? 0.0f : neg_inf;
-          pre_lab[r] = (p.labels != nullptr && j < p.n_support) ? __ldg(p.labels + j) : -1;
+        for (int r = 0; r < 2; ++r) {
+          const int i = et + r * epi_threads;
+          if (i < BN) {
+            const int j = j0 + i;
+            if (EPI == NW_EPI_EUCLID) pre_cadd[r] = j < n1 ? __ldg(p.s_sqnorm + j) : pos_inf;
+            else pre_cadd[r] = j < n1 ? 0.0f : neg_inf;
+            pre_lab[r] = (p.labels != nullptr && j < p.n_support) ? __ldg(p.labels + j) : -1;
+          }
         }
         if (et == 0) pre_lab_next = (p.labels != nullptr && (j0 + BN) < p.n_support) ? __ldg(p.labels + j0 + BN) : -1;
       };
       load_meta(t0);
 
       float m = neg_inf, l = 0.0f;
+      int open_cls = -1;  // two sets: class whose partial this set currently holds (warp-uniform)
       for (int t = t0; t < t1; ++t, ++tc) {
         const uint32_t as = tc & 1u;
         const uint32_t aph = (tc >> 1) & 1u;
@@ -457,12 +465,15 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // publish this tile's column metadata (fetched into registers one tile ahead, so the global-load
         // latency is hidden behind the previous tile's epilogue math)
 #pragma unroll
-        for (int r = 0; r < BN / EPI_THREADS; ++r) {
-          meta.cadd[et + r * EPI_THREADS] = pre_cadd[r];
-          meta.lab[et + r * EPI_THREADS] = pre_lab[r];
+        for (int r = 0; r < 2; ++r) {
+          const int i = et + r * epi_threads;
+          if (i < BN) {
+            meta.cadd[i] = pre_cadd[r];
+            meta.lab[i] = pre_lab[r];
+          }
         }
         if (et == 0) meta.lab[BN] = pre_lab_next;
-        named_bar_sync(1, EPI_THREADS);
+        named_bar_sync(1, epi_threads);
         if (t + 1 < t1) load_meta(t + 1);
 
         mbar_wait(smem_u32(&tail->tfull[as]), aph);
@@ -490,9 +501,19 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                                   n1 - (j0 + (c + 1) * 32), p.emit_vec != 0);
             continue;
           }
+          if (p.sets == 2 && ((c >> 1) & 1) != eg) continue;  // chunk pairs alternate between the two sets
           float acc0[32], acc1[32];
           tmem_ld_32x32(t_addr + c * 32, acc0);
           tmem_ld_32x32(t_addr + (c + 1) * 32, acc1);
+          if (p.sets == 2) {
+            // this set skipped the columns in between: if they ended the class it was accumulating, close its
+            // partial now (the other set closes its own; the two tables are combined after the kernel)
+            const int first = meta.lab[c * 32];
+            if (open_cls >= 0 && first != open_cls) {
+              flush(open_cls, m, l);
+              l = 0.0f;
+            }
+          }
           // class-end masks of both chunks while the TMEM loads are in flight
           const int i0 = c * 32 + lane, i1 = i0 + 32;
           const int ja = j0 + i0, jb = j0 + i1;
@@ -503,6 +524,11 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           tmem_ld_wait();
           epilogue_chunk<EPI>(acc0, meta.cadd + c * 32, meta.lab + c * 32, em0, qn, scale2, m, l, flush);
           epilogue_chunk<EPI>(acc1, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, em1, qn, scale2, m, l, flush);
+          if (p.sets == 2) {
+            // class left open after this pair (none if its last valid column closed a class or is padding)
+            const int j_last = j0 + (c + 2) * 32 - 1;
+            open_cls = (j_last < n1 && !(em1 >> 31)) ? meta.lab[(c + 2) * 32 - 1] : -1;
+          }
         }
         // all TMEM reads of this accumulator are complete -> hand it back to the (leader's) MMA warp
         tc_fence_before();
@@ -512,6 +538,8 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           else mbar_arrive(smem_u32(&tail->tempty[as]));
         }
       }
+      // two sets: the unit's last columns may belong to the other set; close what this set still holds
+      if (MODE == MODE_CLASS_LSE && p.sets == 2 && open_cls >= 0) flush(open_cls, m, l);
     }
   }
 
@@ -552,7 +580,7 @@ struct TableList {
 __global__ void __launch_bounds__(32) merge_side_kernel(const TableList tables, const float* __restrict__ side,
                                                         const int32_t* __restrict__ labels, int n_query,
                                                         int n_support, int n_classes, int chunks,
-                                                        int tiles_per_chunk, int s_tiles) {
+                                                        int tiles_per_chunk, int s_tiles, int sets) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_query) return;
   const size_t row_off = size_t(b) * n_classes;
@@ -564,31 +592,28 @@ __global__ void __launch_bounds__(32) merge_side_kernel(const TableList tables, 
     else
       for (int r = 0; r < tables.n; ++r) tables.t[r][row_off + cls] = v;
   };
-#pragma unroll 4
+  auto add = [&](int cls, float v) {
+    if (v == neg_inf) return;
+    if (cls != cur) {
+      if (cur >= 0) put(cur, acc);
+      cur = cls;
+      acc = neg_inf;
+    }
+    acc = logaddexp_f(acc, v);
+  };
+#pragma unroll 2
   for (int g = 0; g < chunks; ++g) {
     const int t0 = g * tiles_per_chunk;
     const int t1 = min(t0 + tiles_per_chunk, s_tiles);
     const int n0 = t0 * BN;
     const int n1 = min(t1 * BN, n_support);
-    const float2 v = *reinterpret_cast<const float2*>(side + (size_t(g) * n_query + b) * 2);
+    const float* sr = side + (size_t(g) * n_query + b) * 2 * sets;  // [slot][set]
     const int c0 = __ldg(labels + n0);
     const int c1 = __ldg(labels + n1 - 1);
-    if (v.x != neg_inf) {
-      if (c0 != cur) {
-        if (cur >= 0) put(cur, acc);
-        cur = c0;
-        acc = neg_inf;
-      }
-      acc = logaddexp_f(acc, v.x);
-    }
-    if (v.y != neg_inf) {
-      if (c1 != cur) {
-        if (cur >= 0) put(cur, acc);
-        cur = c1;
-        acc = neg_inf;
-      }
-      acc = logaddexp_f(acc, v.y);
-    }
+    float v[4];
+    for (int i = 0; i < 2 * sets; ++i) v[i] = sr[i];
+    for (int i = 0; i < sets; ++i) add(c0, v[i]);
+    for (int i = 0; i < sets; ++i) add(c1, v[sets + i]);
   }
   if (cur >= 0) put(cur, acc);
 }
@@ -750,7 +775,9 @@ extern "C" int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t
   const long long units = (long long)plan->chunks * q_groups;
   plan->grid = int(units < workers ? units : workers) * ncta;
   plan->cta_pair = ncta == 2 ? 1 : 0;
-  plan->side_elems = int64_t(plan->chunks) * n_query * 2;
+  // chunk-boundary partials: [chunk][query][2 slots][2 epilogue sets]  (+ room for the second set's table is
+  // added by the caller of the two-set mode, see forward_impl)
+  plan->side_elems = int64_t(plan->chunks) * n_query * 4;
   return NW_OK;
 }
 
@@ -771,7 +798,7 @@ static int launch_forward(const CUtensorMap& map_q, const CUtensorMap& map_s, co
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3((EPI_WARP0 + epi_warps(MODE)) * 32);
+  cfg.blockDim = dim3((EPI_WARP0 + 4 * p.sets) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -812,6 +839,13 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   NW_REQUIRE(side_elems >= plan.side_elems, NW_ERR_WORKSPACE, "side scratch too small: %lld < %lld floats",
              (long long)side_elems, (long long)plan.side_elems);
   const int ncta = plan.cta_pair ? 2 : 1;
+  // Short GEMMs (d <= 1024) are epilogue-bound with one epilogue warp per scheduler: run two independent epilogue
+  // sets, each with its own class-LSE table (the second one lives behind the chunk partials in `side`).
+  const long long table_elems = (long long)n_query * n_classes;
+  const char* env_sets = getenv("NW_B200_EPI_SETS");
+  int sets = (row_elems / k1::BK <= 16 && n_tables == 1 && side_elems >= plan.side_elems + table_elems) ? 2 : 1;
+  if (env_sets && env_sets[0] == '1') sets = 1;
+  float* table1 = side + plan.side_elems;
 
   CUtensorMap map_q, map_s;
   rc = k1::make_map(&map_q, q_bf16, uint64_t(n_query), uint64_t(row_elems), k1::BM);
@@ -819,8 +853,9 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   rc = k1::make_map(&map_s, bank_bf16, uint64_t(n_support), uint64_t(row_elems), k1::BN / ncta);
   if (rc != NW_OK) return rc;
 
-  k1::fill_kernel<<<sm_count() * 4, 256, 0, stream>>>(tables[0], fill_local ? (long long)n_query * n_classes : 0, side,
-                                                      (long long)plan.side_elems, -INFINITY);
+  k1::fill_kernel<<<sm_count() * 4, 256, 0, stream>>>(tables[0], fill_local ? table_elems : 0, side,
+                                                      (long long)plan.side_elems + (sets == 2 ? table_elems : 0),
+                                                      -INFINITY);
   NW_CUDA_OK(cudaGetLastError());
 
   k1::Params p;
@@ -829,8 +864,10 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.labels = labels;
   k1::TableList tl;
   for (int r = 0; r < k1::NW_MAX_PEERS; ++r) p.lse[r] = tl.t[r] = (r < n_tables ? tables[r] : nullptr);
+  if (sets == 2) p.lse[1] = table1;
   p.n_tables = tl.n = n_tables;
   p.rows_per_table = tl.rows_per_table = rows_per_table;
+  p.sets = sets;
   p.side = side;
   p.n_query = n_query;
   p.n_support = int(n_support);
@@ -847,6 +884,7 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.emit_vec = 0;
   p.row_lse = p.p_query = nullptr;
   p.qlabel = nullptr;
+
   if (epilogue == NW_EPI_EUCLID) {
     rc = ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2>(map_q, map_s, p, plan.grid, stream)
                    : k1::launch_forward<NW_EPI_EUCLID, 1>(map_q, map_s, p, plan.grid, stream);
@@ -856,10 +894,14 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   }
   if (rc != NW_OK) return rc;
 
+  if (sets == 2) {  // combine the two epilogue sets' tables
+    k1::lse_merge_kernel<<<sm_count() * 4, 256, 0, stream>>>(tables[0], table1, table_elems);
+    NW_CUDA_OK(cudaGetLastError());
+  }
   if (plan.chunks > 1) {
     k1::merge_side_kernel<<<ceil_div(n_query, 32), 32, 0, stream>>>(tl, side, labels, n_query, int(n_support),
                                                                     n_classes, plan.chunks, plan.tiles_per_chunk,
-                                                                    plan.s_tiles);
+                                                                    plan.s_tiles, sets);
     NW_CUDA_OK(cudaGetLastError());
   }
   return NW_OK;
@@ -929,6 +971,7 @@ extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, co
   p.chunks = plan.chunks;
   p.tiles_per_chunk = plan.tiles_per_chunk;
   p.scale_log2 = scale * kLog2e;
+  p.sets = 2;
   p.emit_out = out;
   p.emit_ld = ld_out;
   p.emit_kind = emit_kind;

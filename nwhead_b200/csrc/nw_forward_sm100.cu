@@ -69,7 +69,7 @@ struct TileMeta {
 
 template <int MODE>
 struct SmemTail {
-  TileMeta meta[ACC_STAGES];
+  TileMeta meta[2][ACC_STAGES];  // [epilogue set][accumulator stage]: the sets stay independent of each other
   float stage[MODE == 0 ? 1 : MAX_EPI_WARPS][32][33];  // emit modes: per-warp 32x32 transpose buffers
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
@@ -119,21 +119,23 @@ constexpr int MODE_EMIT_INFLUENCE = 2;  // dense per-pair output: support influe
 //  of SASS and ran 4x slower on instruction fetch)
 
 struct Flusher {
-  const Params* p;
-  size_t row_off;   // row * C
-  float* side_row;  // side + ((chunk * B + row) * 2) * sets: [slot 0 = head-cut class | slot 1 = tail-cut class][set]
+  const Params* p;   // only dereferenced on the multi-table (peer GPU) routes
+  float* table;      // the one table this thread stores to when route == 0 (local table, or this set's table)
+  size_t row_off;    // row * C
+  float* side_row;   // side + ((chunk * B + row) * 2) * sets: [slot 0 = head-cut class | slot 1 = tail-cut class][set]
   int cf, cl;
   bool head_cut, tail_cut, row_valid;
-  int row, set;
+  int row, set, sets;
+  int route;         // 0: `table`; 1: table[row / rows_per_table]; 2: every table (peer all-gather)
   // Rare path (once per class per row), kept out of line so the unrolled column loop stays compact.
-  // A class that lies completely inside this unit is final: store it to the local table AND to every peer
-  // GPU's table (bank-sharded predict: the all-gather of class columns happens here, tile by tile, as NVLink
-  // peer stores that overlap the MMAs).  Classes cut by a chunk boundary go through `side`.
+  // A class that lies completely inside this unit is final: store it to the local table AND (bank-sharded predict)
+  // to the peer GPUs' tables — the exchange happens here, tile by tile, as NVLink peer stores that overlap the
+  // MMAs.  Classes cut by a chunk boundary go through `side`.
   __device__ __noinline__ void operator()(int cls, float m, float l) const {
     const float v = (m + lg2_approx(l)) * kLn2;
     if (!row_valid) return;
     if (cls == cf && head_cut) side_row[set] = v;
-    else if (cls == cl && tail_cut) side_row[p->sets + set] = v;
+    else if (cls == cl && tail_cut) side_row[sets + set] = v;
     else store(cls, v);
   }
   // single-row class that lies inside the unit: its class log-sum-exp is the score itself
@@ -141,8 +143,8 @@ struct Flusher {
     if (row_valid) store(cls, v);
   }
   __device__ __noinline__ void store(int cls, float v) const {
-    if (p->sets == 2) p->lse[set][row_off + cls] = v;  // two epilogue sets: one table per set, merged afterwards
-    else if (p->rows_per_table > 0) p->lse[row / p->rows_per_table][row_off + cls] = v;
+    if (route == 0) table[row_off + cls] = v;
+    else if (route == 1) p->lse[row / p->rows_per_table][row_off + cls] = v;
     else
       for (int r = 0; r < p->n_tables; ++r) p->lse[r][row_off + cls] = v;
   }
@@ -393,10 +395,10 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     __syncwarp();
   } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4 * p.sets) {
     // ===================================== epilogue ==========================================
-    const int epi_threads = 128 * p.sets;
+    constexpr int epi_threads = 128;         // threads of ONE epilogue set (each set stages its own metadata)
     const int ew = (warp - EPI_WARP0) & 3;   // == warp % 4: TMEM lane quarter this warp may read
     const int eg = (warp - EPI_WARP0) >> 2;  // epilogue set: which pairs of column chunks this warp handles
-    const int et = threadIdx.x - EPI_WARP0 * 32;
+    const int et = (threadIdx.x - EPI_WARP0 * 32) & 127;
     const float scale2 = p.scale_log2;
     const float neg_inf = __int_as_float(0xff800000);
     const float pos_inf = __int_as_float(0x7f800000);
@@ -424,6 +426,9 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       flush.p = &p;
       flush.row = srow;
       flush.set = eg;
+      flush.sets = p.sets;
+      flush.route = p.sets == 2 ? 0 : (p.rows_per_table > 0 ? 1 : (p.n_tables > 1 ? 2 : 0));
+      flush.table = p.lse[p.sets == 2 ? eg : 0];
       flush.row_off = size_t(srow) * p.n_classes;
       flush.side_row = p.side + (size_t(g) * p.n_query + srow) * 2 * p.sets;
       const float qn = (EPI == NW_EPI_EUCLID && flush.row_valid) ? __ldg(p.q_sqnorm + row) : 0.0f;
@@ -460,7 +465,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       for (int t = t0; t < t1; ++t, ++tc) {
         const uint32_t as = tc & 1u;
         const uint32_t aph = (tc >> 1) & 1u;
-        TileMeta& meta = tail->meta[as];
+        TileMeta& meta = tail->meta[eg][as];
         const int j0 = t * BN;
         // publish this tile's column metadata (fetched into registers one tile ahead, so the global-load
         // latency is hidden behind the previous tile's epilogue math)
@@ -473,7 +478,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           }
         }
         if (et == 0) meta.lab[BN] = pre_lab_next;
-        named_bar_sync(1, epi_threads);
+        named_bar_sync(1 + eg, epi_threads);
         if (t + 1 < t1) load_meta(t + 1);
 
         mbar_wait(smem_u32(&tail->tfull[as]), aph);

@@ -120,11 +120,28 @@ class _NWDirectFunction(torch.autograd.Function):
 
 
 class NWHead(nn.Module):
+    BANK_CACHE_SIZE = 2  # banks built from raw (sx, sy) tensors are kept while the tensors stay unmodified
+
     def __init__(self, kernel, n_classes, precision="auto"):
         super().__init__()
         self.kernel = kernel
         self.n_classes = n_classes
         self.precision = precision
+        self._bank_cache = []
+
+    def _bank_for(self, sx, sy, kind):
+        """The reference hands the SAME support tensors to the head on every predict call (nwhead/nw.py:156-160).
+        Building the device bank (sort check, centring, bf16 conversion) once per tensor version instead of once
+        per call keeps that usage pattern fast; in-place modification bumps `_version` and invalidates the entry."""
+        key = (sx.data_ptr(), sx._version, tuple(sx.shape), sy.data_ptr(), sy._version, kind, self.precision,
+               self.n_classes)
+        for k, bank in self._bank_cache:
+            if k == key:
+                return bank
+        bank = SupportBank.build(sx, sy, self.n_classes, kind, self.precision)
+        self._bank_cache.append((key, bank))
+        del self._bank_cache[:-self.BANK_CACHE_SIZE]
+        return bank
 
     def _kind(self):
         kind = getattr(self.kernel, "kind", None)
@@ -161,8 +178,7 @@ class NWHead(nn.Module):
             raise ValueError("NWHead needs at least one support row")
         if needs_grad or sx.dim() == 3 or n < MM_PATH_MIN_ROWS:
             return _NWDirectFunction.apply(x, sx, sy, logit_scale, kind, self.n_classes)
-        bank = SupportBank.build(sx, sy, self.n_classes, kind, self.precision)
-        return bank.forward(x, self.kernel.scale_value())
+        return self._bank_for(sx, sy, kind).forward(x, self.kernel.scale_value())
 
 
 class NWNet(nn.Module):

@@ -251,3 +251,20 @@ def test_many_classes_and_many_queries(cuda_lib, shape):
     out = run_bank(q, s, y, C, "euclidean", "bf16x3")
     ref = O.nw_forward(q, s, y, C, "euclidean")
     assert np.abs(np.exp(out.cpu().numpy()) - np.exp(ref)).max() < 5e-5
+
+
+def test_head_caches_the_bank_of_unchanged_support_tensors(cuda_lib):
+    import nwhead_b200
+
+    q, s, y, _ = clustered_features(6, 20, 48, 9, seed=5)
+    head = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), 6)
+    sx, sy, qx = torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), torch.from_numpy(q).to(DEV)
+    with torch.no_grad():
+        a = head(qx, sx, sy)
+        bank = head._bank_cache[-1][1]
+        b = head(qx, sx, sy)
+        assert head._bank_cache[-1][1] is bank and torch.equal(a, b)      # same tensors -> cached bank
+        sx.mul_(1.5)                                                       # in-place change -> rebuilt
+        c = head(qx, sx, sy)
+        assert head._bank_cache[-1][1] is not bank
+    assert_head_parity(c, O.nw_forward(q, s * 1.5, y, 6, "euclidean"))

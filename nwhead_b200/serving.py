@@ -12,8 +12,7 @@ returns only its own rows.  PCIe traffic per rank drops by R while every query s
 import torch
 import torch.distributed as dist
 
-from .bank import SupportBank, logp_from_class_lse
-from .dist import merge_class_lse
+from .bank import logp_from_class_lse
 
 
 class _Slot:

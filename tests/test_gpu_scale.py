@@ -3,7 +3,6 @@ cannot run at these sizes, so parity is checked (a) against a float64 torch rest
 for a handful of queries (exact differences, chunked over the bank), and (b) through size-independent
 properties: probabilities sum to one, class-aligned shard merge == unsharded, row-shard log-add merge ==
 unsharded, run-to-run bitwise reproducibility."""
-import numpy as np
 import pytest
 import torch
 
@@ -49,8 +48,6 @@ def fp64_class_lse(q, feats, labels):
 
 
 def test_config3_matches_fp64_reference(big):
-    from nwhead_b200.bank import logp_from_class_lse
-
     sel = torch.arange(0, 16, device=DEV)
     logp = big["bank"].forward(big["q"])
     ref_lse = fp64_class_lse(big["q"][sel], big["feats"], big["labels"])

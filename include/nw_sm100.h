@@ -61,6 +61,7 @@ extern "C" {
 /* per-pair outputs of nw_forward_emit */
 #define NW_EMIT_SCORES 0    /* out[b, j] = score(b, j)  (the kernel(x, y) matrix, nwhead/kernel.py:13-44) */
 #define NW_EMIT_INFLUENCE 1 /* out[b, j] = support influence (util/metric.py:47) with w = softmax_j score */
+#define NW_EMIT_BLOCK_BEST 2 /* out[blk, b] = max over support rows [64 blk, 64 blk + 64) of score(b, j) */
 
 /* row layouts written by nw_rows_to_bf16 */
 #define NW_ROWS_BANK 0  /* support rows:  [hi]  or [hi | hi | lo] */
@@ -160,7 +161,11 @@ NW_API int nw_forward_class_lse_peers(int epilogue, float scale, const void* q_b
  *                       row_lse[b]) is formed in registers and never written; needs row_lse (B) = logsumexp_j
  *                       score(b, :), p_query (B) = softmax mass of the query's own class, qlabel (B) and the bank
  *                       labels.  4 bytes per pair of HBM traffic instead of 8 + the weight matrix.
- * labels may be NULL for NW_EMIT_SCORES. */
+ *   NW_EMIT_BLOCK_BEST: candidate search for an exact top-k (nwhead/nw.py:245-249 at scale): out is
+ *                       (ceil(N / 64), ld_out >= B), out[blk, b] = best score of query b inside block blk; the
+ *                       k nearest supports of a query lie in the blocks whose best score is within the operand
+ *                       rounding error of the k-th best block.
+ * labels may be NULL for NW_EMIT_SCORES and NW_EMIT_BLOCK_BEST. */
 NW_API int nw_forward_emit(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
                     const void* bank_bf16, const float* s_sqnorm, const int32_t* labels, int64_t n_support,
                     int row_elems, int emit_kind, const float* row_lse, const float* p_query,

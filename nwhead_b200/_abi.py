@@ -17,7 +17,7 @@ KIND = {"euclidean": 0, "hypersphere_euclidean": 1, "cosine": 2, "dotproduct": 3
 EPI_EUCLID, EPI_LINEAR = 0, 1
 PREC_BF16, PREC_BF16X3 = 1, 3
 ROWS_BANK, ROWS_QUERY = 0, 1
-EMIT_SCORES, EMIT_INFLUENCE = 0, 1
+EMIT_SCORES, EMIT_INFLUENCE, EMIT_BLOCK_BEST = 0, 1, 2
 
 # NW_B200_LIB: developer override to A/B two builds of the library on the same GPU box
 _LIB_PATH = os.environ.get("NW_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnw_sm100.so")

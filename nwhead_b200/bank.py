@@ -293,6 +293,113 @@ class SupportBank:
             out.append(idx)
         return torch.cat(out, dim=0)
 
+    def block_best(self, q: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        """(B, ceil(N/64)) best score of every query inside every block of 64 consecutive bank rows
+        (nw_forward_emit / NW_EMIT_BLOCK_BEST): the candidate search of topk_exact."""
+        lib = load()
+        _abi.require_cuda(q, self.feats_bf16)
+        q_bf16, q_sq = self.prepare_queries(q)
+        b, n, dev = q.shape[0], len(self), self.device
+        nblk = (n + 255) // 256 * 4
+        ld = (b + 3) // 4 * 4
+        out = torch.empty((nblk, ld), dtype=torch.float32, device=dev)
+        epi = _abi.EPI_EUCLID if self.kind in EUCLID_KINDS else _abi.EPI_LINEAR
+        check(
+            lib.nw_forward_emit(epi, float(scale), ptr(q_bf16), ptr(q_sq), b, ptr(self.feats_bf16), ptr(self.sqnorm),
+                                None, n, self.row_elems, _abi.EMIT_BLOCK_BEST, None, None, None, ptr(out), ld,
+                                stream_of(dev)),
+            "nw_forward_emit",
+        )
+        return out[:(n + 63) // 64, :b].t().contiguous(), q_sq
+
+    def topk_exact(self, q: torch.Tensor, k: int, source_feats: torch.Tensor, max_blocks: int = 64,
+                   query_chunk: int = 128) -> torch.Tensor:
+        """EXACT k nearest supports (euclidean banks), indices into `source_feats` (the fp32 tensor the bank was
+        built from), nearest first — the same ranking as the dense fp32 path (ties by ascending index), without
+        the (B, N) score matrix:
+
+          1. tensor-core pass: best reduced-precision score beta_j of every query in every block j of 64 bank rows;
+          2. candidates = the rows of the m best blocks; exact fp32 differences (nw_direct_scores) over those rows
+             only, ranked by nw_rank_rows -> tau_c, the exact k-th best candidate score;
+          3. certificate: no row outside the candidates can score >= tau_c.  Such a row has a reduced-precision
+             score <= beta_(m+1), and the pass is off by a bounded amount: with operands rounded to bf16 the
+             distance between the rounded vectors differs from the true one by at most eta = 2^-8 (|q| + max|s|)
+             (triangle inequality; 2^-9 per element, doubled for slack), so its true score is at most
+             U = -(max(sqrt(-beta_(m+1)) - eta, 0))^2 (+ fp32 accumulation slack); bf16x3 drops only the lo*lo
+             products, U = beta_(m+1) + 2^-15 |q| max|s|.  U < tau_c certifies the query.
+
+        m is sized from the same bounds before the gather (blocks that could still reach the k-th best block
+        score), capped at `max_blocks`.  Uncertified queries take the dense exact path, so the result is exact for
+        every input; the budget only decides how often the cheap path is enough (`last_topk_path` counts both)."""
+        from .kernel import dense_scores
+        from .utils import rank_rows
+
+        if self.kind != "euclidean":
+            raise NotImplementedError("topk_exact is provided for the euclidean kernel")
+        lib = load()
+        dev, n, d = self.device, len(self), self.d
+        if source_feats.shape[0] != n or source_feats.shape[1:].numel() != d:
+            raise ValueError("source_feats must be the (N, d) tensor the bank was built from")
+        k = min(int(k), n)
+        src_all = source_feats.detach().float().reshape(n, d)
+        out = torch.empty((q.shape[0], k), dtype=torch.int64, device=dev)
+        smax = self.sqnorm.max().sqrt()
+        lane = torch.arange(64, device=dev)
+        self.last_topk_path = {"blocks": 0, "dense": 0}
+        for i0 in range(0, q.shape[0], query_chunk):
+            qc = q[i0:i0 + query_chunk].detach().float().reshape(-1, d).contiguous()
+            b = qc.shape[0]
+            best, q_sq = self.block_best(qc)                      # (b, nblk) scores = -squared distance
+            nblk = best.shape[1]
+            order = rank_rows(best, min(nblk, max(max_blocks + 1, k)))   # blocks by best score, descending
+            sorted_best = best.gather(1, order)
+            slack = 2.0 ** -18 * (q_sq + smax * smax)             # fp32 accumulation of the dot products
+            if self.precision == _abi.PREC_BF16:
+                eta = 2.0 ** -8 * (q_sq.sqrt() + smax)
+
+                def upper(beta):      # largest true score a row with reduced-precision score beta can have
+                    return -((-beta - slack).clamp_min(0).sqrt() - eta).clamp_min(0) ** 2 + slack
+
+                def lower(beta):      # smallest
+                    return -((-beta + slack).clamp_min(0).sqrt() + eta) ** 2 - slack
+            else:
+                lolo = 2.0 ** -15 * q_sq.sqrt() * smax + 2 * slack
+                upper, lower = (lambda beta: beta + lolo), (lambda beta: beta - lolo)
+            if nblk > k:
+                # the k best blocks each hold a row scoring >= lower(beta_(k)): blocks whose best row cannot reach
+                # that are out.  The certificate below is what guarantees exactness; this only sizes the gather.
+                need = (upper(sorted_best.t()).t() >= lower(sorted_best[:, k - 1])[:, None]).sum(1)
+                m = int(need.max().item())
+            else:
+                m = nblk
+            m = min(max(m, (k + 63) // 64), max_blocks, nblk)
+            pending = torch.arange(b, device=dev)
+            if m * 64 >= k:
+                rows = (order[:, :m, None] * 64 + lane).reshape(b, m * 64)
+                src = rows.clamp_max(n - 1)
+                if self.perm is not None:
+                    src = self.perm[src]
+                src = torch.where(rows < n, src, torch.full_like(src, 1 << 40))
+                # ascending source index = the dense path's tie order (indices below 2^24 are exact in fp32)
+                src = src.gather(1, rank_rows(-src.float(), m * 64)) if n < (1 << 24) else src.sort(1).values
+                valid = src < n
+                src = src.clamp_max(n - 1)
+                cand = src_all.index_select(0, src.reshape(-1)).reshape(b, m * 64, d)
+                sc = torch.empty((b, m * 64), dtype=torch.float32, device=dev)
+                check(lib.nw_direct_scores(KIND["euclidean"], 1.0, ptr(qc), b, d, ptr(cand), m * 64, 1, ptr(sc),
+                                           stream_of(dev)), "nw_direct_scores")
+                sc = torch.where(valid, sc, torch.full_like(sc, float("-inf")))
+                pos = rank_rows(sc, k)
+                tau = sc.gather(1, pos[:, k - 1:k]).flatten()
+                ok = upper(sorted_best[:, m]) < tau if m < nblk else torch.ones_like(tau, dtype=torch.bool)
+                out[i0 + pending[ok]] = src.gather(1, pos)[ok]
+                pending = pending[~ok]
+            self.last_topk_path["blocks"] += b - int(pending.numel())
+            if pending.numel():  # too many near-ties for the candidate budget: dense exact scores for those queries
+                out[i0 + pending] = rank_rows(dense_scores("euclidean", qc[pending], src_all), k)
+                self.last_topk_path["dense"] += int(pending.numel())
+        return out
+
     def support_influence(self, q: torch.Tensor, qlabel: torch.Tensor, scale: float = 1.0,
                           source_order: bool = True) -> torch.Tensor:
         """support_influence (reference util/metric.py:23-50) computed from FEATURES in two tensor-core passes:

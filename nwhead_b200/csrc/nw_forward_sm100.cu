@@ -115,6 +115,7 @@ struct Params {
 constexpr int MODE_CLASS_LSE = 0;       // online softmax + per-class sums (the NW head)
 constexpr int MODE_EMIT_SCORES = 1;     // dense per-pair output: the similarity scores
 constexpr int MODE_EMIT_INFLUENCE = 2;  // dense per-pair output: support influence
+constexpr int MODE_EMIT_BLOCKBEST = 3;  // best score of every block of 64 support rows (candidate search for top-k)
 // (the emit kind is a template parameter: one kernel with a runtime switch and logf inlined 64 times was > 64 KB
 //  of SASS and ran 4x slower on instruction fetch)
 
@@ -264,6 +265,24 @@ __device__ __forceinline__ void emit_chunk(float (&acc)[32], const float* __rest
     }
   }
   __syncwarp();
+}
+
+// MODE_EMIT_BLOCKBEST: best score of this thread's query row over one 32-column chunk (padding columns excluded).
+template <int EPI>
+__device__ __forceinline__ float chunk_best(const float (&acc)[32], const float* __restrict__ cadd, float qn,
+                                            float scale, int n_valid) {
+  float best = __int_as_float(0xff800000);
+  if (EPI == NW_EPI_EUCLID) {
+    float dmin = __int_as_float(0x7f800000);  // padding columns carry cadd = +inf and never win
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dmin = fminf(dmin, fmaf(-2.0f, acc[i], qn + cadd[i]));
+    best = -sqrt_approx(fmaxf(dmin, 0.0f));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < n_valid) best = fmaxf(best, acc[i] * scale);
+  }
+  return n_valid > 0 ? best : __int_as_float(0xff800000);
 }
 
 template <int EPI, int NCTA, int MODE>
@@ -501,6 +520,14 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             tmem_ld_32x32(t_addr + c * 32, acc0);
             tmem_ld_32x32(t_addr + (c + 1) * 32, acc1);
             tmem_ld_wait();
+            if (MODE == MODE_EMIT_BLOCKBEST) {
+              const float b0 = chunk_best<EPI>(acc0, meta.cadd + c * 32, qn, p.scale_log2 * kLn2, n1 - (j0 + c * 32));
+              const float b1 = chunk_best<EPI>(acc1, meta.cadd + (c + 1) * 32, qn, p.scale_log2 * kLn2,
+                                               n1 - (j0 + (c + 1) * 32));
+              // out[block][query]: 32 consecutive query rows per warp -> one coalesced 128-byte store
+              if (flush.row_valid) p.emit_out[(long long)(t * (BN / 64) + (c >> 1)) * p.emit_ld + row] = fmaxf(b0, b1);
+              continue;
+            }
             const int row0 = (qg * NCTA + int(cta_rank)) * BM + ew * 32;
             float(*stg)[33] = tail->stage[warp - EPI_WARP0];
             emit_chunk<EPI, INFL>(acc0, meta.cadd + c * 32, meta.lab + c * 32, qn, p.scale_log2 * kLn2, e_z, e_p, e_qy,
@@ -944,15 +971,16 @@ extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, co
                                void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NW_REQUIRE(epilogue == NW_EPI_EUCLID || epilogue == NW_EPI_LINEAR, NW_ERR_INVALID, "unknown epilogue %d", epilogue);
-  NW_REQUIRE(emit_kind == NW_EMIT_SCORES || emit_kind == NW_EMIT_INFLUENCE, NW_ERR_INVALID, "unknown emit kind %d",
-             emit_kind);
+  NW_REQUIRE(emit_kind == NW_EMIT_SCORES || emit_kind == NW_EMIT_INFLUENCE || emit_kind == NW_EMIT_BLOCK_BEST,
+             NW_ERR_INVALID, "unknown emit kind %d", emit_kind);
   NW_REQUIRE(q_bf16 && bank_bf16 && out, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(epilogue != NW_EPI_EUCLID || (q_sqnorm && s_sqnorm), NW_ERR_INVALID,
              "the euclidean epilogue needs q_sqnorm and s_sqnorm");
   NW_REQUIRE(emit_kind != NW_EMIT_INFLUENCE || (labels && row_lse && p_query && qlabel), NW_ERR_INVALID,
              "influence needs labels, row_lse, p_query and qlabel");
   NW_REQUIRE(row_elems > 0 && row_elems % k1::BK == 0, NW_ERR_INVALID, "row_elems must be a positive multiple of 64");
-  NW_REQUIRE(ld_out >= n_support, NW_ERR_INVALID, "ld_out must be >= n_support");
+  NW_REQUIRE(emit_kind == NW_EMIT_BLOCK_BEST ? ld_out >= n_query : ld_out >= n_support, NW_ERR_INVALID,
+             "ld_out must be >= n_support (>= n_query for NW_EMIT_BLOCK_BEST)");
   NW_REQUIRE((reinterpret_cast<uintptr_t>(q_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(bank_bf16) & 15) == 0,
              NW_ERR_INVALID, "bf16 operands must be 16-byte aligned");
   int rc = nw_device_check();
@@ -989,17 +1017,16 @@ extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, co
   p.row_lse = row_lse;
   p.p_query = p_query;
   p.qlabel = qlabel;
-  const int key = (epilogue == NW_EPI_EUCLID ? 0 : 4) + (ncta == 2 ? 2 : 0) + (emit_kind == NW_EMIT_INFLUENCE ? 1 : 0);
-  switch (key) {
-    case 0: rc = k1::launch_forward<NW_EPI_EUCLID, 1, k1::MODE_EMIT_SCORES>(map_q, map_s, p, plan.grid, stream); break;
-    case 1: rc = k1::launch_forward<NW_EPI_EUCLID, 1, k1::MODE_EMIT_INFLUENCE>(map_q, map_s, p, plan.grid, stream); break;
-    case 2: rc = k1::launch_forward<NW_EPI_EUCLID, 2, k1::MODE_EMIT_SCORES>(map_q, map_s, p, plan.grid, stream); break;
-    case 3: rc = k1::launch_forward<NW_EPI_EUCLID, 2, k1::MODE_EMIT_INFLUENCE>(map_q, map_s, p, plan.grid, stream); break;
-    case 4: rc = k1::launch_forward<NW_EPI_LINEAR, 1, k1::MODE_EMIT_SCORES>(map_q, map_s, p, plan.grid, stream); break;
-    case 5: rc = k1::launch_forward<NW_EPI_LINEAR, 1, k1::MODE_EMIT_INFLUENCE>(map_q, map_s, p, plan.grid, stream); break;
-    case 6: rc = k1::launch_forward<NW_EPI_LINEAR, 2, k1::MODE_EMIT_SCORES>(map_q, map_s, p, plan.grid, stream); break;
-    default: rc = k1::launch_forward<NW_EPI_LINEAR, 2, k1::MODE_EMIT_INFLUENCE>(map_q, map_s, p, plan.grid, stream); break;
-  }
+  const bool euc = epilogue == NW_EPI_EUCLID;
+#define NW_LAUNCH_EMIT(MODE_)                                                                                    \
+  rc = euc ? (ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2, MODE_>(map_q, map_s, p, plan.grid, stream)           \
+                        : k1::launch_forward<NW_EPI_EUCLID, 1, MODE_>(map_q, map_s, p, plan.grid, stream))          \
+           : (ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2, MODE_>(map_q, map_s, p, plan.grid, stream)           \
+                        : k1::launch_forward<NW_EPI_LINEAR, 1, MODE_>(map_q, map_s, p, plan.grid, stream))
+  if (emit_kind == NW_EMIT_SCORES) NW_LAUNCH_EMIT(k1::MODE_EMIT_SCORES);
+  else if (emit_kind == NW_EMIT_INFLUENCE) NW_LAUNCH_EMIT(k1::MODE_EMIT_INFLUENCE);
+  else NW_LAUNCH_EMIT(k1::MODE_EMIT_BLOCKBEST);
+#undef NW_LAUNCH_EMIT
   return rc;
 }
 

@@ -346,14 +346,21 @@ class NWNet(nn.Module):
         '''Returns indices of nearest neighbors of x in the support set, nearest first
         (reference nwhead/nw.py:245-249: the full ranking; pass k to keep only the first k).
         exact=True  : fp32 exact-difference scores (nw_direct_scores) + full ranking, bit-exact with the
-                      reference on ties-free data.
+                      reference on ties-free data.  With k given and an euclidean bank of TOPK_EXACT_MIN_ROWS rows
+                      or more, the same ranking comes from SupportBank.topk_exact (tensor-core search over blocks
+                      of 64 rows, fp32 re-rank of the certified candidates) without the (B, N) score matrix.
         exact=False : tensor-core scores against the precomputed bank (SupportBank.topk) for large banks /
                       batches; ranking accuracy is that of the bank's operand precision.'''
         from .utils import rank_rows
 
         qfeat = self.featurizer(x).detach()
+        bank = self.support_eval.full_bank
         if not exact:
-            bank = self.support_eval.full_bank
             return bank.topk(qfeat, len(bank) if k is None else k, self.kernel.scale_value())
+        if k is not None and bank.kind == "euclidean" and len(bank) >= self.TOPK_EXACT_MIN_ROWS and k <= 1024:
+            # large bank: tensor-core candidate search + exact fp32 re-rank (same ranking, no (B, N) matrix)
+            return bank.topk_exact(qfeat, k, self.full_feat)
         distances = self.kernel(qfeat, self.full_feat)
         return rank_rows(distances, k)
+
+    TOPK_EXACT_MIN_ROWS = 65536

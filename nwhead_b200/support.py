@@ -108,8 +108,8 @@ class SupportSetEval(SupportSet):
         self._source_to_bank_row = inv
 
         # KNN and "HNSW": both exact on the GPU (no hnswlib index to build)
-        self.knn = KNN(self.full_feat, self.full_y, n_neighbors=self.n_neighbors)
-        self.hnsw = HNSW(self.full_feat, self.full_y, n_neighbors=self.n_neighbors)
+        self.knn = KNN(self.full_feat, self.full_y, n_neighbors=self.n_neighbors, bank=self.full_bank)
+        self.hnsw = HNSW(self.full_feat, self.full_y, n_neighbors=self.n_neighbors, bank=self.full_bank)
 
     def get_support(self, mode, x=None):
         '''Returns the support for an inference mode: a SupportBank for 'full' / 'cluster' / 'random', a list of

@@ -181,13 +181,21 @@ class KNN:
     """Exact k-nearest-neighbour support (reference nwhead/utils.py:178-193): the k nearest bank rows
     of every query, concatenated into ONE shared support of B*k rows."""
 
-    def __init__(self, data, labels, n_neighbors=20) -> None:
+    BANK_SEARCH_MIN_ROWS = 65536
+
+    def __init__(self, data, labels, n_neighbors=20, bank=None) -> None:
         self.data, self.labels, self.n_neighbors = data, labels, n_neighbors
+        # an euclidean SupportBank over the same rows: large searches go through its tensor-core block search
+        # (SupportBank.topk_exact: same ranking as the dense scores, bit for bit)
+        self.bank = bank if bank is not None and bank.kind == "euclidean" else None
 
     def __call__(self, x):
         from .kernel import dense_scores
 
-        idx = rank_rows(dense_scores("euclidean", x, self.data), self.n_neighbors).flatten()
+        if self.bank is not None and len(self.bank) >= self.BANK_SEARCH_MIN_ROWS:
+            idx = self.bank.topk_exact(x, self.n_neighbors, self.data).flatten()
+        else:
+            idx = rank_rows(dense_scores("euclidean", x, self.data), self.n_neighbors).flatten()
         return self.data.index_select(0, idx), self.labels.index_select(0, idx)
 
 

@@ -268,3 +268,33 @@ def test_head_caches_the_bank_of_unchanged_support_tensors(cuda_lib):
         c = head(qx, sx, sy)
         assert head._bank_cache[-1][1] is not bank
     assert_head_parity(c, O.nw_forward(q, s * 1.5, y, 6, "euclidean"))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_exact_topk_via_block_candidates(cuda_lib, precision):
+    """SupportBank.topk_exact == dense fp32 ranking (nw_direct_scores + nw_rank_rows), bit for bit, on a shuffled
+    support with ragged N; also with a candidate budget so small that some queries take the dense fallback."""
+    from nwhead_b200 import SupportBank
+    from nwhead_b200.kernel import dense_scores
+    from nwhead_b200.utils import rank_rows
+
+    rng = np.random.default_rng(31)
+    B, N, d, C, k = 45, 20011, 64, 50, 10
+    y = rng.integers(0, C, N).astype(np.int64)
+    mu = rng.normal(size=(C, d)) * 2
+    s = (mu[y] + rng.normal(size=(N, d))).astype(np.float32)
+    q = (mu[rng.integers(0, C, B)] + rng.normal(size=(B, d))).astype(np.float32)
+    sx, qx = torch.from_numpy(s).to(DEV), torch.from_numpy(q).to(DEV)
+    bank = SupportBank.build(sx, torch.from_numpy(y).to(DEV), C, "euclidean", precision)
+    want = rank_rows(dense_scores("euclidean", qx, sx), k)
+    got = bank.topk_exact(qx, k, sx, query_chunk=16)
+    assert torch.equal(got, want)
+    ref = O.topk_neighbors(q, s, k)
+    assert np.array_equal(got.cpu().numpy(), ref)            # and equal to the float64 oracle on this data
+    assert torch.equal(bank.topk_exact(qx, k, sx, max_blocks=1), want)   # forces the dense fallback for most rows
+    bb, _ = bank.block_best(qx)
+    dense = dense_scores("euclidean", qx, sx)
+    assert bb.shape == (B, (N + 63) // 64)
+    blk_max = torch.full((B, bb.shape[1] * 64), float("-inf"), device=DEV)
+    blk_max[:, :N] = dense if bank.perm is None else dense[:, bank.perm]
+    assert (bb - blk_max.view(B, -1, 64).amax(2)).abs().max().item() < (0.05 if precision == "bf16" else 1e-3)

@@ -68,6 +68,15 @@ def test_precompute_predict_neighbors(cuda_lib, golden_flow, kind):
             nb = net.get_neighbors(xq).cpu().numpy()
             assert nb.shape == g[f"{kind}/neighbors"].shape and nb.dtype == np.int64
             assert np.array_equal(nb, g[f"{kind}/neighbors"])
+            # the large-bank route (tensor-core block search + exact re-rank) gives the same neighbours and
+            # the same knn-mode prediction; the thresholds are lowered so that this small bank takes it
+            k = 5
+            dense_nb = net.get_neighbors(xq, k).cpu().numpy()
+            net.TOPK_EXACT_MIN_ROWS = 1
+            assert np.array_equal(net.get_neighbors(xq, k).cpu().numpy(), dense_nb)
+            assert sum(net.support_eval.full_bank.last_topk_path.values()) == len(xq)
+            net.support_eval.knn.BANK_SEARCH_MIN_ROWS = 1
+            assert np.array_equal(net.predict(xq, mode="knn").cpu().numpy(), out)
 
 
 @pytest.mark.parametrize("kind", ["euclidean", "cosine"])

@@ -232,6 +232,15 @@ NW_API size_t nw_class_centroids_workspace_bytes(int n_classes, int d);
 NW_API int nw_class_centroids(const float* rows, int d, int64_t ld, const int64_t* perm, const int32_t* offsets,
                        int n_classes, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* k-means assignment step (K3b) — the inner loop of compute_clusters(embeddings, labels, n_clusters=k > 1)
+ * (nwhead/utils.py:230: one scikit-learn KMeans fit per class).  group[i] is the class of row i (0 <= group <
+ * n_groups); centroids is (n_groups * k, d) with the k centroids of a class stored consecutively.  Row i is
+ * compared with the k centroids of its own class only (squared euclidean distance, exact fp32 differences):
+ * assign_out[i] = group[i] * k + argmin_j (lowest j on ties), dist_out[i] = that squared distance (may be
+ * NULL).  The update step is nw_class_centroids over the rows ordered by assign_out. */
+NW_API int nw_kmeans_assign(const float* rows, int d, int64_t ld, const int32_t* group, int64_t n_rows,
+                     const float* centroids, int k, int32_t* assign_out, float* dist_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * support_influence (K4) — replaces the per-query Python loop of util/metric.py:23-50.
  * ------------------------------------------------------------------------------------------ */

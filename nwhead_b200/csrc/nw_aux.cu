@@ -230,6 +230,105 @@ static long long next_pow2(long long n) {
   return p;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K3b: k-means assignment step (reference compute_clusters with n_clusters > 1, nwhead/utils.py:230:
+// per-class KMeans).  Every row is compared with the k centroids of ITS OWN class only (exact fp32
+// differences), one warp per row, 8 centroids per pass over the row; the centroids of a class are
+// shared by its rows and stay in L1/L2.  Algorithmic traffic: N*d*4 bytes read + 8 bytes per row written.
+// ---------------------------------------------------------------------------------------------
+constexpr int KM_TILE = 8;
+constexpr int KM_THREADS = 256;
+
+// the rows are read once: keep them out of L1 so that the class's centroids stay there
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(const float* __restrict__ rows, int d, long long ld,
+                                                                   const int32_t* __restrict__ group,
+                                                                   long long n_rows,
+                                                                   const float* __restrict__ cent, int k,
+                                                                   int32_t* __restrict__ assign,
+                                                                   float* __restrict__ dist) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (KM_THREADS / 32);
+  for (long long row = (long long)blockIdx.x * (KM_THREADS / 32) + (threadIdx.x >> 5); row < n_rows; row += warps) {
+    const int g = group[row];
+    const float* x = rows + row * ld;
+    const float* c0 = cent + (size_t)g * k * d;
+    float best = INFINITY;
+    int best_j = 0;
+    for (int j0 = 0; j0 < k; j0 += KM_TILE) {
+      const int kk = min(KM_TILE, k - j0);
+      float acc[KM_TILE];
+#pragma unroll
+      for (int j = 0; j < KM_TILE; ++j) acc[j] = 0.f;
+      if (VEC) {
+        int e = lane * 4;
+        for (; e + 3 * 128 < d; e += 4 * 128) {  // 4 row loads in flight per lane before the first use
+          float4 xv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) xv[u] = ld_stream_f4(x + e + u * 128);
+#pragma unroll
+          for (int j = 0; j < KM_TILE; ++j) {
+            if (j < kk) {
+              const float* cj = c0 + (size_t)(j0 + j) * d + e;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(cj + u * 128));
+                const float a = xv[u].x - cv.x, b = xv[u].y - cv.y, c = xv[u].z - cv.z, w = xv[u].w - cv.w;
+                acc[j] += a * a + b * b + c * c + w * w;
+              }
+            }
+          }
+        }
+        for (; e < d; e += 128) {
+          const float4 xv = ld_stream_f4(x + e);
+#pragma unroll
+          for (int j = 0; j < KM_TILE; ++j) {
+            if (j < kk) {
+              const float4 cv = __ldg(reinterpret_cast<const float4*>(c0 + (size_t)(j0 + j) * d + e));
+              const float a = xv.x - cv.x, b = xv.y - cv.y, c = xv.z - cv.z, w = xv.w - cv.w;
+              acc[j] += a * a + b * b + c * c + w * w;
+            }
+          }
+        }
+      } else {
+        for (int e = lane; e < d; e += 32) {
+          const float xv = x[e];
+#pragma unroll
+          for (int j = 0; j < KM_TILE; ++j) {
+            if (j < kk) {
+              const float a = xv - __ldg(c0 + (size_t)(j0 + j) * d + e);
+              acc[j] += a * a;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KM_TILE; ++j) {
+        if (j < kk) {
+          const float v = warp_sum(acc[j]);
+          if (v < best) {  // strict: the lowest centroid index wins a tie
+            best = v;
+            best_j = j0 + j;
+          }
+        }
+      }
+    }
+    if (lane == 0) {
+      assign[row] = g * k + best_j;
+      if (dist) dist[row] = best;
+    }
+  }
+}
+
 }  // namespace aux
 }  // namespace nw
 
@@ -265,6 +364,24 @@ extern "C" int nw_class_centroids(const float* rows, int d, int64_t ld, const in
   const long long total = (long long)n_classes * d;
   aux::centroid_finish_kernel<<<unsigned(ceil_div_ll(total, 256)), 256, 0, stream>>>(partial, offsets, n_classes, d,
                                                                                     out);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_kmeans_assign(const float* rows, int d, int64_t ld, const int32_t* group, int64_t n_rows,
+                                const float* centroids, int k, int32_t* assign_out, float* dist_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(rows && group && centroids && assign_out, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(d > 0 && ld >= d && n_rows > 0 && k > 0, NW_ERR_INVALID, "bad shape");
+  const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(centroids) & 15) == 0);
+  auto kernel = vec ? aux::kmeans_assign_kernel<true> : aux::kmeans_assign_kernel<false>;
+  int resident = 0;  // persistent grid: exactly the blocks that fit, each striding over the rows
+  NW_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, aux::KM_THREADS, 0));
+  const long long want = ceil_div_ll(n_rows, aux::KM_THREADS / 32);
+  const long long fit = (long long)sm_count() * (resident > 0 ? resident : 1);
+  kernel<<<unsigned(want < fit ? want : fit), aux::KM_THREADS, 0, stream>>>(rows, d, ld, group, n_rows, centroids, k,
+                                                                            assign_out, dist_out);
   NW_CUDA_OK(cudaGetLastError());
   return NW_OK;
 }

@@ -9,7 +9,7 @@ import torch
 
 from .bank import SupportBank
 from .utils import (DatasetMetadata, FeatureDataset, FullDataset, HNSW, InfiniteUniformClassLoader, KNN,
-                    class_centroids)
+                    class_centroids, kmeans_centroids)
 
 
 class SupportSet:
@@ -90,12 +90,16 @@ class SupportSetEval(SupportSet):
             self.env_banks = [SupportBank.build(f, y, self.n_classes, self.kernel_type, self.precision)
                               for f, y in zip(sfeat_env, sy_env)]
 
-        # Cluster: n_shot_cluster == 1 -> class means reduced on the GPU from the fp32 features
-        if self.n_shot_cluster != 1:
-            raise NotImplementedError("n_shot_cluster > 1 (host-side KMeans in the reference) is outside the B200 path")
-        self.cluster_feat, self.cluster_y = class_centroids(
-            sfeat if sfeat.stride(1) == 1 else sfeat.contiguous(), self.full_bank.perm, self.full_bank.offsets,
-            self.n_classes)
+        # Cluster: n_shot_cluster == 1 -> class means reduced on the GPU from the fp32 features;
+        # n_shot_cluster > 1 -> per-class k-means for all classes at once (nw_kmeans_assign + nw_class_centroids)
+        cfeat = sfeat if sfeat.stride(1) == 1 else sfeat.contiguous()
+        if self.n_shot_cluster == 1:
+            self.cluster_feat, self.cluster_y = class_centroids(cfeat, self.full_bank.perm, self.full_bank.offsets,
+                                                                self.n_classes)
+        else:
+            self.cluster_feat, self.cluster_y = kmeans_centroids(
+                cfeat, sy.to(torch.int32).contiguous(), self.full_bank.perm, self.full_bank.offsets, self.n_classes,
+                self.n_shot_cluster)
         self.cluster_bank = SupportBank.build(self.cluster_feat, self.cluster_y, self.n_classes, self.kernel_type,
                                               self.precision)
 

@@ -112,17 +112,16 @@ class InfiniteUniformClassLoader(DataLoader):
 
 
 def compute_clusters(embeddings, labels, n_clusters, closest=False):
-    """Cluster-mode support (reference nwhead/utils.py:218-246).
+    """Cluster-mode support (reference nwhead/utils.py:218-246): per class, KMeans(n_clusters, random_state=0).
 
-    n_clusters == 1 (the NWNet default, nwhead/nw.py:24): KMeans with one cluster is the class mean,
-    computed on the GPU by nw_class_centroids.  n_clusters > 1 (k-means++ / Lloyd on the host in the
-    reference, parity unpinned) is not provided.
+    n_clusters == 1 (the NWNet default, nwhead/nw.py:24): KMeans with one cluster is the class mean, one pass of
+    nw_class_centroids.  n_clusters > 1: k-means++ seeding + Lloyd iterations for ALL classes at once on the GPU
+    (kmeans_centroids below: nw_kmeans_assign + nw_class_centroids per iteration).  scikit-learn's random stream
+    cannot be reproduced, so for k > 1 the centroids are those of the same objective run to strict convergence —
+    equal to the reference's wherever the clustering is unambiguous (tests/golden/clusters.npz), in any order
+    within a class (the NW head is invariant to the order of its support rows).
+    closest=True returns, for every centroid, the nearest real embedding of its class (nwhead/utils.py:234-241).
     Returns (centroids (U*k, d) fp32, labels (U*k,) int64) over the sorted unique labels."""
-    if n_clusters != 1 or closest:
-        raise NotImplementedError(
-            "only n_clusters=1 (the NWNet default: class means, nw_class_centroids) runs on the B200 path; the "
-            "reference's k>1 / closest=True variants are host-side scikit-learn KMeans (nwhead/utils.py:227-241) "
-            "and there is no CPU fallback here")
     dev = _abi.require_cuda(embeddings, labels)
     lib = load()
     feats = embeddings.detach()
@@ -137,14 +136,99 @@ def compute_clusters(embeddings, labels, n_clusters, closest=False):
     lab32 = torch.empty((n,), dtype=torch.int32, device=dev)
     status = torch.empty((2,), dtype=torch.int32, device=dev)
     check(lib.nw_labels_to_i32(ptr(labels), None, n, n_classes, ptr(lab32), ptr(status), st), "nw_labels_to_i32")
-    perm = None
+    perm, sorted32 = None, lab32
     if status[1].item():
         perm = torch.sort(labels, stable=True).indices.contiguous()
-        check(lib.nw_labels_to_i32(ptr(labels), ptr(perm), n, n_classes, ptr(lab32), ptr(status), st),
+        sorted32 = torch.empty_like(lab32)
+        check(lib.nw_labels_to_i32(ptr(labels), ptr(perm), n, n_classes, ptr(sorted32), ptr(status), st),
               "nw_labels_to_i32")
     offsets = torch.empty((n_classes + 1,), dtype=torch.int32, device=dev)
-    check(lib.nw_class_offsets(ptr(lab32), n, n_classes, ptr(offsets), st), "nw_class_offsets")
-    return class_centroids(feats, perm, offsets, n_classes)
+    check(lib.nw_class_offsets(ptr(sorted32), n, n_classes, ptr(offsets), st), "nw_class_offsets")
+    if n_clusters == 1 and not closest:
+        return class_centroids(feats, perm, offsets, n_classes)
+    return kmeans_centroids(feats, lab32, perm, offsets, n_classes, n_clusters, closest=closest)
+
+
+def _kmeans_assign(feats, group, centroids, k):
+    """nw_kmeans_assign: (assignment group*k + j, squared distance to the chosen centroid) for every row."""
+    lib = load()
+    dev = feats.device
+    n, d = feats.shape
+    assign = torch.empty((n,), dtype=torch.int32, device=dev)
+    dist = torch.empty((n,), dtype=torch.float32, device=dev)
+    check(lib.nw_kmeans_assign(ptr(feats), d, feats.stride(0), ptr(group), n, ptr(centroids), k, ptr(assign),
+                               ptr(dist), stream_of(dev)), "nw_kmeans_assign")
+    return assign, dist
+
+
+def kmeans_centroids(feats, group, perm, offsets, n_classes, k, closest=False, seed=0, max_iter=300):
+    """Per-class k-means for all classes at once (reference nwhead/utils.py:227-231, one sklearn fit per class).
+
+    feats (N, d) fp32; group (N,) int32 class of every row; perm/offsets: the class-sorted order of the rows
+    (SupportBank.perm / .offsets).  Seeding is k-means++ (each further centre drawn with probability
+    proportional to the squared distance to the nearest chosen one) from numpy RandomState(seed): one uniform per
+    class and centre.  Lloyd iterations run until no row changes cluster (sklearn's strict-convergence stop) or
+    max_iter (sklearn's default 300); an emptied cluster keeps its centre."""
+    import numpy as np
+
+    lib = load()
+    dev = feats.device
+    n, d = feats.shape
+    st = stream_of(dev)
+    lo, hi = offsets[:-1].long(), offsets[1:].long()
+    cnt = hi - lo
+    present = (cnt > 0).nonzero().flatten()
+    if bool((cnt[present] < k).any()):
+        raise ValueError(f"a class has fewer rows than n_clusters={k}")   # as sklearn's KMeans.fit does
+    to_src = (lambda pos: pos) if perm is None else (lambda pos: perm[pos])
+    rng = np.random.RandomState(seed)
+    cent = torch.zeros((n_classes, k, d), dtype=torch.float32, device=dev)
+
+    def draw():
+        return torch.from_numpy(rng.random_sample(n_classes)).to(dev)
+
+    pick = lo + torch.minimum((draw() * cnt).floor().long(), (cnt - 1).clamp_min(0))
+    cent[:, 0] = feats[to_src(pick.clamp_max(n - 1))]
+    mind = torch.full((n,), float("inf"), dtype=torch.float32, device=dev)
+    last = (hi - 1).clamp_min(0)
+    for j in range(1, k):
+        _, dist = _kmeans_assign(feats, group, cent[:, j - 1].contiguous(), 1)
+        mind = torch.minimum(mind, dist)
+        cs = torch.cumsum((mind if perm is None else mind[perm]).double(), 0)
+        base = torch.where(lo > 0, cs[(lo - 1).clamp_min(0)], torch.zeros_like(cs[:1]))
+        target = base + draw() * (cs[last] - base)
+        pos = torch.minimum(torch.maximum(torch.searchsorted(cs, target, right=True), lo), last)
+        cent[:, j] = feats[to_src(pos)]
+    cent = cent.reshape(n_classes * k, d)
+
+    ws_bytes = lib.nw_class_centroids_workspace_bytes(n_classes * k, d)
+    ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=dev)
+    offs2 = torch.empty((n_classes * k + 1,), dtype=torch.int32, device=dev)
+    new = torch.empty_like(cent)
+    prev = None
+    for _ in range(max_iter):
+        assign, _ = _kmeans_assign(feats, group, cent, k)
+        if prev is not None and torch.equal(assign, prev):
+            break
+        prev = assign
+        srt = torch.sort(assign, stable=True)
+        check(lib.nw_class_offsets(ptr(srt.values), n, n_classes * k, ptr(offs2), st), "nw_class_offsets")
+        check(lib.nw_class_centroids(ptr(feats), d, feats.stride(0), ptr(srt.indices), ptr(offs2), n_classes * k,
+                                     ptr(new), ptr(ws), ws_bytes, st), "nw_class_centroids")
+        cent = torch.where((offs2[1:] > offs2[:-1])[:, None], new, cent)
+
+    cent = cent.reshape(n_classes, k, d)
+    if closest:  # nearest real embedding of the class to every centroid (nwhead/utils.py:234-241)
+        rows = torch.arange(n, device=dev)
+        g64 = group.long()
+        for j in range(k):
+            _, dist = _kmeans_assign(feats, group, cent[:, j].contiguous(), 1)
+            best = torch.full((n_classes,), float("inf"), device=dev).scatter_reduce(0, g64, dist, "amin")
+            first = torch.full((n_classes,), n, dtype=torch.int64, device=dev).scatter_reduce(
+                0, g64, torch.where(dist == best[g64], rows, torch.full_like(rows, n)), "amin")
+            cent[:, j] = feats[first.clamp_max(n - 1)]
+    out = cent.index_select(0, present).reshape(-1, d)
+    return out, present.to(torch.int64).repeat_interleave(k)
 
 
 def class_centroids(feats, perm, offsets, n_classes):

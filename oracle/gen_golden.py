@@ -130,7 +130,30 @@ def cluster_cases(ref):
     assert np.abs(oc - cf.numpy()).max() < 2e-6
     pc, py = TP.port_class_centroids(f, y)
     assert torch.equal(py, cy) and (pc - cf).abs().max() < 2e-6
-    return dict(f=f, y=y, cf=cf, cy=cy)
+    out = dict(f=f, y=y, cf=cf, cy=cy)
+    # n_clusters = 3: per-class blobs whose clustering is unambiguous, so that sklearn's KMeans (reference) and a
+    # k-means++/Lloyd run with any other random stream reach the same fixed point.  Labels are shuffled.
+    k, C3, d3, per = 3, 5, 16, 20
+    centres = torch.randn(C3, k, d3, generator=g) * 6
+    yk = torch.arange(C3).repeat_interleave(k * per)
+    yk[yk == 2] = 6                                  # class ids with gaps: 0,1,3,4,6
+    fk = (centres.reshape(C3 * k, 1, d3) + 0.3 * torch.randn(C3 * k, per, d3, generator=g)).reshape(-1, d3)
+    shuffle = torch.randperm(len(yk), generator=g)
+    fk, yk = fk[shuffle].contiguous(), yk[shuffle].contiguous()
+    cfk, cyk = ref.compute_clusters(fk.numpy(), yk.numpy(), k)
+    ok, oyk = O.kmeans_centroids(fk.numpy(), yk.numpy(), k)
+    assert np.array_equal(oyk, cyk.numpy())
+    assert O.match_centroid_sets(ok, cfk.numpy(), k) < 1e-5
+    # the head over those centroids (order within a class does not matter)
+    qk = fk[:7] + 0.1
+    head = ref.NWHead(ref.get_kernel("euclidean"), 7)
+    pk = head(qk, cfk, cyk)
+    po = O.nw_forward(qk.numpy(), ok, oyk, 7, "euclidean")
+    assert np.abs(np.exp(po) - np.exp(pk.numpy())).max() < 1e-5
+    # closest=True: nearest real embedding to every centroid
+    ck, _ = ref.compute_clusters(fk, yk.numpy(), k, closest=True)
+    out.update(k3_f=fk, k3_y=yk, k3_cf=cfk, k3_cy=cyk, k3_q=qk, k3_logp=pk, k3_closest=ck)
+    return out
 
 
 class TinyDataset(torch.utils.data.Dataset):

@@ -260,6 +260,66 @@ def class_centroids(feats, labels):
     return cent, uniq.astype(np.int64)
 
 
+def kmeans_centroids(feats, labels, k, seed=0, max_iter=300):
+    """compute_clusters(..., n_clusters=k > 1) (nwhead/utils.py:227-231): per class, k-means to strict convergence.
+
+    The reference delegates to scikit-learn's KMeans(random_state=0) (un-vendored, unpinned), whose
+    random stream is not reproducible here: PARITY OF THE SEEDING IS UNPINNED.  What is pinned (gen_golden.py,
+    tests/golden/clusters.npz) is the fixed point: on data whose clustering is unambiguous this function and the
+    reference return the same centroids up to their order within a class.
+    Seeding restated from the k-means++ definition with the product's draw order: RandomState(seed), one uniform
+    per class id in 0..max(labels) for every centre; first centre uniform over the class rows, further centres at
+    the inverse CDF of the squared distance to the nearest chosen centre (rows in class-sorted stable order).
+    Returns (centroids (U*k, d) float64, labels (U*k,))."""
+    feats = _f64(feats)
+    labels = np.asarray(labels)
+    n_classes = int(labels.max()) + 1
+    order = np.argsort(labels, kind="stable")
+    rng = np.random.RandomState(seed)
+    draws = [rng.random_sample(n_classes) for _ in range(k)]
+    out, out_y = [], []
+    for c in np.unique(labels):
+        x = feats[order[labels[order] == c]]
+        if len(x) < k:
+            raise ValueError("a class has fewer rows than n_clusters")
+        cent = [x[min(int(np.floor(draws[0][c] * len(x))), len(x) - 1)]]
+        mind = np.full(len(x), np.inf)
+        for j in range(1, k):
+            mind = np.minimum(mind, ((x - cent[-1]) ** 2).sum(1))
+            cs = np.cumsum(mind)
+            pos = min(int(np.searchsorted(cs, draws[j][c] * cs[-1], side="right")), len(x) - 1)
+            cent.append(x[pos])
+        cent = np.stack(cent)
+        prev = None
+        for _ in range(max_iter):
+            d2 = ((x[:, None, :] - cent[None, :, :]) ** 2).sum(-1)
+            assign = d2.argmin(1)
+            if prev is not None and np.array_equal(assign, prev):
+                break
+            prev = assign
+            for j in range(k):
+                if (assign == j).any():
+                    cent[j] = x[assign == j].mean(0)
+        out.append(cent)
+        out_y += [c] * k
+    return np.concatenate(out), np.asarray(out_y, dtype=np.int64)
+
+
+def match_centroid_sets(a, b, k):
+    """Largest |difference| between two (U*k, d) centroid arrays after matching, inside every class, each row
+    of `a` with its nearest row of `b` (the order of KMeans centres within a class carries no meaning).
+    Returns inf when the matching is not one-to-one."""
+    a, b = _f64(a), _f64(b)
+    worst = 0.0
+    for c0 in range(0, len(a), k):
+        d2 = ((a[c0:c0 + k, None, :] - b[None, c0:c0 + k, :]) ** 2).sum(-1)
+        nearest = d2.argmin(1)
+        if len(set(nearest.tolist())) != k:
+            return float("inf")
+        worst = max(worst, np.abs(a[c0:c0 + k] - b[c0:c0 + k][nearest]).max())
+    return worst
+
+
 # --------------------------------------------------------------------------------------
 # a8: support_influence  (util/metric.py:23-50)
 # --------------------------------------------------------------------------------------

@@ -65,6 +65,64 @@ def test_class_centroids_shapes(cuda_lib, shape):
     assert np.abs(cf.cpu().numpy() - oc).max() < 5e-6
 
 
+def test_kmeans_clusters_golden(cuda_lib, golden_clusters):
+    """compute_clusters(n_clusters=3) on the GPU: same seeding and trajectory as the oracle restatement (centroids
+    in the same order, 1e-5), the reference's (scikit-learn's) centroids up to order within a class, the reference's
+    head output over them, and closest=True rows."""
+    from nwhead_b200 import NWHead, compute_clusters, get_kernel
+
+    g = golden_clusters
+    k = 3
+    f, y = torch.from_numpy(g["k3_f"]).to(DEV), torch.from_numpy(g["k3_y"]).to(DEV)
+    cf, cy = compute_clusters(f, y, k)
+    assert np.array_equal(cy.cpu().numpy(), g["k3_cy"])
+    oc, _ = O.kmeans_centroids(g["k3_f"], g["k3_y"], k)
+    assert np.abs(cf.cpu().numpy() - oc).max() < 1e-5
+    assert O.match_centroid_sets(cf.cpu().numpy(), g["k3_cf"], k) < 1e-5
+    logp = NWHead(get_kernel("euclidean"), 7)(torch.from_numpy(g["k3_q"]).to(DEV), cf, cy)
+    assert np.abs(np.exp(logp.cpu().numpy()) - np.exp(g["k3_logp"])).max() < 1e-5
+    cl, cly = compute_clusters(f, y, k, closest=True)
+    assert torch.equal(cly, cy)
+    assert O.match_centroid_sets(cl.cpu().numpy(), g["k3_closest"], k) == 0.0
+    with pytest.raises(ValueError):
+        compute_clusters(f[:4], torch.tensor([0, 0, 1, 1], device=DEV), 3)
+    # k = 1 with closest=True: the real row nearest to the class mean
+    c1, _ = compute_clusters(f, y, 1, closest=True)
+    m1, _ = compute_clusters(f, y, 1)
+    for row, (c, mean) in enumerate(zip(np.unique(g["k3_y"]), m1.cpu().numpy())):
+        x = g["k3_f"][g["k3_y"] == c]
+        assert np.array_equal(c1[row].cpu().numpy(), x[((x - mean) ** 2).sum(1).argmin()])
+
+
+@pytest.mark.parametrize("shape", [(4000, 64, 12, 4), (3000, 30, 5, 11), (20000, 2048, 8, 2)])
+def test_kmeans_clusters_against_oracle(cuda_lib, shape):
+    """Overlapping clusters, unsorted labels, d not a multiple of 4, k > 8 (two centroid passes): the GPU run follows
+    the oracle's trajectory (same seeding draws), so the centroids agree row for row; the objective is not worse."""
+    from nwhead_b200 import compute_clusters
+
+    N, d, C, k = shape
+    rng = np.random.default_rng(N + k)
+    y = rng.integers(0, C, N).astype(np.int64)
+    mu = rng.normal(size=(C, k, d)) * 1.5
+    f = (mu[y, rng.integers(0, k, N)] + rng.normal(size=(N, d))).astype(np.float32)
+    cf, cy = compute_clusters(torch.from_numpy(f).to(DEV), torch.from_numpy(y).to(DEV), k)
+    cf = cf.cpu().numpy()
+    oc, oy = O.kmeans_centroids(f, y, k)
+    assert np.array_equal(cy.cpu().numpy(), oy)
+
+    def inertia(cent):
+        tot = 0.0
+        for i, c in enumerate(np.unique(y)):
+            x = f[y == c].astype(np.float64)
+            tot += ((x[:, None] - cent[i * k:(i + 1) * k][None]) ** 2).sum(-1).min(1).sum()
+        return tot
+
+    # fp32-vs-float64 near-ties may flip single rows and let the trajectories part; the objective may not suffer
+    assert inertia(cf.astype(np.float64)) <= inertia(oc) * (1 + 1e-3)
+    if d <= 64:
+        assert np.abs(cf - oc).max() < 1e-4
+
+
 def test_support_influence_golden(cuda_lib, golden_influence):
     from nwhead_b200 import support_influence
 

@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import nw_oracle as O
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
@@ -19,7 +21,7 @@ class TinyDataset(torch.utils.data.Dataset):
         return self.x[i], self.targets[i]
 
 
-def make_net(g, kind):
+def make_net(g, kind, n_shot_cluster=1):
     import nwhead_b200
 
     feat = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(192, 16), torch.nn.ReLU())
@@ -28,7 +30,7 @@ def make_net(g, kind):
         feat[1].bias.copy_(torch.from_numpy(g["b"]))
     ds = TinyDataset(g["ds_x"], g["ds_y"])
     net = nwhead_b200.NWNet(feat, 6, support_dataset=ds, feat_dim=16, kernel_type=kind, n_shot=2, n_way=4,
-                            n_shot_random=2, n_shot_full=5, n_shot_cluster=1, n_neighbors=3, device=DEV)
+                            n_shot_random=2, n_shot_full=5, n_shot_cluster=n_shot_cluster, n_neighbors=3, device=DEV)
     return net.to(DEV), feat
 
 
@@ -77,6 +79,29 @@ def test_precompute_predict_neighbors(cuda_lib, golden_flow, kind):
             assert sum(net.support_eval.full_bank.last_topk_path.values()) == len(xq)
             net.support_eval.knn.BANK_SEARCH_MIN_ROWS = 1
             assert np.array_equal(net.predict(xq, mode="knn").cpu().numpy(), out)
+
+
+def test_cluster_mode_with_two_clusters_per_class(cuda_lib, golden_flow):
+    """n_shot_cluster=2 (reference: one scikit-learn KMeans(2) per class, nwhead/support.py:118-123): two centroids
+    per class from the GPU k-means, equal to the oracle's run on the same features; predict('cluster') is the head
+    over them."""
+    import nwhead_b200
+
+    g = golden_flow
+    net, _ = make_net(g, "euclidean", n_shot_cluster=2)
+    net.eval()
+    xq = torch.from_numpy(g["xq"]).to(DEV)
+    with torch.no_grad():
+        net.precompute()
+        se = net.support_eval
+        classes = np.unique(net.full_y.cpu().numpy())
+        assert np.array_equal(se.cluster_y.cpu().numpy(), np.repeat(classes, 2))
+        oc, _ = O.kmeans_centroids(net.full_feat.cpu().numpy(), net.full_y.cpu().numpy(), 2)
+        assert np.abs(se.cluster_feat.cpu().numpy() - oc).max() < 1e-5
+        out = net.predict(xq, mode="cluster")
+        qf = net.featurizer(xq)
+        ref = O.nw_forward(qf.cpu().numpy(), oc, np.repeat(classes, 2), 6, "euclidean")
+        assert np.abs(np.exp(out.cpu().numpy()) - np.exp(ref)).max() < 1e-3
 
 
 @pytest.mark.parametrize("kind", ["euclidean", "cosine"])

@@ -95,6 +95,17 @@ def cfg4_cluster(feats, labels, n_classes):
     ms = timed(lambda: cbank.forward(q))
     emit(config=f"cfg4 cluster-mode predict B=4096 vs {len(cbank)} centroids d={d}", ms=ms, queries_per_s=4096 / ms * 1e3,
          tflops=2.0 * 4096 * len(cbank) * d / ms / 1e9)
+    # n_shot_cluster = 3: per-class k-means for all 1000 classes at once (the reference runs 1000 sklearn fits)
+    from nwhead_b200.utils import _kmeans_assign, kmeans_centroids
+    lab32 = labels.to(torch.int32)
+    t0 = time.perf_counter()
+    c3, _ = kmeans_centroids(feats, lab32, None, bank.offsets, n_classes, 3)
+    torch.cuda.synchronize()
+    total_ms = (time.perf_counter() - t0) * 1e3
+    ms = timed(lambda: _kmeans_assign(feats, lab32, c3, 3))
+    emit(config=f"cfg4 k-means k=3 N={n} d={d} C={n_classes}", total_ms=total_ms, assign_pass_ms=ms,
+         assign_GBs=(n * d * 4 + n * 12) / ms / 1e6, peak_GBs=PEAKS["hbm_gbs"],
+         assign_frac=(n * d * 4 + n * 12) / ms / 1e6 / PEAKS["hbm_gbs"])
     return bank
 
 
@@ -237,6 +248,10 @@ def cfg1_cfg2_with_resnet18():
 
 def main():
     _abi.check(_abi.load().nw_device_check(), "nw_device_check")
+    if "--cfg4" in sys.argv:
+        feats, labels, _ = synth(1280000, 2048, 1000, 1234)
+        cfg4_cluster(feats, labels, 1000)
+        return
     if "--resnet" in sys.argv:
         cfg1_cfg2_with_resnet18()
     cfg2_episodic()

@@ -109,6 +109,13 @@ NW_API int nw_rows_to_bf16(const float* rows, int64_t n, int d, int64_t ld, cons
                     int normalize, int layout, int precision, void* out_bf16, int row_elems,
                     float* sqnorm_out, void* stream);
 
+/* resid_sq_out[i] = squared norm of what nw_rows_to_bf16 (normalize = 0) discards from row i: |x - hi|^2 for
+ * NW_PREC_BF16, |x - hi - lo|^2 for NW_PREC_BF16X3, x = rows[i, :] - center.  By the triangle inequality the
+ * distance between two rounded rows differs from the true one by at most the sum of their residual norms: the
+ * error certificate of the exact neighbour search behind NWNet.get_neighbors (nwhead/nw.py:245-249). */
+NW_API int nw_rounding_residual(const float* rows, int64_t n, int d, int64_t ld, const float* center, int precision,
+                         float* resid_sq_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused tensor-core forward (K1) — replaces, for a shared 2-D support with N > 25,
  * NWHead.forward (nwhead/nw.py:266-289): one_hot (276), expand (277-279), kernel (283:

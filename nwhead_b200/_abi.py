@@ -51,6 +51,7 @@ SIGNATURES = {
     "nw_column_mean": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nw_rows_to_bf16": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_void_p, c_int, c_void_p, c_void_p]),
+    "nw_rounding_residual": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "nw_forward_plan": (c_int, [c_int, c_int64, POINTER(ForwardPlan)]),
     "nw_forward_class_lse": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                      c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),

@@ -312,21 +312,34 @@ class SupportBank:
         )
         return out[:(n + 63) // 64, :b].t().contiguous(), q_sq
 
+    def rounding_residual(self, rows: torch.Tensor) -> torch.Tensor:
+        """(n,) norm of what this bank's operand rounding discards from each fp32 row (nw_rounding_residual)."""
+        lib = load()
+        rows = rows.detach().float().reshape(rows.shape[0], -1)
+        if rows.stride(1) != 1:
+            rows = rows.contiguous()
+        out = torch.empty((rows.shape[0],), dtype=torch.float32, device=rows.device)
+        check(lib.nw_rounding_residual(ptr(rows), rows.shape[0], self.d, rows.stride(0), ptr(self.center),
+                                       self.precision, ptr(out), stream_of(rows.device)), "nw_rounding_residual")
+        return out.sqrt()
+
     def topk_exact(self, q: torch.Tensor, k: int, source_feats: torch.Tensor, max_blocks: int = 64,
                    query_chunk: int = 128) -> torch.Tensor:
         """EXACT k nearest supports (euclidean banks), indices into `source_feats` (the fp32 tensor the bank was
         built from), nearest first — the same ranking as the dense fp32 path (ties by ascending index), without
         the (B, N) score matrix:
 
-          1. tensor-core pass: best reduced-precision score beta_j of every query in every block j of 64 bank rows;
+          1. tensor-core pass: best reduced-precision score beta_j = -distance of every query in every block j of
+             64 bank rows;
           2. candidates = the rows of the m best blocks; exact fp32 differences (nw_direct_scores) over those rows
              only, ranked by nw_rank_rows -> tau_c, the exact k-th best candidate score;
           3. certificate: no row outside the candidates can score >= tau_c.  Such a row has a reduced-precision
-             score <= beta_(m+1), and the pass is off by a bounded amount: with operands rounded to bf16 the
-             distance between the rounded vectors differs from the true one by at most eta = 2^-8 (|q| + max|s|)
-             (triangle inequality; 2^-9 per element, doubled for slack), so its true score is at most
-             U = -(max(sqrt(-beta_(m+1)) - eta, 0))^2 (+ fp32 accumulation slack); bf16x3 drops only the lo*lo
-             products, U = beta_(m+1) + 2^-15 |q| max|s|.  U < tau_c certifies the query.
+             score <= beta_(m+1), and the pass is off by a bounded amount: the distance between two rounded rows
+             differs from the true one by at most eta = |q - q~| + max_j |s_j - s~_j| (triangle inequality; the
+             residual norms are measured, nw_rounding_residual), and the fp32 accumulation moves the squared
+             distance by at most e2 = 2^-18 (|q|^2 + max|s|^2).  So its true score is at most
+             U = -(sqrt(beta_(m+1)^2 - e2) - eta); U < tau_c certifies the query.  (bf16x3 drops the lo.lo products
+             as well: the squared distance is short by at most (2^-8 (|q| + max|s|))^2.)
 
         m is sized from the same bounds before the gather (blocks that could still reach the k-th best block
         score), capped at `max_blocks`.  Uncertified queries take the dense exact path, so the result is exact for
@@ -342,29 +355,32 @@ class SupportBank:
             raise ValueError("source_feats must be the (N, d) tensor the bank was built from")
         k = min(int(k), n)
         src_all = source_feats.detach().float().reshape(n, d)
+        if getattr(self, "_resid_key", None) != (src_all.data_ptr(), src_all._version):
+            self._resid_max = self.rounding_residual(src_all).max()
+            self._resid_key = (src_all.data_ptr(), src_all._version)
         out = torch.empty((q.shape[0], k), dtype=torch.int64, device=dev)
-        smax = self.sqnorm.max().sqrt()
+        smax = self.sqnorm.max().sqrt() * (1 + 2.0 ** -7)         # norms of the rounded rows -> of the rows
         lane = torch.arange(64, device=dev)
+        fp32_sum = 1.0 - (d + 8) * 2.0 ** -24                     # the exact path's own summation error (relative)
         self.last_topk_path = {"blocks": 0, "dense": 0}
         for i0 in range(0, q.shape[0], query_chunk):
             qc = q[i0:i0 + query_chunk].detach().float().reshape(-1, d).contiguous()
             b = qc.shape[0]
-            best, q_sq = self.block_best(qc)                      # (b, nblk) scores = -squared distance
+            best, q_sq = self.block_best(qc)                      # (b, nblk) scores = -distance
             nblk = best.shape[1]
             order = rank_rows(best, min(nblk, max(max_blocks + 1, k)))   # blocks by best score, descending
             sorted_best = best.gather(1, order)
-            slack = 2.0 ** -18 * (q_sq + smax * smax)             # fp32 accumulation of the dot products
-            if self.precision == _abi.PREC_BF16:
-                eta = 2.0 ** -8 * (q_sq.sqrt() + smax)
+            qn = q_sq.sqrt() * (1 + 2.0 ** -7)
+            e2 = 2.0 ** -18 * (qn * qn + smax * smax)             # fp32 accumulation, squared-distance domain
+            eta = (self.rounding_residual(qc) + self._resid_max) * (1 + 2.0 ** -10)
+            lolo = (2.0 ** -8 * (qn + smax)) ** 2 if self.precision != _abi.PREC_BF16 else torch.zeros_like(e2)
 
-                def upper(beta):      # largest true score a row with reduced-precision score beta can have
-                    return -((-beta - slack).clamp_min(0).sqrt() - eta).clamp_min(0) ** 2 + slack
+            def upper(beta):      # largest exact-path score of a row whose reduced-precision score is beta
+                return -((beta * beta - e2).clamp_min(0).sqrt() - eta).clamp_min(0) * fp32_sum
 
-                def lower(beta):      # smallest
-                    return -((-beta + slack).clamp_min(0).sqrt() + eta) ** 2 - slack
-            else:
-                lolo = 2.0 ** -15 * q_sq.sqrt() * smax + 2 * slack
-                upper, lower = (lambda beta: beta + lolo), (lambda beta: beta - lolo)
+            def lower(beta):      # smallest
+                return -((beta * beta + e2 + lolo).sqrt() + eta) / fp32_sum
+
             if nblk > k:
                 # the k best blocks each hold a row scoring >= lower(beta_(k)): blocks whose best row cannot reach
                 # that are out.  The certificate below is what guarantees exactness; this only sizes the gather.

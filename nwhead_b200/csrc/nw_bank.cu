@@ -197,6 +197,26 @@ __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restri
   if (lane == 0 && sqnorm_out) sqnorm_out[row] = sq;
 }
 
+// Squared norm of what the bf16 rounding discards, per row: |x - hi|^2 (NW_PREC_BF16) or |x - hi - lo|^2
+// (NW_PREC_BF16X3), with x = rows[i, :] - center exactly as rows_to_bf16_kernel forms it.  One warp per row.
+__global__ void __launch_bounds__(256) rounding_residual_kernel(const float* __restrict__ rows, long long n, int d,
+                                                                long long ld, const float* __restrict__ center,
+                                                                int precision, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* src = rows + row * ld;
+  float acc = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float x = src[c] - (center ? center[c] : 0.f);
+    float r = x - __bfloat162float(__float2bfloat16_rn(x));
+    if (precision == NW_PREC_BF16X3) r -= __bfloat162float(__float2bfloat16_rn(r));
+    acc += r * r;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+
 }  // namespace k0
 }  // namespace nw
 
@@ -287,6 +307,19 @@ extern "C" int nw_rows_to_bf16(const float* rows, int64_t n, int d, int64_t ld, 
   else
     k0::rows_to_bf16_kernel<false><<<unsigned(blocks), warps_per_block * 32, 0, stream>>>(
         rows, n, d, ld, perm, center, normalize, layout, precision, out, row_elems, sqnorm_out);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_rounding_residual(const float* rows, int64_t n, int d, int64_t ld, const float* center,
+                                    int precision, float* resid_sq_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(rows && resid_sq_out, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n > 0 && d > 0 && ld >= d, NW_ERR_INVALID, "bad shape n=%lld d=%d ld=%lld", (long long)n, d, (long long)ld);
+  NW_REQUIRE(precision == NW_PREC_BF16 || precision == NW_PREC_BF16X3, NW_ERR_INVALID, "unknown precision %d", precision);
+  const long long blocks = ceil_div_ll(n, 8);
+  NW_REQUIRE(blocks < (1ll << 31), NW_ERR_UNSUPPORTED, "too many rows");
+  k0::rounding_residual_kernel<<<unsigned(blocks), 256, 0, stream>>>(rows, n, d, ld, center, precision, resid_sq_out);
   NW_CUDA_OK(cudaGetLastError());
   return NW_OK;
 }

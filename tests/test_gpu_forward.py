@@ -292,6 +292,18 @@ def test_exact_topk_via_block_candidates(cuda_lib, precision):
     ref = O.topk_neighbors(q, s, k)
     assert np.array_equal(got.cpu().numpy(), ref)            # and equal to the float64 oracle on this data
     assert torch.equal(bank.topk_exact(qx, k, sx, max_blocks=1), want)   # forces the dense fallback for most rows
+    assert bank.last_topk_path["dense"] > 0
+    # adversarial: thousands of rows within 1e-3 of each other around every query (far below bf16 resolution),
+    # spread over all blocks by the label shuffle -> the certificate has to widen the search or fall back
+    s2 = s.copy()
+    near = rng.choice(N, 4000, replace=False)
+    s2[near] = q[rng.integers(0, B, 4000)] + rng.normal(size=(4000, d)).astype(np.float32) * 1e-3
+    sx2 = torch.from_numpy(s2).to(DEV)
+    bank2 = SupportBank.build(sx2, torch.from_numpy(y).to(DEV), C, "euclidean", precision)
+    assert torch.equal(bank2.topk_exact(qx, k, sx2), rank_rows(dense_scores("euclidean", qx, sx2), k))
+    res = bank.rounding_residual(sx)                          # measured residuals obey the a-priori bf16 bound
+    cn = (sx - bank.center).norm(dim=1)
+    assert (res <= cn * (2.0 ** -8 if precision == "bf16" else 2.0 ** -16)).all() and res.max() > 0
     bb, _ = bank.block_best(qx)
     dense = dense_scores("euclidean", qx, sx)
     assert bb.shape == (B, (N + 63) // 64)

@@ -244,9 +244,12 @@ NW_API int nw_class_centroids(const float* rows, int d, int64_t ld, const int64_
  * n_groups); centroids is (n_groups * k, d) with the k centroids of a class stored consecutively.  Row i is
  * compared with the k centroids of its own class only (squared euclidean distance, exact fp32 differences):
  * assign_out[i] = group[i] * k + argmin_j (lowest j on ties), dist_out[i] = that squared distance (may be
- * NULL).  The update step is nw_class_centroids over the rows ordered by assign_out. */
-NW_API int nw_kmeans_assign(const float* rows, int d, int64_t ld, const int32_t* group, int64_t n_rows,
-                     const float* centroids, int k, int32_t* assign_out, float* dist_out, void* stream);
+ * NULL).  order (may be NULL = identity) lists the rows in class-sorted order: rows are visited in that order,
+ * two per warp, so that neighbours share their class's centroid loads; results do not depend on it.
+ * The update step is nw_class_centroids over the rows ordered by assign_out. */
+NW_API int nw_kmeans_assign(const float* rows, int d, int64_t ld, const int32_t* group, const int64_t* order,
+                     int64_t n_rows, const float* centroids, int k, int32_t* assign_out, float* dist_out,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * support_influence (K4) — replaces the per-query Python loop of util/metric.py:23-50.

@@ -76,8 +76,8 @@ SIGNATURES = {
     "nw_class_centroids_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nw_class_centroids": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),
-    "nw_kmeans_assign": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p,
-                                 c_void_p]),
+    "nw_kmeans_assign": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_void_p]),
     "nw_onehot_argmax": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "nw_support_influence": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int,
                                      c_void_p, c_void_p]),

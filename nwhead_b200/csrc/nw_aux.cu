@@ -234,13 +234,15 @@ static long long next_pow2(long long n) {
 // ---------------------------------------------------------------------------------------------
 // K3b: k-means assignment step (reference compute_clusters with n_clusters > 1, nwhead/utils.py:230:
 // per-class KMeans).  Every row is compared with the k centroids of ITS OWN class only (exact fp32
-// differences), one warp per row, 8 centroids per pass over the row; the centroids of a class are
-// shared by its rows and stay in L1/L2.  Algorithmic traffic: N*d*4 bytes read + 8 bytes per row written.
+// differences).  One warp per PAIR of rows that are consecutive in class-sorted order: the two rows share
+// every centroid load (the L1 wavefronts of the centroid reads, not HBM, bound a one-row-per-warp version),
+// the rows bypass L1 so that the class's centroids stay there.  Algorithmic traffic: N*d*4 bytes read +
+// 8 bytes per row written.
 // ---------------------------------------------------------------------------------------------
-constexpr int KM_TILE = 8;
+constexpr int KM_TILE = 4;  // centroids per pass over a row
 constexpr int KM_THREADS = 256;
 
-// the rows are read once: keep them out of L1 so that the class's centroids stay there
+// the rows are read once: keep them out of L1
 __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -249,82 +251,142 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
   return v;
 }
 
+__device__ __forceinline__ float sqdiff4(const float4 x, const float4 c) {
+  const float a = x.x - c.x, b = x.y - c.y, e = x.z - c.z, w = x.w - c.w;
+  return a * a + b * b + e * e + w * w;
+}
+
+// one row against the k centroids at c0: best squared distance and its index (lowest index on ties)
+template <bool VEC>
+__device__ __forceinline__ void km_one(const float* __restrict__ x, const float* __restrict__ c0, int d, int k, int lane,
+                                       float& best, int& best_j) {
+  best = INFINITY;
+  best_j = 0;
+  for (int j0 = 0; j0 < k; j0 += KM_TILE) {
+    const int kk = min(KM_TILE, k - j0);
+    float acc[KM_TILE];
+#pragma unroll
+    for (int j = 0; j < KM_TILE; ++j) acc[j] = 0.f;
+    if (VEC) {
+      for (int e = lane * 4; e < d; e += 128) {
+        const float4 xv = ld_stream_f4(x + e);
+#pragma unroll
+        for (int j = 0; j < KM_TILE; ++j)
+          if (j < kk) acc[j] += sqdiff4(xv, __ldg(reinterpret_cast<const float4*>(c0 + (size_t)(j0 + j) * d + e)));
+      }
+    } else {
+      for (int e = lane; e < d; e += 32) {
+        const float xv = x[e];
+#pragma unroll
+        for (int j = 0; j < KM_TILE; ++j) {
+          if (j < kk) {
+            const float a = xv - __ldg(c0 + (size_t)(j0 + j) * d + e);
+            acc[j] += a * a;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < KM_TILE; ++j) {
+      if (j < kk) {
+        const float v = warp_sum(acc[j]);
+        if (v < best) {
+          best = v;
+          best_j = j0 + j;
+        }
+      }
+    }
+  }
+}
+
+// two rows of the same class: every centroid value is loaded once for both (same per-row arithmetic and
+// summation order as km_one, so a row's result does not depend on how it was paired)
+__device__ __forceinline__ void km_two(const float* __restrict__ xa, const float* __restrict__ xb,
+                                       const float* __restrict__ c0, int d, int k, int lane, float& best_a, int& ja,
+                                       float& best_b, int& jb) {
+  best_a = best_b = INFINITY;
+  ja = jb = 0;
+  for (int j0 = 0; j0 < k; j0 += KM_TILE) {
+    const int kk = min(KM_TILE, k - j0);
+    float acc_a[KM_TILE], acc_b[KM_TILE];
+#pragma unroll
+    for (int j = 0; j < KM_TILE; ++j) acc_a[j] = acc_b[j] = 0.f;
+    int e = lane * 4;
+    for (; e + 128 < d; e += 256) {  // 4 row loads in flight per lane before the first use
+      const float4 a0 = ld_stream_f4(xa + e), a1 = ld_stream_f4(xa + e + 128);
+      const float4 b0 = ld_stream_f4(xb + e), b1 = ld_stream_f4(xb + e + 128);
+#pragma unroll
+      for (int j = 0; j < KM_TILE; ++j) {
+        if (j < kk) {
+          const float* cj = c0 + (size_t)(j0 + j) * d + e;
+          const float4 c_lo = __ldg(reinterpret_cast<const float4*>(cj));
+          const float4 c_hi = __ldg(reinterpret_cast<const float4*>(cj + 128));
+          acc_a[j] += sqdiff4(a0, c_lo);
+          acc_b[j] += sqdiff4(b0, c_lo);
+          acc_a[j] += sqdiff4(a1, c_hi);
+          acc_b[j] += sqdiff4(b1, c_hi);
+        }
+      }
+    }
+    for (; e < d; e += 128) {
+      const float4 a0 = ld_stream_f4(xa + e), b0 = ld_stream_f4(xb + e);
+#pragma unroll
+      for (int j = 0; j < KM_TILE; ++j) {
+        if (j < kk) {
+          const float4 cv = __ldg(reinterpret_cast<const float4*>(c0 + (size_t)(j0 + j) * d + e));
+          acc_a[j] += sqdiff4(a0, cv);
+          acc_b[j] += sqdiff4(b0, cv);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < KM_TILE; ++j) {
+      if (j < kk) {
+        const float va = warp_sum(acc_a[j]), vb = warp_sum(acc_b[j]);
+        if (va < best_a) {
+          best_a = va;
+          ja = j0 + j;
+        }
+        if (vb < best_b) {
+          best_b = vb;
+          jb = j0 + j;
+        }
+      }
+    }
+  }
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(const float* __restrict__ rows, int d, long long ld,
                                                                    const int32_t* __restrict__ group,
+                                                                   const int64_t* __restrict__ order,
                                                                    long long n_rows,
                                                                    const float* __restrict__ cent, int k,
                                                                    int32_t* __restrict__ assign,
                                                                    float* __restrict__ dist) {
   const int lane = threadIdx.x & 31;
   const long long warps = (long long)gridDim.x * (KM_THREADS / 32);
-  for (long long row = (long long)blockIdx.x * (KM_THREADS / 32) + (threadIdx.x >> 5); row < n_rows; row += warps) {
-    const int g = group[row];
-    const float* x = rows + row * ld;
-    const float* c0 = cent + (size_t)g * k * d;
-    float best = INFINITY;
-    int best_j = 0;
-    for (int j0 = 0; j0 < k; j0 += KM_TILE) {
-      const int kk = min(KM_TILE, k - j0);
-      float acc[KM_TILE];
-#pragma unroll
-      for (int j = 0; j < KM_TILE; ++j) acc[j] = 0.f;
-      if (VEC) {
-        int e = lane * 4;
-        for (; e + 3 * 128 < d; e += 4 * 128) {  // 4 row loads in flight per lane before the first use
-          float4 xv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) xv[u] = ld_stream_f4(x + e + u * 128);
-#pragma unroll
-          for (int j = 0; j < KM_TILE; ++j) {
-            if (j < kk) {
-              const float* cj = c0 + (size_t)(j0 + j) * d + e;
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float4 cv = __ldg(reinterpret_cast<const float4*>(cj + u * 128));
-                const float a = xv[u].x - cv.x, b = xv[u].y - cv.y, c = xv[u].z - cv.z, w = xv[u].w - cv.w;
-                acc[j] += a * a + b * b + c * c + w * w;
-              }
-            }
-          }
-        }
-        for (; e < d; e += 128) {
-          const float4 xv = ld_stream_f4(x + e);
-#pragma unroll
-          for (int j = 0; j < KM_TILE; ++j) {
-            if (j < kk) {
-              const float4 cv = __ldg(reinterpret_cast<const float4*>(c0 + (size_t)(j0 + j) * d + e));
-              const float a = xv.x - cv.x, b = xv.y - cv.y, c = xv.z - cv.z, w = xv.w - cv.w;
-              acc[j] += a * a + b * b + c * c + w * w;
-            }
-          }
-        }
-      } else {
-        for (int e = lane; e < d; e += 32) {
-          const float xv = x[e];
-#pragma unroll
-          for (int j = 0; j < KM_TILE; ++j) {
-            if (j < kk) {
-              const float a = xv - __ldg(c0 + (size_t)(j0 + j) * d + e);
-              acc[j] += a * a;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < KM_TILE; ++j) {
-        if (j < kk) {
-          const float v = warp_sum(acc[j]);
-          if (v < best) {  // strict: the lowest centroid index wins a tie
-            best = v;
-            best_j = j0 + j;
-          }
-        }
-      }
+  const long long pairs = (n_rows + 1) / 2;
+  for (long long p = (long long)blockIdx.x * (KM_THREADS / 32) + (threadIdx.x >> 5); p < pairs; p += warps) {
+    const bool two = 2 * p + 1 < n_rows;
+    const long long ra = order ? order[2 * p] : 2 * p;
+    const long long rb = two ? (order ? order[2 * p + 1] : 2 * p + 1) : ra;
+    const int ga = group[ra], gb = group[rb];
+    float best_a, best_b;
+    int ja, jb;
+    if (VEC && two && ga == gb) {
+      km_two(rows + ra * ld, rows + rb * ld, cent + (size_t)ga * k * d, d, k, lane, best_a, ja, best_b, jb);
+    } else {
+      km_one<VEC>(rows + ra * ld, cent + (size_t)ga * k * d, d, k, lane, best_a, ja);
+      if (two) km_one<VEC>(rows + rb * ld, cent + (size_t)gb * k * d, d, k, lane, best_b, jb);
     }
     if (lane == 0) {
-      assign[row] = g * k + best_j;
-      if (dist) dist[row] = best;
+      assign[ra] = ga * k + ja;
+      if (dist) dist[ra] = best_a;
+      if (two) {
+        assign[rb] = gb * k + jb;
+        if (dist) dist[rb] = best_b;
+      }
     }
   }
 }
@@ -368,20 +430,21 @@ extern "C" int nw_class_centroids(const float* rows, int d, int64_t ld, const in
   return NW_OK;
 }
 
-extern "C" int nw_kmeans_assign(const float* rows, int d, int64_t ld, const int32_t* group, int64_t n_rows,
-                                const float* centroids, int k, int32_t* assign_out, float* dist_out, void* stream_) {
+extern "C" int nw_kmeans_assign(const float* rows, int d, int64_t ld, const int32_t* group, const int64_t* order,
+                                int64_t n_rows, const float* centroids, int k, int32_t* assign_out, float* dist_out,
+                                void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NW_REQUIRE(rows && group && centroids && assign_out, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(d > 0 && ld >= d && n_rows > 0 && k > 0, NW_ERR_INVALID, "bad shape");
   const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(centroids) & 15) == 0);
   auto kernel = vec ? aux::kmeans_assign_kernel<true> : aux::kmeans_assign_kernel<false>;
-  int resident = 0;  // persistent grid: exactly the blocks that fit, each striding over the rows
+  int resident = 0;  // persistent grid: exactly the blocks that fit, each striding over the row pairs
   NW_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, aux::KM_THREADS, 0));
-  const long long want = ceil_div_ll(n_rows, aux::KM_THREADS / 32);
+  const long long want = ceil_div_ll((n_rows + 1) / 2, aux::KM_THREADS / 32);
   const long long fit = (long long)sm_count() * (resident > 0 ? resident : 1);
-  kernel<<<unsigned(want < fit ? want : fit), aux::KM_THREADS, 0, stream>>>(rows, d, ld, group, n_rows, centroids, k,
-                                                                            assign_out, dist_out);
+  kernel<<<unsigned(want < fit ? want : fit), aux::KM_THREADS, 0, stream>>>(rows, d, ld, group, order, n_rows,
+                                                                            centroids, k, assign_out, dist_out);
   NW_CUDA_OK(cudaGetLastError());
   return NW_OK;
 }

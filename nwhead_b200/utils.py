@@ -149,14 +149,15 @@ def compute_clusters(embeddings, labels, n_clusters, closest=False):
     return kmeans_centroids(feats, lab32, perm, offsets, n_classes, n_clusters, closest=closest)
 
 
-def _kmeans_assign(feats, group, centroids, k):
-    """nw_kmeans_assign: (assignment group*k + j, squared distance to the chosen centroid) for every row."""
+def _kmeans_assign(feats, group, centroids, k, order=None):
+    """nw_kmeans_assign: (assignment group*k + j, squared distance to the chosen centroid) for every row;
+    order = the class-sorted visiting order of the rows (None: they are class-sorted already)."""
     lib = load()
     dev = feats.device
     n, d = feats.shape
     assign = torch.empty((n,), dtype=torch.int32, device=dev)
     dist = torch.empty((n,), dtype=torch.float32, device=dev)
-    check(lib.nw_kmeans_assign(ptr(feats), d, feats.stride(0), ptr(group), n, ptr(centroids), k, ptr(assign),
+    check(lib.nw_kmeans_assign(ptr(feats), d, feats.stride(0), ptr(group), ptr(order), n, ptr(centroids), k, ptr(assign),
                                ptr(dist), stream_of(dev)), "nw_kmeans_assign")
     return assign, dist
 
@@ -192,7 +193,7 @@ def kmeans_centroids(feats, group, perm, offsets, n_classes, k, closest=False, s
     mind = torch.full((n,), float("inf"), dtype=torch.float32, device=dev)
     last = (hi - 1).clamp_min(0)
     for j in range(1, k):
-        _, dist = _kmeans_assign(feats, group, cent[:, j - 1].contiguous(), 1)
+        _, dist = _kmeans_assign(feats, group, cent[:, j - 1].contiguous(), 1, perm)
         mind = torch.minimum(mind, dist)
         cs = torch.cumsum((mind if perm is None else mind[perm]).double(), 0)
         base = torch.where(lo > 0, cs[(lo - 1).clamp_min(0)], torch.zeros_like(cs[:1]))
@@ -207,7 +208,7 @@ def kmeans_centroids(feats, group, perm, offsets, n_classes, k, closest=False, s
     new = torch.empty_like(cent)
     prev = None
     for _ in range(max_iter):
-        assign, _ = _kmeans_assign(feats, group, cent, k)
+        assign, _ = _kmeans_assign(feats, group, cent, k, perm)
         if prev is not None and torch.equal(assign, prev):
             break
         prev = assign
@@ -222,7 +223,7 @@ def kmeans_centroids(feats, group, perm, offsets, n_classes, k, closest=False, s
         rows = torch.arange(n, device=dev)
         g64 = group.long()
         for j in range(k):
-            _, dist = _kmeans_assign(feats, group, cent[:, j].contiguous(), 1)
+            _, dist = _kmeans_assign(feats, group, cent[:, j].contiguous(), 1, perm)
             best = torch.full((n_classes,), float("inf"), device=dev).scatter_reduce(0, g64, dist, "amin")
             first = torch.full((n_classes,), n, dtype=torch.int64, device=dev).scatter_reduce(
                 0, g64, torch.where(dist == best[g64], rows, torch.full_like(rows, n)), "amin")

@@ -293,9 +293,10 @@ class SupportBank:
             out.append(idx)
         return torch.cat(out, dim=0)
 
-    def block_best(self, q: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    def block_best(self, q: torch.Tensor, scale: float = 1.0):
         """(B, ceil(N/64)) best score of every query inside every block of 64 consecutive bank rows
-        (nw_forward_emit / NW_EMIT_BLOCK_BEST): the candidate search of topk_exact."""
+        (nw_forward_emit / NW_EMIT_BLOCK_BEST): the candidate search of topk_exact.  Also returns the (B,)
+        squared norms of the prepared (centred, rounded) queries."""
         lib = load()
         _abi.require_cuda(q, self.feats_bf16)
         q_bf16, q_sq = self.prepare_queries(q)

@@ -7,6 +7,8 @@ Two execution paths, both through libnw_sm100 (no PyTorch or CPU fallback):
   * direct fp32 path  (nw_direct_*): exact differences, differentiable, per-query 3-D supports —
     episodic training (`forward`) and tiny supports.
 """
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -133,13 +135,15 @@ class NWHead(nn.Module):
         """The reference hands the SAME support tensors to the head on every predict call (nwhead/nw.py:156-160).
         Building the device bank (sort check, centring, bf16 conversion) once per tensor version instead of once
         per call keeps that usage pattern fast; in-place modification bumps `_version` and invalidates the entry."""
-        key = (sx.data_ptr(), sx._version, tuple(sx.shape), sy.data_ptr(), sy._version, kind, self.precision,
-               self.n_classes)
-        for k, bank in self._bank_cache:
-            if k == key:
+        # identity of the live tensor OBJECTS (weak references), not their addresses: a freed support's memory is
+        # routinely handed to the next one (knn mode builds a new support per batch)
+        key = (sx._version, sy._version, kind, self.precision, self.n_classes)
+        for ref_x, ref_y, k, bank in self._bank_cache:
+            if ref_x() is sx and ref_y() is sy and k == key:
                 return bank
         bank = SupportBank.build(sx, sy, self.n_classes, kind, self.precision)
-        self._bank_cache.append((key, bank))
+        self._bank_cache = [e for e in self._bank_cache if e[0]() is not None and e[1]() is not None]
+        self._bank_cache.append((weakref.ref(sx), weakref.ref(sy), key, bank))
         del self._bank_cache[:-self.BANK_CACHE_SIZE]
         return bank
 

@@ -261,13 +261,20 @@ def test_head_caches_the_bank_of_unchanged_support_tensors(cuda_lib):
     sx, sy, qx = torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), torch.from_numpy(q).to(DEV)
     with torch.no_grad():
         a = head(qx, sx, sy)
-        bank = head._bank_cache[-1][1]
+        bank = head._bank_cache[-1][-1]
         b = head(qx, sx, sy)
-        assert head._bank_cache[-1][1] is bank and torch.equal(a, b)      # same tensors -> cached bank
+        assert head._bank_cache[-1][-1] is bank and torch.equal(a, b)     # same tensors -> cached bank
         sx.mul_(1.5)                                                       # in-place change -> rebuilt
         c = head(qx, sx, sy)
-        assert head._bank_cache[-1][1] is not bank
-    assert_head_parity(c, O.nw_forward(q, s * 1.5, y, 6, "euclidean"))
+        assert head._bank_cache[-1][-1] is not bank
+        assert_head_parity(c, O.nw_forward(q, s * 1.5, y, 6, "euclidean"))
+        # a NEW support tensor that lands on the freed memory of an old one (same address, shape and version, as
+        # knn mode produces batch after batch) must not be served the old bank
+        for scale in (1.0, 3.0, 0.5):
+            tmp = torch.from_numpy(s * scale).to(DEV)
+            out = head(qx, tmp, sy)
+            assert_head_parity(out, O.nw_forward(q, s * scale, y, 6, "euclidean"))
+            del tmp
 
 
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])

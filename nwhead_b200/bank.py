@@ -15,6 +15,7 @@ HBM layout (all contiguous, 16-byte aligned):
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Optional
 
 import torch
@@ -356,9 +357,11 @@ class SupportBank:
             raise ValueError("source_feats must be the (N, d) tensor the bank was built from")
         k = min(int(k), n)
         src_all = source_feats.detach().float().reshape(n, d)
-        if getattr(self, "_resid_key", None) != (src_all.data_ptr(), src_all._version):
-            self._resid_max = self.rounding_residual(src_all).max()
-            self._resid_key = (src_all.data_ptr(), src_all._version)
+        cached = getattr(self, "_resid_of", None)   # (weak reference to the tensor object, its version, max residual)
+        if cached is None or cached[0]() is not source_feats or cached[1] != source_feats._version:
+            cached = (weakref.ref(source_feats), source_feats._version, self.rounding_residual(src_all).max())
+            self._resid_of = cached
+        resid_max = cached[2]
         out = torch.empty((q.shape[0], k), dtype=torch.int64, device=dev)
         smax = self.sqnorm.max().sqrt() * (1 + 2.0 ** -7)         # norms of the rounded rows -> of the rows
         lane = torch.arange(64, device=dev)
@@ -373,7 +376,7 @@ class SupportBank:
             sorted_best = best.gather(1, order)
             qn = q_sq.sqrt() * (1 + 2.0 ** -7)
             e2 = 2.0 ** -18 * (qn * qn + smax * smax)             # fp32 accumulation, squared-distance domain
-            eta = (self.rounding_residual(qc) + self._resid_max) * (1 + 2.0 ** -10)
+            eta = (self.rounding_residual(qc) + resid_max) * (1 + 2.0 ** -10)
             lolo = (2.0 ** -8 * (qn + smax)) ** 2 if self.precision != _abi.PREC_BF16 else torch.zeros_like(e2)
 
             def upper(beta):      # largest exact-path score of a row whose reduced-precision score is beta

@@ -97,6 +97,7 @@ struct Params {
   int n_classes;
   int kblocks;
   int q_groups;  // query tiles of 128 * NCTA rows
+  int s_keep;    // support tiles are loaded with the L2 evict_last policy (several query groups re-read them)
   int s_tiles;
   int chunks;
   int tiles_per_chunk;
@@ -342,10 +343,10 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       // Queries are re-read for every support tile; a support tile is read by all query groups of the chunk
       // within a few microseconds.  Both are marked evict_last: same-box A/B on the sustained bench gave
       // supports evict_last +1.3 %, evict_normal 0, evict_first -4 % (fewer re-reads of the bank from HBM).
-      // When every worker streams its own support tiles (one or two query groups) there is nothing to keep:
+      // When every worker streams its own support tiles (one query group) there is nothing to keep:
       // evict_last there cost 3-9 % at B <= 256.
       const uint64_t pol_q = l2_policy_evict_last();
-      const uint64_t pol_s = p.q_groups >= 4 ? l2_policy_evict_last() : l2_policy_evict_normal();
+      const uint64_t pol_s = p.s_keep ? l2_policy_evict_last() : l2_policy_evict_normal();
       uint32_t it = 0;
       for (int u = worker; u < n_units; u += n_workers) {
         const int g = u / p.q_groups;
@@ -605,26 +606,31 @@ __device__ __forceinline__ float logaddexp_f(float a, float b) {
 
 // Apply the chunk-boundary partials in chunk order (fixed order => bitwise reproducible).
 // A class that is cut by a chunk boundary receives ALL of its mass through `side` (never a direct store), and
-// the cut classes appear in non-decreasing order along the chunks, so one thread per query row run-length
-// merges the (class, value) pairs in registers and writes each class once: no read-modify-write chain through
-// global memory, and the loads of different chunks are independent (software pipelined by the unroll).
+// the cut classes appear in non-decreasing order along the chunks, so the (class, value) pairs are run-length
+// merged in registers and each class is written once: no read-modify-write chain through global memory.
+// One WARP per query row: the lanes fetch the entries of 32 chunks at once (one memory latency per 32 chunks —
+// with one thread per row the 148 dependent round trips of a small-batch step cost 170 us of its 950), then
+// every lane replays the same in-order merge from registers through shuffles and lane 0 stores.
 struct TableList {
   float* t[NW_MAX_PEERS];
   int n;
   int rows_per_table;
 };
 
-__global__ void __launch_bounds__(32) merge_side_kernel(const TableList tables, const float* __restrict__ side,
-                                                        const int32_t* __restrict__ labels, int n_query,
-                                                        int n_support, int n_classes, int chunks,
-                                                        int tiles_per_chunk, int s_tiles, int sets) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n_query) return;
+constexpr int MERGE_ROWS_PER_BLOCK = 4;
+
+__global__ void __launch_bounds__(MERGE_ROWS_PER_BLOCK * 32) merge_side_kernel(
+    const TableList tables, const float* __restrict__ side, const int32_t* __restrict__ labels, int n_query,
+    int n_support, int n_classes, int chunks, int tiles_per_chunk, int s_tiles, int sets) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * MERGE_ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (b >= n_query) return;  // uniform per warp
   const size_t row_off = size_t(b) * n_classes;
   const float neg_inf = __int_as_float(0xff800000);
   int cur = -1;
   float acc = neg_inf;
   auto put = [&](int cls, float v) {
+    if (lane != 0) return;
     if (tables.rows_per_table > 0) tables.t[b / tables.rows_per_table][row_off + cls] = v;
     else
       for (int r = 0; r < tables.n; ++r) tables.t[r][row_off + cls] = v;
@@ -638,19 +644,27 @@ __global__ void __launch_bounds__(32) merge_side_kernel(const TableList tables, 
     }
     acc = logaddexp_f(acc, v);
   };
-#pragma unroll 2
-  for (int g = 0; g < chunks; ++g) {
-    const int t0 = g * tiles_per_chunk;
-    const int t1 = min(t0 + tiles_per_chunk, s_tiles);
-    const int n0 = t0 * BN;
-    const int n1 = min(t1 * BN, n_support);
-    const float* sr = side + (size_t(g) * n_query + b) * 2 * sets;  // [slot][set]
-    const int c0 = __ldg(labels + n0);
-    const int c1 = __ldg(labels + n1 - 1);
-    float v[4];
-    for (int i = 0; i < 2 * sets; ++i) v[i] = sr[i];
-    for (int i = 0; i < sets; ++i) add(c0, v[i]);
-    for (int i = 0; i < sets; ++i) add(c1, v[sets + i]);
+  for (int base = 0; base < chunks; base += 32) {
+    const int g = base + lane;
+    int c0 = 0, c1 = 0;
+    float v[4] = {neg_inf, neg_inf, neg_inf, neg_inf};  // [slot][set]
+    if (g < chunks) {
+      const int t0 = g * tiles_per_chunk;
+      const int t1 = min(t0 + tiles_per_chunk, s_tiles);
+      c0 = __ldg(labels + size_t(t0) * BN);
+      c1 = __ldg(labels + min(size_t(t1) * BN, size_t(n_support)) - 1);
+      const float* sr = side + (size_t(g) * n_query + b) * 2 * sets;
+      for (int i = 0; i < 2 * sets; ++i) v[i] = sr[i];
+    }
+    const int cnt = min(32, chunks - base);
+    for (int j = 0; j < cnt; ++j) {
+      const int jc0 = __shfl_sync(0xffffffffu, c0, j), jc1 = __shfl_sync(0xffffffffu, c1, j);
+      float jv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) jv[i] = __shfl_sync(0xffffffffu, v[i], j);
+      for (int i = 0; i < sets; ++i) add(jc0, jv[i]);
+      for (int i = 0; i < sets; ++i) add(jc1, jv[sets + i]);
+    }
   }
   if (cur >= 0) put(cur, acc);
 }
@@ -775,6 +789,17 @@ using namespace nw;
 static bool force_single_cta() {
   const char* e = getenv("NW_B200_FORCE_1CTA");
   return e && e[0] == '1';
+}
+
+// L2 policy of the support tiles: evict_last once `min_groups` query groups share every tile (default 2:
+// same-box A/B at B=512 gave +4 % over evict_normal, 0 within noise at B=768/1024;
+// NW_B200_S_KEEP_MIN_GROUPS overrides, for A/B runs on one box).
+static int support_keep_policy(int q_groups) {
+  static const int min_groups = [] {
+    const char* e = getenv("NW_B200_S_KEEP_MIN_GROUPS");
+    return e && *e ? atoi(e) : 2;
+  }();
+  return q_groups >= min_groups ? 1 : 0;
 }
 
 extern "C" int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t* plan) {
@@ -911,6 +936,7 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.n_classes = n_classes;
   p.kblocks = row_elems / k1::BK;
   p.q_groups = plan.q_tiles;
+  p.s_keep = support_keep_policy(plan.q_tiles);
   p.s_tiles = plan.s_tiles;
   p.chunks = plan.chunks;
   p.tiles_per_chunk = plan.tiles_per_chunk;
@@ -936,9 +962,8 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
     NW_CUDA_OK(cudaGetLastError());
   }
   if (plan.chunks > 1) {
-    k1::merge_side_kernel<<<ceil_div(n_query, 32), 32, 0, stream>>>(tl, side, labels, n_query, int(n_support),
-                                                                    n_classes, plan.chunks, plan.tiles_per_chunk,
-                                                                    plan.s_tiles, sets);
+    k1::merge_side_kernel<<<ceil_div(n_query, k1::MERGE_ROWS_PER_BLOCK), k1::MERGE_ROWS_PER_BLOCK * 32, 0, stream>>>(
+        tl, side, labels, n_query, int(n_support), n_classes, plan.chunks, plan.tiles_per_chunk, plan.s_tiles, sets);
     NW_CUDA_OK(cudaGetLastError());
   }
   return NW_OK;
@@ -1005,6 +1030,7 @@ extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, co
   p.n_classes = 1;
   p.kblocks = row_elems / k1::BK;
   p.q_groups = plan.q_tiles;
+  p.s_keep = support_keep_policy(plan.q_tiles);
   p.s_tiles = plan.s_tiles;
   p.chunks = plan.chunks;
   p.tiles_per_chunk = plan.tiles_per_chunk;

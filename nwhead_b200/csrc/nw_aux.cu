@@ -216,6 +216,37 @@ __global__ void rank_global_step_kernel(uint64_t* __restrict__ keys, long long p
   }
 }
 
+// Top-k selection (k <= SORT_CHUNK / 4): every block sorts one chunk of SORT_CHUNK keys in shared memory and keeps
+// its k best; the survivors (n * k / SORT_CHUNK of them) go through the same step again until one chunk is left.
+// The keys are unique (score, index) pairs, so the result equals the first k entries of the full sort, at a
+// quarter of its compare-exchange stages and with no pass over global memory between them.
+template <bool FROM_SCORES>
+__global__ void __launch_bounds__(1024) rank_select_kernel(const float* __restrict__ scores,
+                                                           const uint64_t* __restrict__ in, long long n_in,
+                                                           long long in_stride, uint64_t* __restrict__ out,
+                                                           long long out_stride, int k) {
+  __shared__ uint64_t sm[SORT_CHUNK];
+  const long long r = blockIdx.y;
+  const long long base = (long long)blockIdx.x * SORT_CHUNK;
+  for (int i = threadIdx.x; i < SORT_CHUNK; i += blockDim.x) {
+    const long long g = base + i;
+    uint64_t key = ~uint64_t(0);
+    if (g < n_in) key = FROM_SCORES ? make_key(scores[r * n_in + g], uint32_t(g)) : in[r * in_stride + g];
+    sm[i] = key;
+  }
+  __syncthreads();
+  for (int size = 2; size <= SORT_CHUNK; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < SORT_CHUNK / 2; t += blockDim.x) {
+        const int i = 2 * t - (t & (stride - 1));
+        cmp_swap(sm[i], sm[i + stride], (i & size) == 0);
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k; i += blockDim.x) out[r * out_stride + (long long)blockIdx.x * k + i] = sm[i];
+}
+
 __global__ void rank_emit_kernel(const uint64_t* __restrict__ keys, long long padded, long long k,
                                  int64_t* __restrict__ idx_out) {
   const long long r = blockIdx.y;
@@ -496,11 +527,36 @@ extern "C" int nw_rank_rows(const float* scores, int n_rows, int64_t n_cols, int
   NW_REQUIRE(workspace_bytes >= nw_rank_rows_workspace_bytes(n_rows, n_cols), NW_ERR_WORKSPACE, "workspace too small");
   const long long padded = aux::next_pow2(n_cols);
   uint64_t* keys = static_cast<uint64_t*>(workspace);
+  const long long chunk = aux::SORT_CHUNK;
+  const long long n1 = ceil_div_ll(n_cols, chunk) * k;       // survivors of the first selection level
+  const long long n2 = ceil_div_ll(n1, chunk) * k;           // ... of the second (later levels are smaller)
+  if (k <= chunk / 4 && n_cols > chunk && n1 + n2 <= padded) {
+    // level outputs alternate between two regions of the workspace: [0, n_rows * n1) and the n_rows * n2 after it
+    uint64_t* region[2] = {keys, keys + (long long)n_rows * n1};
+    {
+      dim3 grid(unsigned(ceil_div_ll(n_cols, chunk)), n_rows);
+      aux::rank_select_kernel<true><<<grid, 1024, 0, stream>>>(scores, nullptr, n_cols, 0, region[0], n1, int(k));
+    }
+    long long n_cur = n1;
+    int cur = 0;
+    for (;;) {
+      const long long nch = ceil_div_ll(n_cur, chunk);
+      dim3 grid(unsigned(nch), n_rows);
+      aux::rank_select_kernel<false><<<grid, 1024, 0, stream>>>(nullptr, region[cur], n_cur, n_cur, region[cur ^ 1],
+                                                                nch * k, int(k));
+      cur ^= 1;
+      n_cur = nch * k;
+      if (nch == 1) break;
+    }
+    dim3 grid(unsigned(ceil_div_ll(k, 256)), n_rows);
+    aux::rank_emit_kernel<<<grid, 256, 0, stream>>>(region[cur], n_cur, k, idx_out);
+    NW_CUDA_OK(cudaGetLastError());
+    return NW_OK;
+  }
   {
     dim3 grid(unsigned(ceil_div_ll(padded, 256)), n_rows);
     aux::rank_init_kernel<<<grid, 256, 0, stream>>>(scores, n_cols, padded, keys);
   }
-  const long long chunk = aux::SORT_CHUNK;
   const long long nchunks = padded > chunk ? padded / chunk : 1;
   {
     dim3 grid(unsigned(nchunks), n_rows);

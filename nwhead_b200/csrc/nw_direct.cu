@@ -29,53 +29,106 @@ __global__ void inv_norm_kernel(const float* __restrict__ x, long long rows, int
   if (lane == 0) inv[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
 }
 
-// one warp per (query, support) pair
+// One warp per TILE of TQ queries x TS supports.  Every (query, support) pair is accumulated exactly as a
+// one-warp-per-pair kernel would do it — lane l takes columns l, l+32, ... in order with one fmaf each, then a
+// butterfly sum — so a pair's score does not depend on the tile shape or on its neighbours (the neighbour search
+// relies on that: candidates scored one by one must reproduce the dense matrix bit for bit).  The tile only
+// shares the LOADS: each q and s value is read once per TQ x TS pairs instead of once per pair (the pair-per-warp
+// version moved 8 bytes through L1/L2 per fmaf and ran at 2 TFLOP/s).
+// batched (per-query supports, TQ == 1): support row j of query b is s[(b * n_support + j) * d].
+template <int TQ, int TS>
 __global__ void __launch_bounds__(256) scores_kernel(int kind, float scale, const float* __restrict__ q,
                                                      int n_query, int d, const float* __restrict__ s,
                                                      long long n_support, int batched,
                                                      float* __restrict__ scores) {
   const int lane = threadIdx.x & 31;
-  const long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pair >= (long long)n_query * n_support) return;
-  const long long b = pair / n_support;
-  const long long j = pair - b * n_support;
-  const float* qp = q + b * d;
-  const float* sp = s + (batched ? pair : j) * d;
-  float out;
-  if (kind == NW_KIND_EUCLIDEAN) {
-    float acc = 0.f;
+  const long long tiles_s = (n_support + TS - 1) / TS;
+  const long long tiles_q = (n_query + TQ - 1) / TQ;
+  const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile >= tiles_q * tiles_s) return;
+  const long long b0 = (tile / tiles_s) * TQ;
+  const long long j0 = (tile % tiles_s) * TS;
+  const float* qp[TQ];
+  const float* sp[TS];
+#pragma unroll
+  for (int i = 0; i < TQ; ++i) qp[i] = q + min(b0 + i, (long long)n_query - 1) * d;  // edge rows: recomputed, not stored
+#pragma unroll
+  for (int j = 0; j < TS; ++j) sp[j] = s + ((batched ? b0 * n_support : 0) + min(j0 + j, n_support - 1)) * d;
+
+  float iq[TQ], is[TS];
+  if (direct::kind_normalised(kind)) {
+    float qq[TQ], ss[TS];
+#pragma unroll
+    for (int i = 0; i < TQ; ++i) qq[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < TS; ++j) ss[j] = 0.f;
     for (int c = lane; c < d; c += 32) {
-      const float df = qp[c] - sp[c];
-      acc = fmaf(df, df, acc);
+#pragma unroll
+      for (int i = 0; i < TQ; ++i) qq[i] = fmaf(qp[i][c], qp[i][c], qq[i]);
+#pragma unroll
+      for (int j = 0; j < TS; ++j) ss[j] = fmaf(sp[j][c], sp[j][c], ss[j]);
     }
-    out = -sqrtf(warp_sum(acc));
-  } else if (kind == NW_KIND_DOT) {
-    float acc = 0.f;
-    for (int c = lane; c < d; c += 32) acc = fmaf(qp[c], sp[c], acc);
-    out = warp_sum(acc);
+#pragma unroll
+    for (int i = 0; i < TQ; ++i) iq[i] = 1.0f / fmaxf(sqrtf(warp_sum(qq[i])), 1e-12f);
+#pragma unroll
+    for (int j = 0; j < TS; ++j) is[j] = 1.0f / fmaxf(sqrtf(warp_sum(ss[j])), 1e-12f);
+  }
+
+  float acc[TQ][TS];
+#pragma unroll
+  for (int i = 0; i < TQ; ++i)
+#pragma unroll
+    for (int j = 0; j < TS; ++j) acc[i][j] = 0.f;
+  const bool euclid = direct::kind_euclid(kind);
+  if (!direct::kind_normalised(kind)) {
+    for (int c = lane; c < d; c += 32) {
+      float qv[TQ], sv[TS];
+#pragma unroll
+      for (int i = 0; i < TQ; ++i) qv[i] = qp[i][c];
+#pragma unroll
+      for (int j = 0; j < TS; ++j) sv[j] = sp[j][c];
+#pragma unroll
+      for (int i = 0; i < TQ; ++i)
+#pragma unroll
+        for (int j = 0; j < TS; ++j) {
+          if (euclid) {
+            const float df = qv[i] - sv[j];
+            acc[i][j] = fmaf(df, df, acc[i][j]);
+          } else {
+            acc[i][j] = fmaf(qv[i], sv[j], acc[i][j]);
+          }
+        }
+    }
   } else {
-    float qq = 0.f, ss = 0.f;
     for (int c = lane; c < d; c += 32) {
-      qq = fmaf(qp[c], qp[c], qq);
-      ss = fmaf(sp[c], sp[c], ss);
-    }
-    const float iq = 1.0f / fmaxf(sqrtf(warp_sum(qq)), 1e-12f);
-    const float is = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
-    float acc = 0.f;
-    if (kind == NW_KIND_HYPERSPHERE) {
-      for (int c = lane; c < d; c += 32) {
-        // separately rounded products (no FMA contraction): identical rows must give exactly 0
-        const float df = __fsub_rn(__fmul_rn(qp[c], iq), __fmul_rn(sp[c], is));
-        acc = fmaf(df, df, acc);
-      }
-      out = -sqrtf(warp_sum(acc));
-    } else {
-      for (int c = lane; c < d; c += 32) acc = fmaf(__fmul_rn(qp[c], iq), __fmul_rn(sp[c], is), acc);
-      out = warp_sum(acc);
-      if (kind == NW_KIND_CLIP) out *= scale;
+      float qv[TQ], sv[TS];
+      // separately rounded products (no FMA contraction): identical rows must give exactly 0 (hypersphere)
+#pragma unroll
+      for (int i = 0; i < TQ; ++i) qv[i] = __fmul_rn(qp[i][c], iq[i]);
+#pragma unroll
+      for (int j = 0; j < TS; ++j) sv[j] = __fmul_rn(sp[j][c], is[j]);
+#pragma unroll
+      for (int i = 0; i < TQ; ++i)
+#pragma unroll
+        for (int j = 0; j < TS; ++j) {
+          if (euclid) {
+            const float df = __fsub_rn(qv[i], sv[j]);
+            acc[i][j] = fmaf(df, df, acc[i][j]);
+          } else {
+            acc[i][j] = fmaf(qv[i], sv[j], acc[i][j]);
+          }
+        }
     }
   }
-  if (lane == 0) scores[pair] = out;
+#pragma unroll
+  for (int i = 0; i < TQ; ++i)
+#pragma unroll
+    for (int j = 0; j < TS; ++j) {
+      float out = warp_sum(acc[i][j]);
+      if (euclid) out = -sqrtf(out);
+      else if (kind == NW_KIND_CLIP) out *= scale;
+      if (lane == 0 && b0 + i < n_query && j0 + j < n_support) scores[(b0 + i) * n_support + j0 + j] = out;
+    }
 }
 
 __device__ __forceinline__ float block_max(float v, float* red) {
@@ -534,11 +587,17 @@ extern "C" int nw_direct_scores(int kind, float scale, const float* q, int n_que
   if (rc != NW_OK) return rc;
   NW_REQUIRE(q && s && scores, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(n_query > 0 && d > 0 && n_support > 0, NW_ERR_INVALID, "shapes must be positive");
-  const long long pairs = (long long)n_query * n_support;
-  const long long blocks = ceil_div_ll(pairs, 8);
+  const bool wide = !support_batched && n_query >= 3;  // 4 x 4 pairs per warp; else 1 query x 4 supports
+  const long long tiles = wide ? ceil_div_ll(n_query, 4) * ceil_div_ll(n_support, 4)
+                               : (long long)n_query * ceil_div_ll(n_support, 4);
+  const long long blocks = ceil_div_ll(tiles, 8);
   NW_REQUIRE(blocks < (1ll << 31), NW_ERR_UNSUPPORTED, "too many (query, support) pairs for the direct path");
-  direct::scores_kernel<<<unsigned(blocks), 256, 0, stream>>>(kind, scale, q, n_query, d, s, n_support,
-                                                              support_batched, scores);
+  if (wide)
+    direct::scores_kernel<4, 4><<<unsigned(blocks), 256, 0, stream>>>(kind, scale, q, n_query, d, s, n_support, 0,
+                                                                      scores);
+  else
+    direct::scores_kernel<1, 4><<<unsigned(blocks), 256, 0, stream>>>(kind, scale, q, n_query, d, s, n_support,
+                                                                      support_batched, scores);
   NW_CUDA_OK(cudaGetLastError());
   return NW_OK;
 }

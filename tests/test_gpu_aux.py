@@ -176,6 +176,21 @@ def test_rank_rows_bit_exact(cuda_lib, n):
     assert np.array_equal(rank_rows(torch.from_numpy(sc).to(DEV), k).cpu().numpy(), got[:, :k])
 
 
+@pytest.mark.parametrize("n,k", [(4097, 1), (5800, 20), (70000, 1024), (300001, 20), (300001, 1000), (5000, 1025)])
+def test_rank_rows_selection_equals_full_sort(cuda_lib, n, k):
+    """k <= 1024 over more than one sort chunk takes the selection path: the first k of the full stable ranking,
+    including ties (scores quantised to 50 levels -> ascending index inside a tie) and -inf / +inf entries."""
+    from nwhead_b200.utils import rank_rows
+
+    rng = np.random.default_rng(n + k)
+    sc = rng.integers(0, 50, size=(5, n)).astype(np.float32)
+    sc[0, rng.integers(0, n, 40)] = -np.inf
+    sc[1, rng.integers(0, n, 40)] = np.inf
+    sc[2] = rng.normal(size=n).astype(np.float32)
+    got = rank_rows(torch.from_numpy(sc).to(DEV), k).cpu().numpy()
+    assert np.array_equal(got, np.argsort(-sc, axis=1, kind="stable")[:, :k])
+
+
 def test_bank_save_load_roundtrip(cuda_lib, tmp_path):
     from nwhead_b200 import SupportBank
 

@@ -46,8 +46,10 @@ __global__ void __launch_bounds__(256) scores_kernel(int kind, float scale, cons
   const long long tiles_q = (n_query + TQ - 1) / TQ;
   const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tile >= tiles_q * tiles_s) return;
-  const long long b0 = (tile / tiles_s) * TQ;
-  const long long j0 = (tile % tiles_s) * TS;
+  // shared support: neighbouring warps take the SAME supports and different queries, so the support rows are
+  // fetched from HBM once (the whole query batch stays in L2); per-query supports: query-major
+  const long long b0 = (batched ? tile / tiles_s : tile % tiles_q) * TQ;
+  const long long j0 = (batched ? tile % tiles_s : tile / tiles_q) * TS;
   const float* qp[TQ];
   const float* sp[TS];
 #pragma unroll

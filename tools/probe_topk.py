@@ -30,6 +30,9 @@ def main():
         got, t_fast = timed(lambda: bank.topk_exact(q, k, feats))
         want, t_dense = timed(lambda: rank_rows(dense_scores("euclidean", q, feats), k), reps=1)
         bb, t_bb = timed(lambda: bank.block_best(q))
+        if prec == "bf16":
+            _, t_sc = timed(lambda: dense_scores("euclidean", q, feats), reps=1)
+            print(f"dense scores alone {t_sc:.1f} ms = {2e-9 * b * n * d / t_sc:.1f} TFLOP/s (sub+fma per element)", flush=True)
         print(f"{prec}: N={n} d={d} B={b} k={k}  topk_exact {t_fast:.1f} ms (block_best {t_bb:.1f} ms)  "
               f"dense {t_dense:.1f} ms  equal={torch.equal(got, want)} paths={bank.last_topk_path}", flush=True)
         del bank

@@ -133,6 +133,101 @@ __global__ void __launch_bounds__(256) scores_kernel(int kind, float scale, cons
     }
 }
 
+// Shared-support scores for large problems (euclidean / dot): a block of 8 warps owns 32 queries x 32 supports
+// and walks the feature axis in 128-column slabs staged in shared memory (cp.async, double buffered); warp w
+// keeps 8 x 16 pairs in registers.  Lane l still accumulates columns l, l+32, ... in order with one fmaf each and
+// the same butterfly follows, so every pair gets the bits of the warp-tile kernel above; what changes is that an
+// operand value is fetched from L2 once per 32 pairs (the warp-tile kernel was L2-bound on the query re-reads).
+constexpr int SB_ROWS = 32;    // queries and supports per block
+constexpr int SB_COLS = 128;   // columns per slab
+constexpr int SB_STAGE_FLOATS = 2 * SB_ROWS * SB_COLS;
+constexpr size_t SB_SMEM_BYTES = 2 * SB_STAGE_FLOATS * sizeof(float);
+
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+template <bool EUCLID>
+__global__ void __launch_bounds__(256, 1) scores_block_kernel(const float* __restrict__ q, int n_query, int d,
+                                                              const float* __restrict__ s, long long n_support,
+                                                              float* __restrict__ scores) {
+  extern __shared__ __align__(16) float slab[];  // [stage][32 query rows | 32 support rows][128]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long tiles_q = (n_query + SB_ROWS - 1) / SB_ROWS;
+  const long long b0 = ((long long)blockIdx.x % tiles_q) * SB_ROWS;  // support-major: neighbours share supports
+  const long long j0 = ((long long)blockIdx.x / tiles_q) * SB_ROWS;
+
+  auto load_stage = [&](int stage, int c0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = threadIdx.x + i * 256;  // 64 rows x 32 float4
+      const int row = f >> 5;
+      const int c = c0 + (f & 31) * 4;
+      const float* src = row < SB_ROWS ? q + min(b0 + row, (long long)n_query - 1) * d
+                                       : s + min(j0 + row - SB_ROWS, n_support - 1) * d;
+      float* dst = slab + stage * SB_STAGE_FLOATS + row * SB_COLS + (f & 31) * 4;
+      if (c < d) cp_async_16(dst, src + c);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);  // adds exact zeros
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int q_row0 = (warp >> 1) * 8, s_row0 = (warp & 1) * 16;
+  float acc[8][16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+
+  const int n_slabs = (d + SB_COLS - 1) / SB_COLS;
+  load_stage(0, 0);
+  for (int sl = 0; sl < n_slabs; ++sl) {
+    if (sl + 1 < n_slabs) {
+      load_stage((sl + 1) & 1, (sl + 1) * SB_COLS);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* qs = slab + (sl & 1) * SB_STAGE_FLOATS + q_row0 * SB_COLS + lane;
+    const float* ss = slab + (sl & 1) * SB_STAGE_FLOATS + (SB_ROWS + s_row0) * SB_COLS + lane;
+#pragma unroll
+    for (int kk = 0; kk < SB_COLS / 32; ++kk) {
+      float qv[8], sv[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qv[i] = qs[i * SB_COLS + kk * 32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sv[j] = ss[j * SB_COLS + kk * 32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (EUCLID) {
+            const float df = qv[i] - sv[j];
+            acc[i][j] = fmaf(df, df, acc[i][j]);
+          } else {
+            acc[i][j] = fmaf(qv[i], sv[j], acc[i][j]);
+          }
+        }
+    }
+    __syncthreads();  // this stage is refilled two iterations from now
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float keep = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float v = warp_sum(acc[i][j]);
+      if (EUCLID) v = -sqrtf(v);
+      if (lane == j) keep = v;
+    }
+    const long long b = b0 + q_row0 + i, col = j0 + s_row0 + lane;
+    if (lane < 16 && b < n_query && col < n_support) scores[b * n_support + col] = keep;
+  }
+}
+
 __device__ __forceinline__ float block_max(float v, float* red) {
   v = warp_max(v);
   __syncthreads();
@@ -589,6 +684,17 @@ extern "C" int nw_direct_scores(int kind, float scale, const float* q, int n_que
   if (rc != NW_OK) return rc;
   NW_REQUIRE(q && s && scores, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(n_query > 0 && d > 0 && n_support > 0, NW_ERR_INVALID, "shapes must be positive");
+  const bool aligned = d % 4 == 0 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(s)) & 15) == 0;
+  if (!support_batched && (kind == NW_KIND_EUCLIDEAN || kind == NW_KIND_DOT) && n_query >= 16 && n_support >= 64 &&
+      aligned) {  // 32 x 32 pairs per block through shared-memory slabs
+    const long long blocks = ceil_div_ll(n_query, direct::SB_ROWS) * ceil_div_ll(n_support, direct::SB_ROWS);
+    NW_REQUIRE(blocks < (1ll << 31), NW_ERR_UNSUPPORTED, "too many (query, support) pairs for the direct path");
+    auto kernel = kind == NW_KIND_EUCLIDEAN ? direct::scores_block_kernel<true> : direct::scores_block_kernel<false>;
+    NW_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(direct::SB_SMEM_BYTES)));
+    kernel<<<unsigned(blocks), 256, direct::SB_SMEM_BYTES, stream>>>(q, n_query, d, s, n_support, scores);
+    NW_CUDA_OK(cudaGetLastError());
+    return NW_OK;
+  }
   const bool wide = !support_batched && n_query >= 3;  // 4 x 4 pairs per warp; else 1 query x 4 supports
   const long long tiles = wide ? ceil_div_ll(n_query, 4) * ceil_div_ll(n_support, 4)
                                : (long long)n_query * ceil_div_ll(n_support, 4);

@@ -206,7 +206,10 @@ NW_API int nw_direct_scores(int kind, float scale, const float* q, int n_query, 
 
 /* softmax over the support axis + label aggregation + log: logp (B, C), row_lse (B) = logsumexp_j
  * scores[b, :] (saved for backward).  labels int64 as handed to F.one_hot: (N) or (B, N).
- * status_flag: caller-zeroed int32, bit 0 is OR-ed in when a label is outside [0, C) (never cleared). */
+ * status_flag: caller-zeroed int32, set to 1 (plain store, never cleared) when a label is outside [0, C) —
+ * what F.one_hot rejects at nwhead/nw.py:276.  It may be device memory or device-visible (mapped / UVA pinned)
+ * HOST memory, so the caller can poll it without a copy.  Such a label contributes to no class, in the forward
+ * and in nw_direct_backward alike (no out-of-bounds access is possible). */
 NW_API int nw_direct_aggregate(const float* scores, const int64_t* labels, int labels_batched, int n_query,
                         int64_t n_support, int n_classes, float* logp, float* row_lse, int32_t* status_flag,
                         void* stream);
@@ -216,6 +219,9 @@ NW_API int nw_direct_forward(int kind, float scale, const float* q, int n_query,
                       int64_t n_support, int support_batched, const int64_t* labels, int labels_batched,
                       int n_classes, float* scores, float* logp, float* row_lse, int32_t* status_flag,
                       void* stream);
+
+/* d + n_classes limit of nw_direct_backward (one feature row + one class table staged in shared memory) */
+#define NW_DIRECT_BACKWARD_MAX_D_PLUS_C 49152
 
 /* closed-form backward.  workspace: nw_direct_backward_workspace_elems(...) floats.
  * grad_q (B, d) and grad_s ((N, d) or (B, N, d)) may each be NULL when not needed.

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 import torch
@@ -18,6 +19,7 @@ EPI_EUCLID, EPI_LINEAR = 0, 1
 PREC_BF16, PREC_BF16X3 = 1, 3
 ROWS_BANK, ROWS_QUERY = 0, 1
 EMIT_SCORES, EMIT_INFLUENCE, EMIT_BLOCK_BEST = 0, 1, 2
+DIRECT_BACKWARD_MAX_D_PLUS_C = 49152  # NW_DIRECT_BACKWARD_MAX_D_PLUS_C
 
 # NW_B200_LIB: developer override to A/B two builds of the library on the same GPU box
 _LIB_PATH = os.environ.get("NW_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnw_sm100.so")
@@ -86,6 +88,37 @@ SIGNATURES = {
 }
 
 _lib = None
+_tls = threading.local()
+
+
+class _DeviceBoundLib:
+    """The loaded library with every entry point wrapped so that it runs with the RIGHT CUDA device current.
+
+    The C ABI takes plain pointers and a stream; kernels launch in the current-device context.  A caller that
+    works on `cuda:1` while `cuda:0` is current (the reference does `.to(x.device)` and never calls set_device)
+    would otherwise launch on the wrong GPU, or fail with cudaErrorInvalidResourceHandle for a non-default
+    stream.  `stream_of(device)` — which every launching call evaluates as an argument — records the device; the
+    wrapper switches to it for the duration of the call when it is not already current (one integer compare on
+    the usual path)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        for name in SIGNATURES:
+            setattr(self, name, self._bind(getattr(cdll, name)))
+
+    @staticmethod
+    def _bind(fn):
+        def call(*args):
+            dev = getattr(_tls, "device", None)
+            _tls.device = None
+            if dev is not None and dev != torch.cuda.current_device():
+                with torch.cuda.device(dev):
+                    return fn(*args)
+            return fn(*args)
+
+        call.__name__ = fn.__name__
+        call.argtypes, call.restype = fn.argtypes, fn.restype
+        return call
 
 
 def lib_path() -> str:
@@ -109,8 +142,8 @@ def load():
         fn.argtypes = args
     if lib.nw_abi_version() != 1:
         raise NWLibraryError("libnw_sm100.so ABI version mismatch")
-    _lib = lib
-    return lib
+    _lib = _DeviceBoundLib(lib)
+    return _lib
 
 
 def check(status: int, what: str) -> None:
@@ -125,6 +158,9 @@ def ptr(t):
 
 
 def stream_of(device) -> c_void_p:
+    """Current stream of `device` as the ABI's void*; also tells the next library call which device to run on."""
+    device = torch.device(device)
+    _tls.device = device.index if device.index is not None else torch.cuda.current_device()
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

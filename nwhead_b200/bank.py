@@ -100,6 +100,8 @@ class SupportBank:
             raise NotImplementedError(kind)
         dev = _abi.require_cuda(feats, labels)
         lib = load()
+        if feats.dtype in (torch.float16, torch.bfloat16):  # features computed under autocast
+            feats = feats.float()
         if feats.dtype != torch.float32:
             raise TypeError(f"support features must be float32, got {feats.dtype}")  # reference: fp64 raises
         if labels.dtype != torch.int64:
@@ -200,6 +202,8 @@ class SupportBank:
     # ------------------------------------------------------------------------------------------
     def prepare_queries(self, q: torch.Tensor):
         """fp32 queries -> (bf16 rows in the query layout, squared norms), centred / normalised like the bank."""
+        if q.dtype in (torch.float16, torch.bfloat16):
+            q = q.float()
         if q.dtype != torch.float32:
             raise TypeError(f"query features must be float32, got {q.dtype}")
         q = q.detach()
@@ -366,7 +370,9 @@ class SupportBank:
         k = min(int(k), n)
         src_all = source_feats.detach().float().reshape(n, d)
         cached = getattr(self, "_resid_of", None)   # (weak reference to the tensor object, its version, max residual)
-        if cached is None or cached[0]() is not source_feats or cached[1] != source_feats._version:
+        if source_feats.is_inference():             # no version counter to validate a cache entry against
+            cached = (None, None, self.rounding_residual(src_all).max())
+        elif cached is None or cached[0]() is not source_feats or cached[1] != source_feats._version:
             cached = (weakref.ref(source_feats), source_feats._version, self.rounding_residual(src_all).max())
             self._resid_of = cached
         resid_max = cached[2]

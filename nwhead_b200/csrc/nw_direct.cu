@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const float* __restrict_
     const long long y = lab[j];
     if (y < 0 || y >= n_classes) ++bad;
   }
-  if (bad) atomicOr(status, 1);
+  if (bad) *reinterpret_cast<volatile int32_t*>(status) = 1;  // plain store: the flag may be mapped host memory
   mx = block_max(mx, red);
   float sum = 0.f;
   for (long long j = threadIdx.x; j < n_support; j += blockDim.x) sum += expf(sc[j] - mx);
@@ -307,7 +307,9 @@ __global__ void __launch_bounds__(256) coef_kernel(int kind, float scale, const 
   for (long long j = threadIdx.x; j < n_support; j += blockDim.x) {
     const float s = sc[j];
     const float p = expf(s - z);
-    const float gs = p * (gP[lab[j]] - dsum);
+    // an out-of-range label (rejected by the forward's status flag) contributes to no class: never index gP with it
+    const long long y = lab[j];
+    const float gs = p * ((y >= 0 && y < n_classes ? gP[y] : 0.f) - dsum);
     float v;
     if (kind_euclid(kind)) {
       const float dist = -s;
@@ -501,10 +503,11 @@ __global__ void __launch_bounds__(256) small_forward_kernel(int kind, float scal
   bool bad = false;
   for (int j = threadIdx.x; j < n_support; j += 256) {
     const long long y = lb[j];
-    bad |= (y < 0 || y >= n_classes);
-    lab[j] = int(y);
+    const bool oob = y < 0 || y >= n_classes;
+    bad |= oob;
+    lab[j] = oob ? -1 : int(y);  // (a 64-bit label must not alias a class after narrowing)
   }
-  if (bad) atomicOr(status, 1);
+  if (bad) *reinterpret_cast<volatile int32_t*>(status) = 1;
   __syncthreads();
   float mx = __int_as_float(0xff800000);
   for (int j = threadIdx.x; j < n_support; j += 256) mx = fmaxf(mx, sc[j]);
@@ -560,7 +563,8 @@ __global__ void __launch_bounds__(256) small_coef_gradq_kernel(
   float gscale = 0.f;
   for (int j = threadIdx.x; j < n_support; j += 256) {
     const float sv = scores[(long long)b * n_support + j];
-    const float gs = expf(sv - z) * (gP[lb[j]] - dsum);
+    const long long y = lb[j];  // out-of-range labels belong to no class (see coef_kernel)
+    const float gs = expf(sv - z) * ((y >= 0 && y < n_classes ? gP[y] : 0.f) - dsum);
     float v;
     if (euc) {
       const float dist = -sv;
@@ -763,8 +767,19 @@ extern "C" int nw_direct_backward(int kind, float scale, const float* q, int n_q
              "NULL pointer argument");
   NW_REQUIRE(grad_q || grad_s, NW_ERR_INVALID, "at least one of grad_q / grad_s must be requested");
   NW_REQUIRE(n_query > 0 && d > 0 && n_support > 0 && n_classes > 0, NW_ERR_INVALID, "shapes must be positive");
-  NW_REQUIRE(d + n_classes <= 10240, NW_ERR_UNSUPPORTED,
-             "direct backward stages one feature row and one class table in 40 KB of shared memory (d + C <= 10240)");
+  NW_REQUIRE(d + n_classes <= NW_DIRECT_BACKWARD_MAX_D_PLUS_C, NW_ERR_UNSUPPORTED,
+             "direct backward stages one feature row and one class table in shared memory (d + C <= %d)",
+             NW_DIRECT_BACKWARD_MAX_D_PLUS_C);
+  // more than the default 48 KB of dynamic shared memory is an opt-in per kernel (and per device: cheap, idempotent)
+  const size_t big = size_t(d + n_classes) * sizeof(float);
+  if (big > 48 * 1024) {
+    const int cap = NW_DIRECT_BACKWARD_MAX_D_PLUS_C * int(sizeof(float));
+    NW_CUDA_OK(cudaFuncSetAttribute(direct::small_coef_gradq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    NW_CUDA_OK(cudaFuncSetAttribute(direct::small_grad_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    NW_CUDA_OK(cudaFuncSetAttribute(direct::coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    NW_CUDA_OK(cudaFuncSetAttribute(direct::grad_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    NW_CUDA_OK(cudaFuncSetAttribute(direct::grad_s_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+  }
   const long long pairs = (long long)n_query * n_support;
   NW_REQUIRE(pairs < (1ll << 31), NW_ERR_UNSUPPORTED, "too many (query, support) pairs for the direct path");
   float* coef = workspace;

@@ -83,20 +83,40 @@ class ShardedBank:
     exchange='peer'  : in-kernel NVLink peer stores into every rank's table + a signal barrier (PeerTables)."""
 
     def __init__(self, shard, group=None, exchange="nccl", max_batch=0):
+        if exchange not in ("nccl", "peer"):
+            raise ValueError(f"unknown exchange {exchange!r}")
         self.shard = shard
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.peer = None
+        if self.world > 1:
+            # Validate the shard plan COLLECTIVELY: a rank without support rows (C < world, empty class ranges)
+            # must make every rank raise, not just itself — the others would wait in the next collective forever.
+            rows = torch.tensor([0 if shard is None else len(shard)], dtype=torch.int64,
+                                device=None if shard is None else shard.device)
+            dist.all_reduce(rows, op=dist.ReduceOp.MIN, group=group)
+            if int(rows.item()) == 0:
+                raise ValueError("a rank owns no support rows: use fewer ranks than non-empty classes")
         if exchange == "peer" and self.world > 1:
+            if max_batch <= 0:
+                raise ValueError("exchange='peer' needs max_batch > 0 (rows of the symmetric class-LSE tables)")
             self.peer = PeerTables(max_batch, shard.n_classes, shard.device, group)
-        elif exchange not in ("nccl", "peer"):
-            raise ValueError(f"unknown exchange {exchange!r}")
 
     @staticmethod
     def from_full(bank, group=None, exchange="nccl", max_batch=0):
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         world = dist.get_world_size(group) if dist.is_initialized() else 1
-        return ShardedBank(bank.class_shard(rank, world) if world > 1 else bank, group, exchange, max_batch)
+        if world == 1:
+            return ShardedBank(bank, group, exchange, max_batch)
+        try:
+            shard = bank.class_shard(rank, world)
+        except ValueError:
+            shard = None  # this rank would own nothing: ShardedBank raises on EVERY rank
+        if shard is None:  # take part in the collective validation, which raises
+            rows = torch.zeros((1,), dtype=torch.int64, device=bank.device)
+            dist.all_reduce(rows, op=dist.ReduceOp.MIN, group=group)
+            raise ValueError("a rank owns no support rows: use fewer ranks than non-empty classes")
+        return ShardedBank(shard, group, exchange, max_batch)
 
     def class_lse(self, q, scale: float = 1.0):
         """(B, C) class log-sum-exp over the WHOLE bank, identical on every rank.  With the peer exchange the

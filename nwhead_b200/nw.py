@@ -19,41 +19,30 @@ from .kernel import get_kernel
 from .support import SupportSetEval, SupportSetTrain
 
 MM_PATH_MIN_ROWS = 26  # torch.cdist uses the matmul form when a side has more than 25 rows
+_HALF_DTYPES = (torch.float16, torch.bfloat16)
 
 
 class _LabelGuard:
-    """Deferred label validation for the direct path.  The kernels OR a bit into a device flag when a label is
-    outside [0, n_classes) (what F.one_hot rejects, reference nwhead/nw.py:276).  The flag is copied to pinned
-    host memory asynchronously and inspected on a LATER call once its event has completed, so the training loop
-    never blocks on the GPU; `check(block=True)` forces the inspection."""
+    """Label validation for the direct path without a host/device synchronisation.
 
-    POLL_EVERY = 32  # the device flag is sticky, so polling it on every 32nd call loses nothing
+    The kernels store 1 into a status flag when a label is outside [0, n_classes) (what F.one_hot rejects,
+    reference nwhead/nw.py:276); such a label contributes to no class and is never used as an index, so nothing
+    can go out of bounds on the device.  The flag lives in PINNED HOST memory that the GPU writes directly (UVA:
+    the pinned pointer is valid on the device), so inspecting it costs one host load: it is polled on EVERY
+    forward and backward call, and `check(block=True)` (NWHead.check_labels) drains the stream first for callers
+    that want the reference's raise-at-the-call behaviour."""
 
     def __init__(self, device):
-        self.flag = torch.zeros((1,), dtype=torch.int32, device=device)
-        self.host = torch.zeros((1,), dtype=torch.int32).pin_memory()
-        self.event = None
-        self.calls = 0
-
-    def after_launch(self):
-        self.calls += 1
-        if self.calls % self.POLL_EVERY and self.calls != 1:
-            return
-        self.host.copy_(self.flag, non_blocking=True)
-        self.event = torch.cuda.Event()
-        self.event.record()
+        self.device = device
+        self.flag = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self._view = self.flag.numpy()
 
     def check(self, block=False):
-        if self.event is None:
-            return
         if block:
-            self.event.synchronize()
-        if self.event.query():
-            self.event = None
-            if int(self.host[0]) != 0:
-                self.flag.zero_()
-                self.host.zero_()
-                raise RuntimeError("Class values must be smaller than num_classes.")
+            torch.cuda.current_stream(self.device).synchronize()
+        if self._view[0]:
+            self._view[0] = 0
+            raise RuntimeError("Class values must be smaller than num_classes.")
 
 
 _guards = {}
@@ -92,7 +81,6 @@ class _NWDirectFunction(torch.autograd.Function):
         check(lib.nw_direct_forward(KIND[kind], scale, ptr(xq), b, d, ptr(sxd), n, int(batched), ptr(syd),
                                     int(syd.dim() == 2), n_classes, ptr(scores), ptr(logp), ptr(row_lse),
                                     ptr(guard.flag), stream_of(dev)), "nw_direct_forward")
-        guard.after_launch()
         ctx.save_for_backward(xq, sxd, syd, scores, row_lse, logp)
         ctx.kind, ctx.n_classes, ctx.scale = kind, n_classes, scale
         ctx.has_scale = logit_scale is not None
@@ -103,6 +91,7 @@ class _NWDirectFunction(torch.autograd.Function):
         lib = load()
         xq, sxd, syd, scores, row_lse, logp = ctx.saved_tensors
         dev = xq.device
+        label_guard(dev).check()  # polled on every call: raises as soon as a finished forward has flagged a bad label
         b, d = xq.shape
         batched = sxd.dim() == 3
         n = sxd.shape[-2]
@@ -137,6 +126,9 @@ class NWHead(nn.Module):
         per call keeps that usage pattern fast; in-place modification bumps `_version` and invalidates the entry."""
         # identity of the live tensor OBJECTS (weak references), not their addresses: a freed support's memory is
         # routinely handed to the next one (knn mode builds a new support per batch)
+        if sx.is_inference() or sy.is_inference():
+            # inference-mode tensors have no version counter: nothing to validate a cached bank against
+            return SupportBank.build(sx, sy, self.n_classes, kind, self.precision)
         key = (sx._version, sy._version, kind, self.precision, self.n_classes)
         for ref_x, ref_y, k, bank in self._bank_cache:
             if ref_x() is sx and ref_y() is sy and k == key:
@@ -146,6 +138,15 @@ class NWHead(nn.Module):
         self._bank_cache.append((weakref.ref(sx), weakref.ref(sy), key, bank))
         del self._bank_cache[:-self.BANK_CACHE_SIZE]
         return bank
+
+    @staticmethod
+    def check_labels(device="cuda") -> None:
+        """Waits for the direct-path work queued on `device` and raises RuntimeError if any of it saw a support
+        label outside [0, n_classes) — the blocking form of the check every call polls without blocking."""
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        label_guard(dev).check(block=True)
 
     def _kind(self):
         kind = getattr(self.kernel, "kind", None)
@@ -163,11 +164,18 @@ class NWHead(nn.Module):
         :return: log of softmaxed probabilities (b, num_classes)
         """
         kind = self._kind()
+        if x.dtype in _HALF_DTYPES:  # a featurizer under autocast: torch.cdist upcasts these too
+            x = x.float()
         if isinstance(sx, SupportBank):
-            # inference-only (the reference's eval step runs predict() with gradients disabled, train.py:408):
-            # the result carries no grad_fn even if x does
+            # inference-only (the reference's eval step runs predict() with gradients disabled, train.py:408).
+            # A differentiable call needs the fp32 support rows: hand NWHead the raw (sx, sy) tensors instead.
+            if torch.is_grad_enabled() and x.requires_grad:
+                raise RuntimeError("a SupportBank is inference-only; pass the raw (sx, sy) support tensors for a "
+                                   "differentiable call (NWNet.predict does this automatically)")
             return sx.forward(x, self.kernel.scale_value())
         _abi.require_cuda(x, sx, sy)
+        if sx.dtype in _HALF_DTYPES:
+            sx = sx.float()
         if x.dtype != torch.float32 or sx.dtype != torch.float32:
             raise TypeError("NWHead expects float32 features")  # the reference raises on fp64 too
         if sy.dtype != torch.int64:
@@ -181,6 +189,11 @@ class NWHead(nn.Module):
         if n == 0:
             raise ValueError("NWHead needs at least one support row")
         if needs_grad or sx.dim() == 3 or n < MM_PATH_MIN_ROWS:
+            if needs_grad and x.shape[-1] + self.n_classes > _abi.DIRECT_BACKWARD_MAX_D_PLUS_C:
+                # fail before the forward, not at .backward()
+                raise NotImplementedError(
+                    f"the differentiable path supports feat_dim + n_classes <= {_abi.DIRECT_BACKWARD_MAX_D_PLUS_C}, "
+                    f"got {x.shape[-1]} + {self.n_classes}")
             return _NWDirectFunction.apply(x, sx, sy, logit_scale, kind, self.n_classes)
         return self._bank_for(sx, sy, kind).forward(x, self.kernel.scale_value())
 
@@ -278,14 +291,17 @@ class NWNet(nn.Module):
         :param mode: Inference mode. One of ['random', 'full', 'cluster', 'ensemble', 'knn', 'hnsw']
         '''
         qfeat = self.featurizer(x)
-        support = self.support_eval.get_support(mode, x=qfeat)
+        # the reference's predict is differentiable (nwhead/nw.py:127-160): with gradients flowing into the
+        # query features the head gets the raw fp32 support rows (direct path), otherwise the device bank
+        raw = torch.is_grad_enabled() and qfeat.requires_grad
+        support = self.support_eval.get_support(mode, x=qfeat, raw=raw)
         if self.debug_mode:
             print('qx shape:', x.shape)
         if mode == 'ensemble':
             # mean over environments of the per-environment class probabilities (reference nwhead/nw.py:143-154)
             probs = 0
             for bank in support:
-                probs = probs + self.nwhead(qfeat, bank).exp()
+                probs = probs + (self.nwhead(qfeat, *bank) if isinstance(bank, tuple) else self.nwhead(qfeat, bank)).exp()
             out = torch.log(probs / len(support))
         elif isinstance(support, SupportBank):
             out = self.nwhead(qfeat, support)

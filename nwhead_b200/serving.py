@@ -25,6 +25,7 @@ class _Slot:
         self.compute_done = torch.cuda.Event()
         self.d2h_done = torch.cuda.Event()
         self.busy = False
+        self.ticket = -1
 
 
 class FullModePredictor:
@@ -60,6 +61,7 @@ class FullModePredictor:
         if slot.busy:
             raise RuntimeError("pipeline full: call result() on the oldest ticket first")
         slot.busy = True
+        slot.ticket = ticket
         self.next += 1
         compute = torch.cuda.current_stream(self.bank.device)
         # The slot's previous use was retired by result() (d2h_done implies its compute finished), so the upload
@@ -83,6 +85,8 @@ class FullModePredictor:
         """Blocks until the batch of `ticket` is back in host memory; returns the pinned (rows, C) tensor
         (valid until the slot is reused `depth` submits later)."""
         slot = self.slots[ticket % len(self.slots)]
+        if not slot.busy or slot.ticket != ticket:
+            raise ValueError(f"ticket {ticket} is not outstanding (never issued, or its result was already taken)")
         slot.d2h_done.synchronize()
         slot.busy = False
         return slot.out_host

@@ -115,22 +115,30 @@ class SupportSetEval(SupportSet):
         self.knn = KNN(self.full_feat, self.full_y, n_neighbors=self.n_neighbors, bank=self.full_bank)
         self.hnsw = HNSW(self.full_feat, self.full_y, n_neighbors=self.n_neighbors, bank=self.full_bank)
 
-    def get_support(self, mode, x=None):
+    def get_support(self, mode, x=None, raw=False):
         '''Returns the support for an inference mode: a SupportBank for 'full' / 'cluster' / 'random', a list of
-        per-environment SupportBanks for 'ensemble', a (features, labels) pair for 'knn'.'''
+        per-environment SupportBanks for 'ensemble', a (features, labels) pair for 'knn'.
+        raw=True returns the fp32 (features, labels) tensors the banks were built from instead (differentiable
+        predict: the direct path needs the unrounded rows).'''
         try:
             if mode == 'random':
                 idx = torch.as_tensor(self.random_iter.sample_indices(), device=self.full_bank.device)
+                if raw:
+                    return self.full_feat[idx], self.full_y[idx]
                 if self._source_to_bank_row is not None:
                     idx = torch.sort(self._source_to_bank_row[idx]).values
                 return self.full_bank.subset(idx)
             elif mode == 'full':
-                return self.full_bank
+                return (self.full_feat, self.full_y) if raw else self.full_bank
             elif mode == 'cluster':
-                return self.cluster_bank
+                return (self.cluster_feat, self.cluster_y) if raw else self.cluster_bank
             elif mode == 'knn':
                 return self.knn(x)
             elif mode == 'ensemble':
+                if raw:
+                    if self.env_banks is None:
+                        return [(self.full_feat, self.full_y)]
+                    return list(zip(self.full_feat_sep, self.full_y_sep))
                 return self.env_banks if self.env_banks is not None else [self.full_bank]
             elif mode == 'hnsw':
                 return self.hnsw(x)

@@ -44,22 +44,45 @@ def load_reference():
     if not reference_available():
         raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
     _install_hnswlib_stub()
-    # The reference's top-level packages are called `nwhead` and `util`; import them under
-    # their own names from the reference root.  Our package is `nwhead_b200`, so no clash.
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    # The reference's top-level packages are called `nwhead` and `util` — the same names as the drop-in shim
+    # packages at this repository's root.  They are loaded here under PRIVATE package names (the reference only
+    # uses relative imports inside `nwhead/`), so neither sys.path nor sys.modules['nwhead'] is touched.
     import importlib
+    import importlib.util
 
-    nw = importlib.import_module("nwhead.nw")
-    kern = importlib.import_module("nwhead.kernel")
-    utils = importlib.import_module("nwhead.utils")
-    support = importlib.import_module("nwhead.support")
-    metric = importlib.import_module("util.metric")
+    def load_pkg(alias, directory):
+        if alias in sys.modules:
+            return sys.modules[alias]
+        pkg = types.ModuleType(alias)
+        pkg.__path__ = [directory]
+        pkg.__package__ = alias
+        sys.modules[alias] = pkg
+        return pkg
+
+    def load_mod(alias_pkg, name, directory):
+        full = f"{alias_pkg}.{name}"
+        if full in sys.modules:
+            return sys.modules[full]
+        spec = importlib.util.spec_from_file_location(full, os.path.join(directory, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[full] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    nw_dir, util_dir = os.path.join(REFERENCE_ROOT, "nwhead"), os.path.join(REFERENCE_ROOT, "util")
+    load_pkg("_reference_nwhead", nw_dir)
+    load_pkg("_reference_util", util_dir)
+    utils = load_mod("_reference_nwhead", "utils", nw_dir)
+    kern = load_mod("_reference_nwhead", "kernel", nw_dir)
+    support = load_mod("_reference_nwhead", "support", nw_dir)
+    nw = load_mod("_reference_nwhead", "nw", nw_dir)
+    metric = load_mod("_reference_util", "metric", util_dir)
     ns = types.SimpleNamespace(
         NWNet=nw.NWNet,
         NWHead=nw.NWHead,
         get_kernel=kern.get_kernel,
         support_influence=metric.support_influence,
+        metric=metric,
         compute_clusters=utils.compute_clusters,
         FullDataset=utils.FullDataset,
         InfiniteUniformClassLoader=utils.InfiniteUniformClassLoader,

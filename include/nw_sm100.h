@@ -134,6 +134,13 @@ typedef struct nw_forward_plan_t {
 
 NW_API int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t* plan_out);
 
+/* Measurement hook (bench.py `sustained.sm_mhz_in_kernel`; no reference counterpart).  While a buffer is set, every
+ * fused-forward launch whose grid fits ADDS, per CTA i, the SM cycles (clock64) and the nanoseconds (globaltimer)
+ * its epilogue role was alive to buf[2 i] and buf[2 i + 1] (uint64, caller-zeroed device memory): cycles / ns is
+ * the SM clock the kernel actually ran at, integrated over the launches.  buf = NULL switches it off.
+ * Process-wide, not thread-safe. */
+NW_API int nw_forward_set_clock_probe(void* buf_u64, int64_t capacity_ctas);
+
 /* class_lse[b, c] = log sum_{j : labels[j] == c} exp(score(b, j)); -inf for classes with no support
  * row in this bank (or bank shard).  Inputs are the bf16 layouts of nw_rows_to_bf16.
  * labels must be class-sorted int32.  q_sqnorm / s_sqnorm are only read for NW_EPI_EUCLID.

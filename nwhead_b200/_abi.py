@@ -55,6 +55,7 @@ SIGNATURES = {
                                 c_void_p, c_int, c_void_p, c_void_p]),
     "nw_rounding_residual": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "nw_forward_plan": (c_int, [c_int, c_int64, POINTER(ForwardPlan)]),
+    "nw_forward_set_clock_probe": (c_int, [c_void_p, c_int64]),
     "nw_forward_class_lse": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                      c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "nw_forward_class_lse_peers": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

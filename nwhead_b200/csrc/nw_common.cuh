@@ -291,6 +291,12 @@ __device__ __forceinline__ float influence_one(float p, float w, bool same) {
   return influence_exact(p, w, den);  // rare, out of line: keeps unrolled callers small (instruction cache)
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

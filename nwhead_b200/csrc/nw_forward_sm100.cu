@@ -108,6 +108,7 @@ struct Params {
   long long emit_ld;
   int emit_kind;             // NW_EMIT_SCORES | NW_EMIT_INFLUENCE
   int emit_vec;              // 1: 16-byte stores are aligned
+  unsigned long long* clock_probe;  // diagnostics (nw_forward_set_clock_probe) or NULL: per-CTA SM cycles + ns
   const float* row_lse;      // (B) logsumexp_j score(b, j)          [influence]
   const float* p_query;      // (B) softmax mass of the query's class [influence]
   const int32_t* qlabel;     // (B) query labels                      [influence]
@@ -428,6 +429,16 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const float neg_inf = __int_as_float(0xff800000);
     const float pos_inf = __int_as_float(0x7f800000);
     uint32_t tc = 0;
+    // Effective SM clock of this launch, measured in the kernel: SM cycles (clock64) over wall time (globaltimer)
+    // across the whole epilogue role of one thread per CTA, accumulated per CTA so that a series of launches
+    // yields the time-weighted mean.  nvidia-smi / NVML clocks are instantaneous samples; this is the integral.
+    const bool probe = p.clock_probe != nullptr && warp == EPI_WARP0 && lane == 0;
+    long long probe_c0 = 0;
+    unsigned long long probe_t0 = 0;
+    if (probe) {
+      probe_c0 = clock64();
+      probe_t0 = globaltimer_ns();
+    }
     for (int u = worker; u < n_units; u += n_workers) {
       const int g = u / p.q_groups;
       const int qg = u - g * p.q_groups;
@@ -578,6 +589,10 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       // two sets: the unit's last columns may belong to the other set; close what this set still holds
       if (MODE == MODE_CLASS_LSE && p.sets == 2 && open_cls >= 0) flush(open_cls, m, l);
+    }
+    if (probe) {
+      atomicAdd(p.clock_probe + 2 * blockIdx.x, (unsigned long long)(clock64() - probe_c0));
+      atomicAdd(p.clock_probe + 2 * blockIdx.x + 1, globaltimer_ns() - probe_t0);
     }
   }
 
@@ -786,6 +801,17 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
 
 using namespace nw;
 
+// diagnostics: per-CTA (SM cycles, nanoseconds) accumulators written by the forward kernels while set
+static unsigned long long* g_clock_probe = nullptr;
+static long long g_clock_probe_ctas = 0;
+
+extern "C" int nw_forward_set_clock_probe(void* buf, int64_t capacity_ctas) {
+  NW_REQUIRE(buf == nullptr || capacity_ctas > 0, NW_ERR_INVALID, "capacity_ctas must be positive");
+  g_clock_probe = static_cast<unsigned long long*>(buf);
+  g_clock_probe_ctas = buf ? capacity_ctas : 0;
+  return NW_OK;
+}
+
 static bool force_single_cta() {
   const char* e = getenv("NW_B200_FORCE_1CTA");
   return e && e[0] == '1';
@@ -945,6 +971,7 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.emit_ld = 0;
   p.emit_kind = 0;
   p.emit_vec = 0;
+  p.clock_probe = (g_clock_probe && plan.grid <= g_clock_probe_ctas) ? g_clock_probe : nullptr;
   p.row_lse = p.p_query = nullptr;
   p.qlabel = nullptr;
 

@@ -59,3 +59,17 @@ def port_class_centroids(feats, labels):
         cents.append(feats[labels == c].mean(dim=0, keepdim=True))
         ys.append(c)
     return torch.cat(cents, dim=0), torch.tensor(ys)
+
+
+def port_compute_clusters(embeddings, labels, n_clusters):
+    """nwhead/utils.py:218-233 (closest=False): one scikit-learn KMeans(n_clusters, random_state=0) fit per class
+    over a boolean-mask gather, classes in sorted-unique order.  This is the CPU baseline of cluster-mode
+    precompute (BASELINE config 4); for n_clusters=1 its result is the class mean (port_class_centroids)."""
+    from sklearn.cluster import KMeans
+
+    cents, ys = [], []
+    for c in torch.unique(labels).tolist():
+        km = KMeans(n_clusters=n_clusters, random_state=0).fit(embeddings[labels == c].numpy())
+        cents.append(torch.from_numpy(km.cluster_centers_).float())
+        ys += [c] * n_clusters
+    return torch.cat(cents, dim=0), torch.tensor(ys)

@@ -80,3 +80,39 @@ def test_two_gpu_bank_shards_match_single_gpu(cuda_lib):
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+def test_second_gpu_while_first_is_current(cuda_lib):
+    """the reference works on any device through `.to(x.device)` and never calls set_device.  Everything
+    here lives on cuda:1 while cuda:0 stays the current device; the library must launch on cuda:1 (on a side stream
+    too) and give the bits of the cuda:0 run."""
+    import nwhead_b200
+
+    assert torch.cuda.current_device() == 0
+    q, s, y, _ = clustered_features(12, 50, 128, 200, seed=5)
+    outs = {}
+    for dev in ("cuda:0", "cuda:1"):
+        qt, st, yt = torch.from_numpy(q).to(dev), torch.from_numpy(s).to(dev), torch.from_numpy(y).to(dev)
+        head = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), 12)
+        bank = nwhead_b200.SupportBank.build(st, yt, 12, "euclidean", "bf16")
+        with torch.no_grad():
+            a = head(qt, bank)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                b = head(qt, bank)
+            side.synchronize()
+        q8 = qt[:8].clone().requires_grad_(True)
+        s10 = st[:10].clone().requires_grad_(True)
+        out = head(q8, s10, yt[:10])
+        out.sum().backward()
+        infl = nwhead_b200.support_influence(torch.softmax(a[:4], 1), torch.nn.functional.one_hot(yt[:4], 12).float(),
+                                             torch.softmax(torch.randn(4, 600, generator=torch.Generator().manual_seed(1)),
+                                                           1).to(dev),
+                                             torch.nn.functional.one_hot(yt, 12).float())
+        assert torch.cuda.current_device() == 0
+        assert a.device == torch.device(dev) and torch.equal(a, b)
+        outs[dev] = [t.detach().cpu() for t in (a, out, q8.grad, s10.grad, infl)]
+    for x0, x1 in zip(outs["cuda:0"], outs["cuda:1"]):
+        assert torch.equal(x0, x1)

@@ -438,6 +438,20 @@ def aux_configs(feats, labels, bank, mu, dev, peaks):
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / iters * 1e6
 
+    class _NoopHead(torch.autograd.Function):  # what torch's own machinery costs around a two-input custom op
+        @staticmethod
+        def forward(ctx, a, b_):
+            ctx.save_for_backward(a, b_)
+            return out_static
+
+        @staticmethod
+        def backward(ctx, g_):
+            a, b_ = ctx.saved_tensors
+            return ga_static, gb_static
+
+    out_static = torch.zeros(8, 200, device=dev)
+    ga_static, gb_static = torch.zeros_like(q0), torch.zeros_like(s0)
+    floor = wall_us(lambda: step(lambda a, b_, c_: _NoopHead.apply(a, b_), q0, s0, sy2, qy2))
     ours = wall_us(lambda: step(head, q0, s0, sy2, qy2))
     eager = wall_us(lambda: step(lambda a, b_, c_: TP.port_nw_forward(a, b_, c_, 200, "euclidean"), q0, s0, sy2, qy2))
     qc, sc, syc, qyc = q0.cpu(), s0.cpu(), sy2.cpu(), qy2.cpu()
@@ -448,8 +462,10 @@ def aux_configs(feats, labels, bank, mu, dev, peaks):
     out["cfg2_episodic_head"] = {
         "workload": "NW head forward+backward B=8 N=10 d=512 C=200 (direct fp32 kernels), wall time per step in a "
                     "tight loop incl. autograd, 2 clones and nll_loss",
-        "wall_us": ours, "torch_gpu_unfused_wall_us": eager,
-        "note": "latency-bound: a tensor-peak fraction is meaningless at 82 kFLOP",
+        "wall_us": ours, "torch_gpu_unfused_wall_us": eager, "autograd_glue_floor_wall_us": floor,
+        "note": "latency-bound: a tensor-peak fraction is meaningless at 82 kFLOP.  The floor is the same loop with "
+                "a custom autograd op that launches nothing (2 clones, nll_loss forward/backward, the autograd "
+                "engine, 2 gradient accumulations): host time no head implementation can remove",
         "cpu_baseline": {"wall_us": cpu_us, "cores": cores, "kind": "port",
                          "sample": "the same step through the reference's op sequence on CPU tensors, 200 iterations"}}
     return out

@@ -109,6 +109,17 @@ NW_API int nw_rows_to_bf16(const float* rows, int64_t n, int d, int64_t ld, cons
                     int normalize, int layout, int precision, void* out_bf16, int row_elems,
                     float* sqnorm_out, void* stream);
 
+/* Query conversion fused with replication across the GPUs that share a sharded bank (nwhead_b200/dist.py; no
+ * reference counterpart — the reference has no multi-GPU code).  This rank converts ITS n query rows (NW_ROWS_QUERY
+ * layout) and stores them as rows [row_offset, row_offset + n) of EVERY destination buffer: out_bf16_host[r] is rank
+ * r's (row_elems / 64, n_total, 64) query buffer and sqnorm_host[r] its (n_total) norm vector, peer-mapped over
+ * NVLink (host arrays of device pointers, n_dest <= 16).  Replaces an fp32 all-gather of the queries followed by
+ * n_dest-fold redundant conversion.  The caller separates these stores from the consuming forward (a signal
+ * barrier across the ranks on the same stream). */
+NW_API int nw_rows_to_bf16_peers(const float* rows, int64_t n, int d, int64_t ld, const float* center, int normalize,
+                          int precision, void* const* out_bf16_host, float* const* sqnorm_host, int n_dest,
+                          int64_t n_total, int64_t row_offset, int row_elems, void* stream);
+
 /* resid_sq_out[i] = squared norm of what nw_rows_to_bf16 (normalize = 0) discards from row i: |x - hi|^2 for
  * NW_PREC_BF16, |x - hi - lo|^2 for NW_PREC_BF16X3, x = rows[i, :] - center.  By the triangle inequality the
  * distance between two rounded rows differs from the true one by at most the sum of their residual norms: the

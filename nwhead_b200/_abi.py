@@ -53,6 +53,8 @@ SIGNATURES = {
     "nw_column_mean": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nw_rows_to_bf16": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_void_p, c_int, c_void_p, c_void_p]),
+    "nw_rows_to_bf16_peers": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_int, POINTER(c_void_p),
+                                      POINTER(c_void_p), c_int, c_int64, c_int64, c_int, c_void_p]),
     "nw_rounding_residual": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "nw_forward_plan": (c_int, [c_int, c_int64, POINTER(ForwardPlan)]),
     "nw_forward_set_clock_probe": (c_int, [c_void_p, c_int64]),

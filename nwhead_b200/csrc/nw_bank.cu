@@ -105,21 +105,34 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
   return uint32_t(__bfloat16_as_ushort(a)) | (uint32_t(__bfloat16_as_ushort(b)) << 16);
 }
 
+// Where the converted rows go.  One destination for the bank and for single-GPU queries; with the bank sharded
+// over several GPUs every rank converts ITS slice of the query batch and stores it straight into every rank's
+// query buffer (peer-mapped symmetric memory, NVLink stores): the queries are replicated by the conversion kernel
+// itself — no fp32 all-gather, no R-fold redundant conversion.
+constexpr int MAX_DEST = 16;
+struct RowDest {
+  __nv_bfloat16* out[MAX_DEST];  // (row_elems / 64, n_total, 64) each
+  float* sqnorm[MAX_DEST];       // (n_total) each, or NULL
+  int n_dest;
+  long long n_total;             // rows of a destination buffer
+  long long row_offset;          // destination row of source row 0
+};
+
 // One warp per output row.  VEC: 16-byte loads (d % 4 == 0, ld % 4 == 0, 16-B aligned base).
 template <bool VEC>
 __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restrict__ rows, long long n, int d,
                                                            long long ld, const int64_t* __restrict__ perm,
                                                            const float* __restrict__ center, int normalize,
-                                                           int layout, int precision,
-                                                           __nv_bfloat16* __restrict__ out, int row_elems,
-                                                           float* __restrict__ sqnorm_out) {
+                                                           int layout, int precision, const RowDest dest,
+                                                           int row_elems) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const float* src = rows + (perm ? perm[row] : row) * ld;
-  // k-block-major output: element (row, col) lives at ((col / 64) * n + row) * 64 + col % 64, so that every
+  // k-block-major output: element (row, col) lives at ((col / 64) * n_total + row) * 64 + col % 64, so that every
   // (row tile, k-block) box the fused forward loads with TMA is one contiguous run of 128-byte rows in HBM
-  auto at = [&](int col) -> __nv_bfloat16* { return out + ((long long)(col >> 6) * n + row) * 64 + (col & 63); };
+  const long long drow = dest.row_offset + row;
+  auto off = [&](int col) -> long long { return ((long long)(col >> 6) * dest.n_total + drow) * 64 + (col & 63); };
 
   float inv = 1.0f;
   if (normalize) {
@@ -158,6 +171,7 @@ __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restri
       __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+        lo[i] = __float2bfloat16_rn(0.f);
         hi[i] = __float2bfloat16_rn(x[i]);
         const float h = __bfloat162float(hi[i]);
         if (precision == NW_PREC_BF16X3) {
@@ -169,10 +183,13 @@ __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restri
         }
       }
       const uint2 ph = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]));
-      *reinterpret_cast<uint2*>(at(c)) = ph;
-      if (precision == NW_PREC_BF16X3) {
-        *reinterpret_cast<uint2*>(at(seg_hi2 + c)) = ph;
-        *reinterpret_cast<uint2*>(at(seg_lo + c)) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+      const uint2 pl = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+      for (int r = 0; r < dest.n_dest; ++r) {
+        *reinterpret_cast<uint2*>(dest.out[r] + off(c)) = ph;
+        if (precision == NW_PREC_BF16X3) {
+          *reinterpret_cast<uint2*>(dest.out[r] + off(seg_hi2 + c)) = ph;
+          *reinterpret_cast<uint2*>(dest.out[r] + off(seg_lo + c)) = pl;
+        }
       }
     }
   } else {
@@ -180,21 +197,29 @@ __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restri
       const float x = (src[c] - (center ? center[c] : 0.f)) * inv;
       const __nv_bfloat16 hi = __float2bfloat16_rn(x);
       const float h = __bfloat162float(hi);
-      *at(c) = hi;
+      __nv_bfloat16 lo = __float2bfloat16_rn(0.f);
       if (precision == NW_PREC_BF16X3) {
-        const __nv_bfloat16 lo = __float2bfloat16_rn(x - h);
+        lo = __float2bfloat16_rn(x - h);
         const float l = __bfloat162float(lo);
-        *at(seg_hi2 + c) = hi;
-        *at(seg_lo + c) = lo;
         sq += h * h + 2.0f * h * l;
       } else {
         sq += h * h;
       }
+      for (int r = 0; r < dest.n_dest; ++r) {
+        dest.out[r][off(c)] = hi;
+        if (precision == NW_PREC_BF16X3) {
+          dest.out[r][off(seg_hi2 + c)] = hi;
+          dest.out[r][off(seg_lo + c)] = lo;
+        }
+      }
     }
   }
-  for (int c = precision * d + lane; c < row_elems; c += 32) *at(c) = __float2bfloat16_rn(0.f);
+  for (int c = precision * d + lane; c < row_elems; c += 32)
+    for (int r = 0; r < dest.n_dest; ++r) dest.out[r][off(c)] = __float2bfloat16_rn(0.f);
   sq = warp_sum(sq);
-  if (lane == 0 && sqnorm_out) sqnorm_out[row] = sq;
+  if (lane == 0)
+    for (int r = 0; r < dest.n_dest; ++r)
+      if (dest.sqnorm[r]) dest.sqnorm[r][drow] = sq;
 }
 
 // Squared norm of what the bf16 rounding discards, per row: |x - hi|^2 (NW_PREC_BF16) or |x - hi - lo|^2
@@ -284,31 +309,67 @@ extern "C" int nw_column_mean(const float* rows, int64_t n, int d, int64_t ld, f
   return NW_OK;
 }
 
-extern "C" int nw_rows_to_bf16(const float* rows, int64_t n, int d, int64_t ld, const int64_t* perm,
-                               const float* center, int normalize, int layout, int precision, void* out_bf16,
-                               int row_elems, float* sqnorm_out, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  NW_REQUIRE(rows && out_bf16, NW_ERR_INVALID, "NULL pointer argument");
+static int rows_to_bf16_impl(const float* rows, int64_t n, int d, int64_t ld, const int64_t* perm, const float* center,
+                             int normalize, int layout, int precision, const k0::RowDest& dest, int row_elems,
+                             cudaStream_t stream) {
+  NW_REQUIRE(rows != nullptr, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(n > 0 && d > 0 && ld >= d, NW_ERR_INVALID, "bad shape n=%lld d=%d ld=%lld", (long long)n, d, (long long)ld);
   NW_REQUIRE(layout == NW_ROWS_BANK || layout == NW_ROWS_QUERY, NW_ERR_INVALID, "unknown layout %d", layout);
   NW_REQUIRE(precision == NW_PREC_BF16 || precision == NW_PREC_BF16X3, NW_ERR_INVALID, "unknown precision %d", precision);
   NW_REQUIRE(row_elems == nw_row_elems(d, precision), NW_ERR_INVALID, "row_elems %d != nw_row_elems(%d, %d)",
              row_elems, d, precision);
-  const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0) &&
-                   (!center || (reinterpret_cast<uintptr_t>(center) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0);
+  bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0) &&
+             (!center || (reinterpret_cast<uintptr_t>(center) & 15) == 0);
+  for (int r = 0; r < dest.n_dest; ++r) {
+    NW_REQUIRE(dest.out[r] != nullptr, NW_ERR_INVALID, "NULL destination %d", r);
+    vec = vec && ((reinterpret_cast<uintptr_t>(dest.out[r]) & 7) == 0);
+  }
   const int warps_per_block = 8;
   const long long blocks = ceil_div_ll(n, warps_per_block);
   NW_REQUIRE(blocks < (1ll << 31), NW_ERR_UNSUPPORTED, "too many rows");
-  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_bf16);
   if (vec)
     k0::rows_to_bf16_kernel<true><<<unsigned(blocks), warps_per_block * 32, 0, stream>>>(
-        rows, n, d, ld, perm, center, normalize, layout, precision, out, row_elems, sqnorm_out);
+        rows, n, d, ld, perm, center, normalize, layout, precision, dest, row_elems);
   else
     k0::rows_to_bf16_kernel<false><<<unsigned(blocks), warps_per_block * 32, 0, stream>>>(
-        rows, n, d, ld, perm, center, normalize, layout, precision, out, row_elems, sqnorm_out);
+        rows, n, d, ld, perm, center, normalize, layout, precision, dest, row_elems);
   NW_CUDA_OK(cudaGetLastError());
   return NW_OK;
+}
+
+extern "C" int nw_rows_to_bf16(const float* rows, int64_t n, int d, int64_t ld, const int64_t* perm,
+                               const float* center, int normalize, int layout, int precision, void* out_bf16,
+                               int row_elems, float* sqnorm_out, void* stream_) {
+  NW_REQUIRE(out_bf16 != nullptr, NW_ERR_INVALID, "NULL pointer argument");
+  k0::RowDest dest = {};
+  dest.out[0] = static_cast<__nv_bfloat16*>(out_bf16);
+  dest.sqnorm[0] = sqnorm_out;
+  dest.n_dest = 1;
+  dest.n_total = n;
+  dest.row_offset = 0;
+  return rows_to_bf16_impl(rows, n, d, ld, perm, center, normalize, layout, precision, dest, row_elems,
+                           static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int nw_rows_to_bf16_peers(const float* rows, int64_t n, int d, int64_t ld, const float* center,
+                                     int normalize, int precision, void* const* out_bf16_host,
+                                     float* const* sqnorm_host, int n_dest, int64_t n_total, int64_t row_offset,
+                                     int row_elems, void* stream_) {
+  NW_REQUIRE(out_bf16_host != nullptr, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n_dest >= 1 && n_dest <= k0::MAX_DEST, NW_ERR_INVALID, "n_dest must be in [1, %d]", k0::MAX_DEST);
+  NW_REQUIRE(row_offset >= 0 && row_offset + n <= n_total, NW_ERR_INVALID,
+             "rows [%lld, %lld) do not fit a destination of %lld rows", (long long)row_offset,
+             (long long)(row_offset + n), (long long)n_total);
+  k0::RowDest dest = {};
+  for (int r = 0; r < n_dest; ++r) {
+    dest.out[r] = static_cast<__nv_bfloat16*>(out_bf16_host[r]);
+    dest.sqnorm[r] = sqnorm_host ? sqnorm_host[r] : nullptr;
+  }
+  dest.n_dest = n_dest;
+  dest.n_total = n_total;
+  dest.row_offset = row_offset;
+  return rows_to_bf16_impl(rows, n, d, ld, nullptr, center, normalize, NW_ROWS_QUERY, precision, dest, row_elems,
+                           static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int nw_rounding_residual(const float* rows, int64_t n, int d, int64_t ld, const float* center,

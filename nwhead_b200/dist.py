@@ -76,6 +76,67 @@ class PeerTables:
         return self.tables[i], self.handles[i], self.ptr_arrays[i], i
 
 
+class PeerQueries:
+    """Double-buffered query buffers in symmetric memory: (row_elems/64, max_batch, 64) bf16 + (max_batch,) fp32
+    squared norms per rank.  `replicate(q_rows)` converts THIS rank's rows of the batch and stores them into every
+    rank's buffer (nw_rows_to_bf16_peers: NVLink stores from the conversion kernel), then a signal barrier on the
+    current stream; afterwards every rank holds the whole prepared batch.  Replaces an fp32 all-gather of the
+    queries (twice the NVLink bytes) followed by world-fold redundant conversion.
+
+    Hazards: step i writes buffer i%2 on every rank, barrier, then each rank's forward reads its own copy.  Buffer
+    i%2 is written again at step i+2; a rank only issues that after it has RETIRED step i (FullModePredictor.result),
+    which needs the exchange after the forward of step i — and every rank takes part in that exchange only once its
+    own forward of step i has finished reading the buffer."""
+
+    CHANNEL0 = 2  # signal-pad channels 0/1 belong to PeerTables
+
+    def __init__(self, shard, max_batch: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _abi
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.shard, self.max_batch = shard, max_batch
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        kb = shard.row_elems // 64
+        self.bufs = []
+        for _ in range(2):
+            qb = symm_mem.empty((kb, max_batch, 64), dtype=torch.bfloat16, device=shard.device)
+            qs = symm_mem.empty((max_batch,), dtype=torch.float32, device=shard.device)
+            qb.zero_()
+            qs.zero_()
+            hb = symm_mem.rendezvous(qb, self.group.group_name)
+            hs = symm_mem.rendezvous(qs, self.group.group_name)
+            pb = (ctypes.c_void_p * self.world)(*list(hb.buffer_ptrs))
+            ps = (ctypes.c_void_p * self.world)(*list(hs.buffer_ptrs))
+            self.bufs.append((qb, qs, hb, pb, ps))
+        torch.cuda.synchronize(shard.device)
+        dist.barrier(self.group)
+        self.step = 0
+        self._abi = _abi
+
+    def replicate(self, q_rows: torch.Tensor, batch: int):
+        """q_rows: this rank's (batch / world, d) fp32 rows.  Returns the (row_elems/64, batch, 64) bf16 batch and
+        its (batch,) squared norms, complete on every rank once the stream reaches the barrier."""
+        abi, bank = self._abi, self.shard
+        rows = q_rows.shape[0]
+        if rows * self.world != batch or batch != self.max_batch:
+            raise ValueError(f"expected {self.max_batch // self.world} rows per rank (batch {self.max_batch}), got {rows}")
+        if q_rows.dtype != torch.float32 or q_rows.stride(1) != 1:
+            q_rows = q_rows.float().contiguous()
+        i = self.step % 2
+        self.step += 1
+        qb, qs, hb, pb, ps = self.bufs[i]
+        from .bank import NORMALISED_KINDS
+
+        abi.check(abi.load().nw_rows_to_bf16_peers(
+            abi.ptr(q_rows), rows, bank.d, q_rows.stride(0), abi.ptr(bank.center), int(bank.kind in NORMALISED_KINDS),
+            bank.precision, pb, ps, self.world, batch, self.rank * rows, bank.row_elems, abi.stream_of(bank.device)),
+            "nw_rows_to_bf16_peers")
+        hb.barrier(channel=self.CHANNEL0 + i)
+        return qb, qs
+
+
 class ShardedBank:
     """This rank's class-aligned shard of a support bank + the merged forward.
 
@@ -146,6 +207,19 @@ class ShardedBank:
             raise ValueError(f"batch {b} exceeds the peer tables' max_batch {self.peer.max_batch}")
         table, hdl, ptrs, ch = self.peer.next()
         q_bf16, q_sq = self.shard.prepare_queries(q)
+        self.shard.class_lse_prepared(q_bf16, q_sq, scale, tables=ptrs, rows_per_table=rows)
+        hdl.barrier(channel=ch)
+        return table[rank * rows:(rank + 1) * rows]
+
+    def class_lse_rows_prepared(self, q_bf16, q_sq, scale: float = 1.0):
+        """class_lse_rows for a batch that is already converted and replicated (PeerQueries.replicate)."""
+        b = q_bf16.shape[1]
+        rank = dist.get_rank(self.group) if self.world > 1 else 0
+        rows = b // self.world
+        if self.peer is None:
+            lse = merge_class_lse(self.shard.class_lse_prepared(q_bf16, q_sq, scale), self.group)
+            return lse[rank * rows:(rank + 1) * rows]
+        table, hdl, ptrs, ch = self.peer.next()
         self.shard.class_lse_prepared(q_bf16, q_sq, scale, tables=ptrs, rows_per_table=rows)
         hdl.barrier(channel=ch)
         return table[rank * rows:(rank + 1) * rows]

@@ -35,6 +35,7 @@ class _LabelGuard:
     def __init__(self, device):
         self.device = device
         self.flag = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self.flag_ptr = self.flag.data_ptr()
         self._view = self.flag.numpy()
 
     def check(self, block=False):
@@ -61,27 +62,36 @@ def _c(t):
 
 class _NWDirectFunction(torch.autograd.Function):
     """Differentiable NWHead.forward (reference nwhead/nw.py:266-289) on the direct fp32 kernels;
-    backward is the closed form of SURVEY.md B.2 (nw_direct_backward)."""
+    backward is the closed form of SURVEY.md B.2 (nw_direct_backward).
+
+    The episodic step (B=8, N=10) is 23 us of GPU work and host-bound, so this wrapper is written for few
+    Python-level operations: two allocations in forward (the result, and one scratch block holding the scores, the
+    row log-sum-exp AND the backward's workspace), two in backward (the gradients), pointers passed as plain
+    integers, no views, no extra library calls."""
 
     @staticmethod
     def forward(ctx, x, sx, sy, logit_scale, kind, n_classes):
         lib = load()
-        dev = _abi.require_cuda(x, sx, sy)
-        xq, sxd, syd = _c(x.detach()), _c(sx.detach()), _c(sy.detach())
+        dev = x.device
+        if not (x.is_cuda and sx.device == dev and sy.device == dev):
+            dev = _abi.require_cuda(x, sx, sy)  # raises: a CPU tensor, or tensors on different devices
+        xq, sxd, syd = _c(x), _c(sx), _c(sy)  # (grad mode is off inside forward: no detach needed)
         b, d = xq.shape
         batched = sxd.dim() == 3
         n = sxd.shape[-2]
+        pairs = b * n
         scale = float(logit_scale.detach().exp()) if logit_scale is not None else 1.0
         guard = label_guard(dev)
         guard.check()
-        buf = torch.empty((b * (n + n_classes + 1),), dtype=torch.float32, device=dev)  # one allocation
-        scores = buf[:b * n].view(b, n)
-        logp = buf[b * n:b * (n + n_classes)].view(b, n_classes)
-        row_lse = buf[b * (n + n_classes):]
-        check(lib.nw_direct_forward(KIND[kind], scale, ptr(xq), b, d, ptr(sxd), n, int(batched), ptr(syd),
-                                    int(syd.dim() == 2), n_classes, ptr(scores), ptr(logp), ptr(row_lse),
-                                    ptr(guard.flag), stream_of(dev)), "nw_direct_forward")
-        ctx.save_for_backward(xq, sxd, syd, scores, row_lse, logp)
+        logp = torch.empty((b, n_classes), dtype=torch.float32, device=dev)
+        # scratch: scores (b*n) | row_lse (b) | backward workspace (nw_direct_backward_workspace_elems)
+        ws = pairs + (pairs if batched else n) + b if any(ctx.needs_input_grad) else 0
+        aux = torch.empty((pairs + b + ws,), dtype=torch.float32, device=dev)
+        p_aux = aux.data_ptr()
+        check(lib.nw_direct_forward(KIND[kind], scale, xq.data_ptr(), b, d, sxd.data_ptr(), n, int(batched),
+                                    syd.data_ptr(), int(syd.dim() == 2), n_classes, p_aux, logp.data_ptr(),
+                                    p_aux + 4 * pairs, guard.flag_ptr, stream_of(dev)), "nw_direct_forward")
+        ctx.save_for_backward(xq, sxd, syd, aux, logp)
         ctx.kind, ctx.n_classes, ctx.scale = kind, n_classes, scale
         ctx.has_scale = logit_scale is not None
         return logp
@@ -89,24 +99,26 @@ class _NWDirectFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         lib = load()
-        xq, sxd, syd, scores, row_lse, logp = ctx.saved_tensors
+        xq, sxd, syd, aux, logp = ctx.saved_tensors
         dev = xq.device
         label_guard(dev).check()  # polled on every call: raises as soon as a finished forward has flagged a bad label
         b, d = xq.shape
         batched = sxd.dim() == 3
         n = sxd.shape[-2]
+        pairs = b * n
         need_q, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         need_scale = ctx.has_scale and ctx.needs_input_grad[3]
-        g = _c(grad_out.detach().float())
+        g = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else grad_out.float().contiguous()
         gq = torch.empty_like(xq) if (need_q or not need_s) else None
         gs = torch.empty_like(sxd) if need_s else None
         gscale = torch.empty((b,), dtype=torch.float32, device=dev) if need_scale else None
-        ws = torch.empty((lib.nw_direct_backward_workspace_elems(b, n, int(batched)),), dtype=torch.float32,
-                         device=dev)
-        check(lib.nw_direct_backward(KIND[ctx.kind], ctx.scale, ptr(xq), b, d, ptr(sxd), n, int(batched),
-                                     ptr(syd), int(syd.dim() == 2), ctx.n_classes, ptr(scores), ptr(row_lse),
-                                     ptr(logp), ptr(g), ptr(ws), ptr(gq), ptr(gs), ptr(gscale),
-                                     stream_of(dev)), "nw_direct_backward")
+        p_aux = aux.data_ptr()
+        check(lib.nw_direct_backward(KIND[ctx.kind], ctx.scale, xq.data_ptr(), b, d, sxd.data_ptr(), n, int(batched),
+                                     syd.data_ptr(), int(syd.dim() == 2), ctx.n_classes, p_aux, p_aux + 4 * pairs,
+                                     logp.data_ptr(), g.data_ptr(), p_aux + 4 * (pairs + b),
+                                     None if gq is None else gq.data_ptr(), None if gs is None else gs.data_ptr(),
+                                     None if gscale is None else gscale.data_ptr(), stream_of(dev)),
+              "nw_direct_backward")
         return (gq if need_q else None, gs, None, gscale.sum() if need_scale else None, None, None)
 
 

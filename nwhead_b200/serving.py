@@ -5,9 +5,11 @@ in host memory.  Host<->device copies run on their own CUDA streams and are doub
 batch i+1 and the read-back of batch i-1 overlap the fused forward of batch i.
 
 With a process group (one rank per GPU, class-aligned bank shards — nwhead_b200/dist.py) the host I/O is
-sharded too: rank r uploads only rows [r*B/R, (r+1)*B/R) of the batch, the ranks all-gather the queries over
-NVLink, run the fused forward on their bank shard, merge with ONE all-reduce(MAX), and each rank finalises and
-returns only its own rows.  PCIe traffic per rank drops by R while every query still sees the whole bank.
+sharded too: rank r uploads only rows [r*B/R, (r+1)*B/R) of the batch, converts them to the bf16 query layout and
+stores them into every rank's query buffer over NVLink from the conversion kernel itself (peer exchange; with the
+NCCL exchange: an all-gather of the fp32 rows), the ranks run the fused forward on their bank shard, exchange the
+class log-sum-exp entries (in-kernel peer stores, or ONE all-reduce(MAX)), and each rank finalises and returns only
+its own rows.  PCIe traffic per rank drops by R while every query still sees the whole bank.
 """
 import torch
 import torch.distributed as dist
@@ -48,8 +50,16 @@ class FullModePredictor:
         dev = bank.device
         self.copy_stream = torch.cuda.Stream(dev)
         self.out_stream = torch.cuda.Stream(dev)
-        self.slots = [_Slot(rows, rows * self.world, bank.d, bank.n_classes, dev, self.world > 1)
-                      for _ in range(depth)]
+        # Bank sharded over several GPUs with the peer exchange: the query conversion kernel replicates this rank's
+        # rows into every rank's query buffer over NVLink (dist.PeerQueries); otherwise the fp32 rows are
+        # all-gathered with NCCL and every rank converts the whole batch.
+        self.peer_queries = None
+        if self.world > 1 and self.sharded.peer is not None and depth <= 2:
+            from .dist import PeerQueries
+
+            self.peer_queries = PeerQueries(bank, rows * self.world, group)
+        self.slots = [_Slot(rows, rows * self.world, bank.d, bank.n_classes, dev,
+                            self.world > 1 and self.peer_queries is None) for _ in range(depth)]
         self.next = 0
 
     def submit(self, q_host: torch.Tensor) -> int:
@@ -66,13 +76,20 @@ class FullModePredictor:
         compute = torch.cuda.current_stream(self.bank.device)
         # The slot's previous use was retired by result() (d2h_done implies its compute finished), so the upload
         # may start right away and overlap the forward of the batch submitted before this one.
+        prepared = None
         with torch.cuda.stream(self.copy_stream):
             slot.q_slice.copy_(q_host, non_blocking=True)
-            if self.world > 1:  # replicate the queries over NVLink on the copy stream too (overlaps the forward)
+            # replicate the queries over NVLink on the copy stream too (overlaps the forward of the previous batch)
+            if self.peer_queries is not None:
+                prepared = self.peer_queries.replicate(slot.q_slice, self.rows * self.world)
+            elif self.world > 1:
                 dist.all_gather_into_tensor(slot.q_full, slot.q_slice, group=self.group)
             slot.h2d_done.record(self.copy_stream)
         compute.wait_event(slot.h2d_done)
-        mine = self.sharded.class_lse_rows(slot.q_full, self.scale)  # this rank's rows of the merged table
+        if prepared is not None:
+            mine = self.sharded.class_lse_rows_prepared(*prepared, self.scale)
+        else:
+            mine = self.sharded.class_lse_rows(slot.q_full, self.scale)  # this rank's rows of the merged table
         logp_from_class_lse(mine, out=slot.logp)
         slot.compute_done.record(compute)
         self.out_stream.wait_event(slot.compute_done)

@@ -37,7 +37,7 @@ def test_train_py_style_caller_runs_unmodified(cuda_lib):
     device = "cuda:0"
     torch.manual_seed(0)
     np.random.seed(0)
-    train_dataset, val_dataset = Blobs(240, 6, 1), Blobs(48, 6, 2)
+    train_dataset, val_dataset = Blobs(360, 12, 1), Blobs(48, 12, 2)
     train_loader = torch.utils.data.DataLoader(train_dataset, batch_size=8, shuffle=True)
     val_loader = torch.utils.data.DataLoader(val_dataset, batch_size=8, shuffle=False)
     num_classes = train_dataset.num_classes
@@ -51,7 +51,7 @@ def test_train_py_style_caller_runs_unmodified(cuda_lib):
                     proj_dim=0,
                     kernel_type='euclidean',
                     n_shot=1,
-                    n_way=4,
+                    n_way=10,
                     debug_mode=False)
     network.to(device)
     criterion = torch.nn.NLLLoss()
@@ -123,7 +123,7 @@ def test_predict_is_differentiable_like_the_reference(cuda_lib):
     np.random.seed(1)
     ds = Blobs(120, 6, 3)
     featurizer = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(192, 16), torch.nn.ReLU())
-    network = NWNet(featurizer, 6, support_dataset=ds, feat_dim=16, n_shot=1, n_way=4).to(device)
+    network = NWNet(featurizer, 6, support_dataset=ds, feat_dim=16, n_shot=1, n_way=6).to(device)
     network.eval()
     network.precompute()
     img = ds.x[:8].to(device)

@@ -300,6 +300,22 @@ NW_API size_t nw_rank_rows_workspace_bytes(int n_rows, int64_t n_cols);
 NW_API int nw_rank_rows(const float* scores, int n_rows, int64_t n_cols, int64_t k, int64_t* idx_out, void* workspace,
                  size_t workspace_bytes, void* stream);
 
+/* Exact top-k refinement — the device side of SupportBank.topk_exact (exact k nearest supports without the (B, N)
+ * score matrix; same ranking as NWNet.get_neighbors' dense fp32 path, nwhead/nw.py:245-249, ties by ascending
+ * source index).  For every query b that is not yet done: the rows of its m best 64-row bank blocks
+ * (block_order[b, 0..m), ranked by the NW_EMIT_BLOCK_BEST pass) are gathered from the fp32 source rows (through
+ * perm: bank row -> source row, NULL = identity), scored exactly (the per-pair arithmetic of nw_direct_scores),
+ * ranked, and the query is certified: with beta = block_best_sorted[b, m] (pass score of the best block left out),
+ * no row outside the candidates can reach the exact k-th candidate score (bounds from q_sqnorm, the measured
+ * rounding residuals resid_q / *resid_max and *smax_sq = max squared norm of the bank rows).  Certified queries get
+ * idx_out[b, 0..k) (source indices, best first) and done[b] = 1; the others add 1 to *n_pending.  One launch, no
+ * host synchronisation.  m <= 64, k <= 64 m; order_stride = entries per query in block_order / block_best_sorted. */
+NW_API int nw_topk_refine(const float* q, int n_query, int d, const float* source_rows, int64_t n_rows,
+                   const int64_t* perm, const int64_t* block_order, const float* block_best_sorted, int order_stride,
+                   int m, int64_t n_blocks, int k, const float* q_sqnorm, const float* resid_q, const float* smax_sq,
+                   const float* resid_max, int precision, int32_t* done, int64_t* idx_out, int32_t* n_pending,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

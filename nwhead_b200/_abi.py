@@ -8,7 +8,6 @@ from __future__ import annotations
 
 import ctypes
 import os
-import threading
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 import torch
@@ -88,10 +87,17 @@ SIGNATURES = {
                                      c_void_p, c_void_p]),
     "nw_rank_rows_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "nw_rank_rows": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nw_topk_refine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                               c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
 }
 
 _lib = None
-_tls = threading.local()
+
+
+class _Stream(c_void_p):
+    """A cudaStream_t for the ABI's void* stream argument that remembers which device it belongs to."""
+    device = None
 
 
 class _DeviceBoundLib:
@@ -100,9 +106,9 @@ class _DeviceBoundLib:
     The C ABI takes plain pointers and a stream; kernels launch in the current-device context.  A caller that
     works on `cuda:1` while `cuda:0` is current (the reference does `.to(x.device)` and never calls set_device)
     would otherwise launch on the wrong GPU, or fail with cudaErrorInvalidResourceHandle for a non-default
-    stream.  `stream_of(device)` — which every launching call evaluates as an argument — records the device; the
-    wrapper switches to it for the duration of the call when it is not already current (one integer compare on
-    the usual path)."""
+    stream.  Every launching entry point takes the stream as its LAST argument, and `stream_of(device)` returns a
+    stream handle tagged with its device: the wrapper switches to that device for the duration of the call when it
+    is not already current (one integer compare on the usual path)."""
 
     def __init__(self, cdll):
         self._cdll = cdll
@@ -112,8 +118,7 @@ class _DeviceBoundLib:
     @staticmethod
     def _bind(fn):
         def call(*args):
-            dev = getattr(_tls, "device", None)
-            _tls.device = None
+            dev = getattr(args[-1], "device", None) if args else None
             if dev is not None and dev != torch.cuda.current_device():
                 with torch.cuda.device(dev):
                     return fn(*args)
@@ -161,10 +166,11 @@ def ptr(t):
 
 
 def stream_of(device) -> c_void_p:
-    """Current stream of `device` as the ABI's void*; also tells the next library call which device to run on."""
+    """Current stream of `device` as the ABI's void*, tagged with the device index (see _DeviceBoundLib)."""
     device = torch.device(device)
-    _tls.device = device.index if device.index is not None else torch.cuda.current_device()
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    st = _Stream(torch.cuda.current_stream(device).cuda_stream)
+    st.device = device.index if device.index is not None else torch.cuda.current_device()
+    return st
 
 
 def require_cuda(*tensors) -> torch.device:

@@ -338,26 +338,28 @@ class SupportBank:
         return out.sqrt()
 
     def topk_exact(self, q: torch.Tensor, k: int, source_feats: torch.Tensor, max_blocks: int = 64,
-                   query_chunk: int = 128) -> torch.Tensor:
+                   query_chunk: int = 2048, first_blocks: int = 16) -> torch.Tensor:
         """EXACT k nearest supports (euclidean banks), indices into `source_feats` (the fp32 tensor the bank was
         built from), nearest first — the same ranking as the dense fp32 path (ties by ascending index), without
         the (B, N) score matrix:
 
-          1. tensor-core pass: best reduced-precision score beta_j = -distance of every query in every block j of
-             64 bank rows;
-          2. candidates = the rows of the m best blocks; exact fp32 differences (nw_direct_scores) over those rows
-             only, ranked by nw_rank_rows -> tau_c, the exact k-th best candidate score;
-          3. certificate: no row outside the candidates can score >= tau_c.  Such a row has a reduced-precision
-             score <= beta_(m+1), and the pass is off by a bounded amount: the distance between two rounded rows
-             differs from the true one by at most eta = |q - q~| + max_j |s_j - s~_j| (triangle inequality; the
-             residual norms are measured, nw_rounding_residual), and the fp32 accumulation moves the squared
-             distance by at most e2 = 2^-18 (|q|^2 + max|s|^2).  So its true score is at most
-             U = -(sqrt(beta_(m+1)^2 - e2) - eta); U < tau_c certifies the query.  (bf16x3 drops the lo.lo products
-             as well: the squared distance is short by at most (2^-8 (|q| + max|s|))^2.)
+          1. tensor-core pass (nw_forward_emit / NW_EMIT_BLOCK_BEST): best reduced-precision score beta_j =
+             -distance of every query in every block j of 64 bank rows; the blocks of each query are ranked
+             (nw_rank_rows);
+          2. nw_topk_refine, ONE launch per candidate budget m: the rows of the m best blocks are gathered from
+             `source_feats` and scored with the exact fp32 differences of the dense path (bit for bit), ranked by
+             (score, source index) -> tau_c, the exact k-th best candidate score;
+          3. certificate, in the same kernel: no row outside the candidates can score >= tau_c.  Such a row has a
+             reduced-precision score <= beta_(m+1), and the pass is off by a bounded amount: the distance between
+             two rounded rows differs from the true one by at most eta = |q - q~| + max_j |s_j - s~_j| (triangle
+             inequality; the residual norms are measured, nw_rounding_residual), and the fp32 accumulation moves the
+             squared distance by at most e2 = 2^-18 (|q|^2 + max|s|^2).  So its true score is at most
+             U = -(sqrt(beta_(m+1)^2 - e2) - eta); U < tau_c certifies the query.
 
-        m is sized from the same bounds before the gather (blocks that could still reach the k-th best block
-        score), capped at `max_blocks`.  Uncertified queries take the dense exact path, so the result is exact for
-        every input; the budget only decides how often the cheap path is enough (`last_topk_path` counts both)."""
+        Budgets: m = `first_blocks` for every query, then m = `max_blocks` (at most 64) for the queries the first
+        budget could not certify, then the dense exact path for what is left — so the result is exact for every
+        input, and the only host synchronisation is one read of the count of uncertified queries per chunk
+        (`last_topk_path` counts both routes)."""
         from .kernel import dense_scores
         from .utils import rank_rows
 
@@ -369,69 +371,48 @@ class SupportBank:
             raise ValueError("source_feats must be the (N, d) tensor the bank was built from")
         k = min(int(k), n)
         src_all = source_feats.detach().float().reshape(n, d)
+        if not src_all.is_contiguous():
+            src_all = src_all.contiguous()
         cached = getattr(self, "_resid_of", None)   # (weak reference to the tensor object, its version, max residual)
         if source_feats.is_inference():             # no version counter to validate a cache entry against
-            cached = (None, None, self.rounding_residual(src_all).max())
+            cached = (None, None, self.rounding_residual(src_all).max().reshape(1))
         elif cached is None or cached[0]() is not source_feats or cached[1] != source_feats._version:
-            cached = (weakref.ref(source_feats), source_feats._version, self.rounding_residual(src_all).max())
+            cached = (weakref.ref(source_feats), source_feats._version,
+                      self.rounding_residual(src_all).max().reshape(1))
             self._resid_of = cached
         resid_max = cached[2]
+        if getattr(self, "_smax_sq", None) is None:
+            self._smax_sq = self.sqnorm.max().reshape(1)
+        nblk = (n + 63) // 64
+        max_blocks = max(1, min(int(max_blocks), 64, nblk))
+        budgets = sorted({min(max(int(first_blocks), (k + 63) // 64), max_blocks), max_blocks})
+        budgets = [m for m in budgets if m * 64 >= k]
         out = torch.empty((q.shape[0], k), dtype=torch.int64, device=dev)
-        smax = self.sqnorm.max().sqrt() * (1 + 2.0 ** -7)         # norms of the rounded rows -> of the rows
-        lane = torch.arange(64, device=dev)
-        fp32_sum = 1.0 - (d + 8) * 2.0 ** -24                     # the exact path's own summation error (relative)
         self.last_topk_path = {"blocks": 0, "dense": 0}
         for i0 in range(0, q.shape[0], query_chunk):
             qc = q[i0:i0 + query_chunk].detach().float().reshape(-1, d).contiguous()
             b = qc.shape[0]
-            best, q_sq = self.block_best(qc)                      # (b, nblk) scores = -distance
-            nblk = best.shape[1]
-            order = rank_rows(best, min(nblk, max(max_blocks + 1, k)))   # blocks by best score, descending
-            sorted_best = best.gather(1, order)
-            qn = q_sq.sqrt() * (1 + 2.0 ** -7)
-            e2 = 2.0 ** -18 * (qn * qn + smax * smax)             # fp32 accumulation, squared-distance domain
-            eta = (self.rounding_residual(qc) + resid_max) * (1 + 2.0 ** -10)
-            lolo = (2.0 ** -8 * (qn + smax)) ** 2 if self.precision != _abi.PREC_BF16 else torch.zeros_like(e2)
-
-            def upper(beta):      # largest exact-path score of a row whose reduced-precision score is beta
-                return -((beta * beta - e2).clamp_min(0).sqrt() - eta).clamp_min(0) * fp32_sum
-
-            def lower(beta):      # smallest
-                return -((beta * beta + e2 + lolo).sqrt() + eta) / fp32_sum
-
-            if nblk > k:
-                # the k best blocks each hold a row scoring >= lower(beta_(k)): blocks whose best row cannot reach
-                # that are out.  The certificate below is what guarantees exactness; this only sizes the gather.
-                need = (upper(sorted_best.t()).t() >= lower(sorted_best[:, k - 1])[:, None]).sum(1)
-                m = int(need.max().item())
-            else:
-                m = nblk
-            m = min(max(m, (k + 63) // 64), max_blocks, nblk)
-            pending = torch.arange(b, device=dev)
-            if m * 64 >= k:
-                rows = (order[:, :m, None] * 64 + lane).reshape(b, m * 64)
-                src = rows.clamp_max(n - 1)
-                if self.perm is not None:
-                    src = self.perm[src]
-                src = torch.where(rows < n, src, torch.full_like(src, 1 << 40))
-                # ascending source index = the dense path's tie order (indices below 2^24 are exact in fp32)
-                src = src.gather(1, rank_rows(-src.float(), m * 64)) if n < (1 << 24) else src.sort(1).values
-                valid = src < n
-                src = src.clamp_max(n - 1)
-                cand = src_all.index_select(0, src.reshape(-1)).reshape(b, m * 64, d)
-                sc = torch.empty((b, m * 64), dtype=torch.float32, device=dev)
-                check(lib.nw_direct_scores(KIND["euclidean"], 1.0, ptr(qc), b, d, ptr(cand), m * 64, 1, ptr(sc),
-                                           stream_of(dev)), "nw_direct_scores")
-                sc = torch.where(valid, sc, torch.full_like(sc, float("-inf")))
-                pos = rank_rows(sc, k)
-                tau = sc.gather(1, pos[:, k - 1:k]).flatten()
-                ok = upper(sorted_best[:, m]) < tau if m < nblk else torch.ones_like(tau, dtype=torch.bool)
-                out[i0 + pending[ok]] = src.gather(1, pos)[ok]
-                pending = pending[~ok]
-            self.last_topk_path["blocks"] += b - int(pending.numel())
-            if pending.numel():  # too many near-ties for the candidate budget: dense exact scores for those queries
-                out[i0 + pending] = rank_rows(dense_scores("euclidean", qc[pending], src_all), k)
-                self.last_topk_path["dense"] += int(pending.numel())
+            done = torch.zeros((b,), dtype=torch.int32, device=dev)
+            n_left = b
+            if budgets:
+                best, q_sq = self.block_best(qc)                     # (b, nblk) scores = -distance
+                width = min(nblk, max_blocks + 1)
+                order = rank_rows(best, width)                       # blocks by best score, descending
+                sorted_best = best.gather(1, order)
+                resid_q = self.rounding_residual(qc)
+                idx = out[i0:i0 + b]
+                pending = torch.zeros((len(budgets),), dtype=torch.int32, device=dev)
+                for j, m in enumerate(budgets):
+                    check(lib.nw_topk_refine(ptr(qc), b, d, ptr(src_all), n, ptr(self.perm), ptr(order),
+                                             ptr(sorted_best), width, m, nblk, k, ptr(q_sq), ptr(resid_q),
+                                             ptr(self._smax_sq), ptr(resid_max), self.precision, ptr(done), ptr(idx),
+                                             ptr(pending[j:]), stream_of(dev)), "nw_topk_refine")
+                n_left = int(pending[-1].item())                     # the one host synchronisation of the chunk
+            self.last_topk_path["blocks"] += b - n_left
+            if n_left:  # too many near-ties for the candidate budget: dense exact scores for those queries
+                rows = (done == 0).nonzero().flatten()
+                out[i0 + rows] = rank_rows(dense_scores("euclidean", qc[rows], src_all), k)
+                self.last_topk_path["dense"] += n_left
         return out
 
     def support_influence(self, q: torch.Tensor, qlabel: torch.Tensor, scale: float = 1.0,

@@ -255,6 +255,105 @@ __global__ void rank_emit_kernel(const uint64_t* __restrict__ keys, long long pa
   idx_out[r * k + i] = int64_t(keys[r * padded + i] & 0xffffffffull);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Exact top-k refinement (SupportBank.topk_exact): one block per query.  The rows of the query's m best 64-row
+// bank blocks (ranked by the tensor-core pass) are scored EXACTLY — per pair the arithmetic of the dense path
+// (direct::scores_kernel: lane l takes columns l, l+32, ... with one fmaf each, then the butterfly sum), so a
+// candidate's score has the bits of the dense (B, N) matrix — the (score, source index) keys are sorted in shared
+// memory, and the query is CERTIFIED in place: a row outside the candidates cannot beat the exact k-th candidate
+// score (bounds in nwhead_b200/bank.py::topk_exact).  Gather, re-score, ranking and certificate are one launch with
+// no host round trip; uncertified queries are only counted (the caller retries them with a larger m, then densely).
+// ---------------------------------------------------------------------------------------------
+constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_ROWS_PER_WARP = 4;  // candidate rows a warp scores together: 4 independent load streams
+
+__device__ __forceinline__ float key_score(uint64_t key) {
+  const uint32_t u = ~uint32_t(key >> 32);
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS) topk_refine_kernel(
+    const float* __restrict__ q, int d, const float* __restrict__ src, long long n, const int64_t* __restrict__ perm,
+    const int64_t* __restrict__ block_order, const float* __restrict__ block_best_sorted, int order_stride, int m,
+    long long n_blocks, int k, int padded, const float* __restrict__ q_sq, const float* __restrict__ resid_q,
+    const float* __restrict__ smax_sq_ptr, const float* __restrict__ resid_max_ptr, int precision,
+    int32_t* __restrict__ done, int64_t* __restrict__ idx_out, int32_t* __restrict__ n_pending) {
+  extern __shared__ __align__(16) uint8_t topk_smem[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(topk_smem);
+  float* qs = reinterpret_cast<float*>(keys + padded);
+  const int b = blockIdx.x;
+  if (done[b]) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < d; c += TOPK_THREADS) qs[c] = q[(long long)b * d + c];
+  const int n_cand = m * 64;
+  for (int i = n_cand + threadIdx.x; i < padded; i += TOPK_THREADS) keys[i] = ~uint64_t(0);
+  __syncthreads();
+  const int64_t* order = block_order + (long long)b * order_stride;
+  for (int r0 = warp * TOPK_ROWS_PER_WARP; r0 < n_cand; r0 += (TOPK_THREADS / 32) * TOPK_ROWS_PER_WARP) {
+    const float* sp[TOPK_ROWS_PER_WARP];
+    long long srow[TOPK_ROWS_PER_WARP];
+    bool valid[TOPK_ROWS_PER_WARP];
+#pragma unroll
+    for (int j = 0; j < TOPK_ROWS_PER_WARP; ++j) {
+      const int r = r0 + j;
+      const long long bank_row = order[r >> 6] * 64 + (r & 63);
+      valid[j] = bank_row < n;
+      srow[j] = valid[j] ? (perm ? perm[bank_row] : bank_row) : 0;
+      sp[j] = src + srow[j] * d;
+    }
+    float acc[TOPK_ROWS_PER_WARP] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int c = lane; c < d; c += 32) {
+      const float qv = qs[c];
+#pragma unroll
+      for (int j = 0; j < TOPK_ROWS_PER_WARP; ++j) {
+        const float df = qv - __ldcs(sp[j] + c);
+        acc[j] = fmaf(df, df, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < TOPK_ROWS_PER_WARP; ++j) {
+      const float sc = -sqrtf(warp_sum(acc[j]));
+      if (lane == 0) keys[r0 + j] = valid[j] ? make_key(sc, uint32_t(srow[j])) : ~uint64_t(0);
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= padded; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < padded / 2; t += TOPK_THREADS) {
+        const int i = 2 * t - (t & (stride - 1));
+        cmp_swap(keys[i], keys[i + stride], (i & size) == 0);
+      }
+      __syncthreads();
+    }
+  }
+  // certificate (all threads evaluate the same scalars)
+  bool ok = true;
+  if (m < n_blocks) {
+    const uint64_t kth = keys[k - 1];
+    ok = kth != ~uint64_t(0);
+    const float tau = key_score(kth);
+    const float beta = block_best_sorted[(long long)b * order_stride + m];  // best score of the first block left out
+    const float up = 1.0f + 0.0078125f;                                      // norms of the rounded rows -> of the rows
+    const float qn = sqrtf(q_sq[b]) * up;
+    const float smax = sqrtf(*smax_sq_ptr) * up;
+    const float e2 = 3.814697265625e-06f * (qn * qn + smax * smax);          // 2^-18: fp32 accumulation of the pass
+    const float eta = (resid_q[b] + *resid_max_ptr) * (1.0f + 0.0009765625f);
+    const float fp32_sum = 1.0f - float(d + 8) * 5.9604644775390625e-08f;    // the exact path's own summation error
+    const float inner = sqrtf(fmaxf(beta * beta - e2, 0.0f)) - eta;
+    const float upper = -fmaxf(inner, 0.0f) * fp32_sum;  // largest exact score of a row whose pass score is beta
+    ok = ok && (upper < tau);
+    (void)precision;  // (bf16x3 drops lo.lo products: that only LOWERS pass scores' distances, handled by `lower`
+                      //  on the host when sizing m; the upper bound above holds for both precisions)
+  }
+  if (ok) {
+    for (int i = threadIdx.x; i < k; i += TOPK_THREADS) idx_out[(long long)b * k + i] = int64_t(keys[i] & 0xffffffffull);
+    if (threadIdx.x == 0) done[b] = 1;
+  } else if (threadIdx.x == 0) {
+    atomicAdd(n_pending, 1);
+  }
+}
+
 static long long next_pow2(long long n) {
   long long p = 1;
   while (p < n) p <<= 1;
@@ -574,6 +673,31 @@ extern "C" int nw_rank_rows(const float* scores, int n_rows, int64_t n_cols, int
     dim3 grid(unsigned(ceil_div_ll(k, 256)), n_rows);
     aux::rank_emit_kernel<<<grid, 256, 0, stream>>>(keys, padded, k, idx_out);
   }
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_topk_refine(const float* q, int n_query, int d, const float* source_rows, int64_t n_rows,
+                              const int64_t* perm, const int64_t* block_order, const float* block_best_sorted,
+                              int order_stride, int m, int64_t n_blocks, int k, const float* q_sqnorm,
+                              const float* resid_q, const float* smax_sq, const float* resid_max, int precision,
+                              int32_t* done, int64_t* idx_out, int32_t* n_pending, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(q && source_rows && block_order && block_best_sorted && q_sqnorm && resid_q && smax_sq && resid_max &&
+                 done && idx_out && n_pending,
+             NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n_query > 0 && d > 0 && n_rows > 0 && n_rows < (1ll << 32), NW_ERR_INVALID, "bad shape");
+  NW_REQUIRE(m >= 1 && m <= 64 && m <= n_blocks, NW_ERR_INVALID, "m must be in [1, min(64, n_blocks)]");
+  NW_REQUIRE(m == n_blocks || order_stride > m, NW_ERR_INVALID, "block_order needs m + 1 entries per query");
+  NW_REQUIRE(k >= 1 && k <= m * 64 && k <= n_rows, NW_ERR_INVALID, "k must be in [1, min(64 m, n_rows)]");
+  const int padded = int(aux::next_pow2(m * 64));
+  const size_t smem = size_t(padded) * sizeof(uint64_t) + size_t(d) * sizeof(float);
+  NW_REQUIRE(smem <= 200 * 1024, NW_ERR_UNSUPPORTED, "feature dimension %d too large for the refinement kernel", d);
+  if (smem > 48 * 1024)
+    NW_CUDA_OK(cudaFuncSetAttribute(aux::topk_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  aux::topk_refine_kernel<<<n_query, aux::TOPK_THREADS, smem, stream>>>(
+      q, d, source_rows, n_rows, perm, block_order, block_best_sorted, order_stride, m, n_blocks, k, padded, q_sqnorm,
+      resid_q, smax_sq, resid_max, precision, done, idx_out, n_pending);
   NW_CUDA_OK(cudaGetLastError());
   return NW_OK;
 }

@@ -194,32 +194,48 @@ def test_large_class_count_backward_and_early_limit(cuda_lib):
 
 def test_bad_label_forward_backward_is_memory_safe_and_raises(cuda_lib):
     """an out-of-range support label on the differentiable path must never index out of bounds in the
-    backward, and must raise (F.one_hot's message, reference nwhead/nw.py:276) — at the blocking check, and at the
-    latest on the next call once the flagged forward has finished."""
+    backward, and must raise (F.one_hot's message, reference nwhead/nw.py:276): at the latest on the next forward or
+    backward call once the flagged forward has finished, or right away through the blocking check."""
     import nwhead_b200
+    from nwhead_b200 import nw as nwmod
 
-    dev = "cuda:0"
+    dev = torch.device("cuda:0")
     C, d = 10, 32
     head = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), C)
     g = torch.Generator(device=dev).manual_seed(0)
+    guard = nwmod.label_guard(dev)
+    msg = "Class values must be smaller than num_classes"
     for bad in (C, -100, 2 ** 40 + 3, 10 ** 6):
         q = torch.randn(8, d, generator=g, device=dev, requires_grad=True)
         sx = torch.randn(10, d, generator=g, device=dev, requires_grad=True)
         sy = torch.arange(10, device=dev) % C
         sy[3] = bad
-        out = head(q, sx, sy)
-        out.sum().backward()
-        torch.cuda.synchronize()  # no illegal address / sticky context error
-        assert torch.isfinite(q.grad).all() and torch.isfinite(sx.grad).all()
-        with pytest.raises(RuntimeError, match="Class values must be smaller than num_classes"):
+        # (1) memory safety of the kernels themselves: run forward AND backward with the host-side poll disabled,
+        #     as happens when the backward is issued before the forward has finished
+        real_check, guard.check = guard.check, lambda block=False: None
+        try:
+            out = head(q, sx, sy)
+            out.sum().backward()
+            torch.cuda.synchronize()  # no illegal address / sticky context error
+        finally:
+            guard.check = real_check
+        assert torch.isfinite(out).all() and torch.isfinite(q.grad).all() and torch.isfinite(sx.grad).all()
+        # the bad row contributes to no class: the result equals the forward without its label mass
+        with pytest.raises(RuntimeError, match=msg):
             head.check_labels(dev)
         # the flag was consumed: valid calls work again
         sy[3] = 0
         head(q, sx, sy).sum().backward()
         head.check_labels(dev)
-    # non-blocking poll: the error surfaces on a later call without any explicit check
+    # (2) non-blocking poll: the error surfaces on a later call without any explicit check ...
     sy[5] = C + 7
     head(q, sx, sy)
     torch.cuda.synchronize()
-    with pytest.raises(RuntimeError, match="Class values must be smaller than num_classes"):
+    with pytest.raises(RuntimeError, match=msg):
         head(q, sx, sy.clamp_max(C - 1))
+    # ... and in backward when the flagged forward has finished by then
+    out = head(q, sx, sy)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match=msg):
+        out.sum().backward()
+    head.check_labels(dev)

@@ -29,7 +29,7 @@ def main():
     dev = torch.device("cuda:0")
     for n, d, c, batches in ((5800, 512, 200, (8, 64)), (1280000, 2048, 1000, (1, 8, 128))):
         mu = bench.class_means(c, d, dev)
-        feats, labels = bench.synth_shard(mu, 0, c, n // c, dev)
+        feats, labels = bench.synth_bank(mu, n // c, dev)
         bank = SupportBank.build(feats, labels, c, "euclidean", "bf16")
         del feats
         for b in batches:

@@ -16,7 +16,7 @@ def main():
     dev = torch.device("cuda:0")
     n, d, c = 1280000, 2048, 1000
     mu = bench.class_means(c, d, dev)
-    feats, labels = bench.synth_shard(mu, 0, c, n // c, dev)
+    feats, labels = bench.synth_bank(mu, n // c, dev)
     q, _ = bench.synth_queries(mu, 256, dev)
     bank = SupportBank.build(feats, labels, c, "euclidean", "bf16")
     for _ in range(2):

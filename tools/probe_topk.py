@@ -23,7 +23,7 @@ def main():
     dev = torch.device("cuda:0")
     n_classes = 1000
     mu = bench.class_means(n_classes, d, dev)
-    feats, labels = bench.synth_shard(mu, 0, n_classes, n // n_classes, dev)
+    feats, labels = bench.synth_bank(mu, n // n_classes, dev)
     q, _ = bench.synth_queries(mu, b, dev)
     for prec in ("bf16", "bf16x3"):
         bank = SupportBank.build(feats, labels, n_classes, "euclidean", prec)

@@ -17,7 +17,7 @@ def main():
     n, d, c = 1280000, 2048, 1000
     peaks = bench.measured_peaks()
     mu = bench.class_means(c, d, dev)
-    feats, labels = bench.synth_shard(mu, 0, c, n // c, dev)
+    feats, labels = bench.synth_bank(mu, n // c, dev)
     bank = SupportBank.build(feats, labels, c, "euclidean", "bf16")
     del feats
     out = []

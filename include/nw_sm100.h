@@ -140,10 +140,16 @@ typedef struct nw_forward_plan_t {
   int tiles_per_chunk; /* support tiles per chunk */
   int grid;            /* persistent CTAs launched */
   int cta_pair;        /* 1: CTA pairs (cluster of 2, tcgen05 cta_group::2, 256x256 tiles); 0: single CTAs */
-  int64_t side_elems;  /* floats of scratch `side` required: chunks * B * 4 */
+  int64_t side_elems;  /* floats of scratch `side` required: chunks * B * 8 */
 } nw_forward_plan_t;
 
 NW_API int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t* plan_out);
+
+/* Epilogue warp sets the class-LSE forward prefers for rows of row_elems bf16 (1, 2 or 4): short GEMMs are bound by
+ * the epilogue's two MUFU operations per score, so several independent sets of 4 epilogue warps share a tile, each
+ * with its own class-LSE table.  The caller offers room for the further tables by passing
+ * side_elems >= plan.side_elems + (sets - 1) * n_query * n_classes; with less, fewer sets run (same results). */
+NW_API int nw_forward_epilogue_sets(int row_elems);
 
 /* Measurement hook (bench.py `sustained.sm_mhz_in_kernel`; no reference counterpart).  While a buffer is set, every
  * fused-forward launch whose grid fits ADDS, per CTA i, the SM cycles (clock64) and the nanoseconds (globaltimer)
@@ -155,9 +161,10 @@ NW_API int nw_forward_set_clock_probe(void* buf_u64, int64_t capacity_ctas);
 /* class_lse[b, c] = log sum_{j : labels[j] == c} exp(score(b, j)); -inf for classes with no support
  * row in this bank (or bank shard).  Inputs are the bf16 layouts of nw_rows_to_bf16.
  * labels must be class-sorted int32.  q_sqnorm / s_sqnorm are only read for NW_EPI_EUCLID.
- * side: scratch of at least plan.side_elems floats.  When row_elems <= 1024 and side has room for another
- * n_query * n_classes floats, the kernel runs two independent epilogue warp sets (each with its own table, the
- * second one placed in `side`) and combines them afterwards — short GEMMs are otherwise epilogue-bound. */
+ * side: scratch of at least plan.side_elems floats.  With room for (sets - 1) * n_query * n_classes more floats
+ * (sets = nw_forward_epilogue_sets(row_elems)) the kernel runs that many independent epilogue warp sets (each with
+ * its own table, the further ones placed in `side`) and combines them afterwards — short GEMMs are otherwise
+ * epilogue-bound. */
 NW_API int nw_forward_class_lse(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
                          const void* bank_bf16, const float* s_sqnorm, const int32_t* labels, int64_t n_support,
                          int row_elems, int n_classes, float* class_lse, float* side, int64_t side_elems,
@@ -275,6 +282,23 @@ NW_API int nw_kmeans_assign(const float* rows, int d, int64_t ld, const int32_t*
                      int64_t n_rows, const float* centroids, int k, int32_t* assign_out, float* dist_out,
                      void* stream);
 
+/* k-means++ seeding with scikit-learn's arithmetic, for all classes at once (compute_clusters with n_clusters > 1,
+ * nwhead/utils.py:230 -> sklearn KMeans(random_state=0): _kmeans_plusplus).
+ * nw_kmeans_seed_dist: dist_out[t, i] = squared distance of row i to candidate row cand_rows[group[i], t] of its own
+ *   class, evaluated like sklearn: both rows centred with the class mean in float32 (X -= X.mean(0)), the squared
+ *   distance accumulated in float64, rounded to float32 and clipped at 0 (_euclidean_distances_upcast).
+ *   class_mean (n_groups, d); cand_rows (n_groups, n_cand) int64 row indices; dist_out (n_cand, n_rows); order as in
+ *   nw_kmeans_assign; n_cand <= 8.
+ * nw_kmeans_seed_pick: pos_out[c, t] = row at the first class-sorted position of class c whose running float32 sum
+ *   of closest[] (sequential, numpy's cumsum) reaches targets[c, t] (float64) — np.searchsorted(np.cumsum(...), v),
+ *   clipped to the class's last row.  offsets (n_classes + 1) class-sorted positions; order maps positions to rows
+ *   (NULL = identity); n_targets <= 8. */
+NW_API int nw_kmeans_seed_dist(const float* rows, int d, int64_t ld, const int32_t* group, const int64_t* order,
+                        int64_t n_rows, const float* class_mean, const int64_t* cand_rows, int n_cand,
+                        float* dist_out, void* stream);
+NW_API int nw_kmeans_seed_pick(const float* closest, const int64_t* order, const int32_t* offsets, int n_classes,
+                        const double* targets, int n_targets, int64_t* pos_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * support_influence (K4) — replaces the per-query Python loop of util/metric.py:23-50.
  * ------------------------------------------------------------------------------------------ */
@@ -302,17 +326,19 @@ NW_API int nw_rank_rows(const float* scores, int n_rows, int64_t n_cols, int64_t
 
 /* Exact top-k refinement — the device side of SupportBank.topk_exact (exact k nearest supports without the (B, N)
  * score matrix; same ranking as NWNet.get_neighbors' dense fp32 path, nwhead/nw.py:245-249, ties by ascending
- * source index).  For every query b that is not yet done: the rows of its m best 64-row bank blocks
- * (block_order[b, 0..m), ranked by the NW_EMIT_BLOCK_BEST pass) are gathered from the fp32 source rows (through
- * perm: bank row -> source row, NULL = identity), scored exactly (the per-pair arithmetic of nw_direct_scores),
- * ranked, and the query is certified: with beta = block_best_sorted[b, m] (pass score of the best block left out),
- * no row outside the candidates can reach the exact k-th candidate score (bounds from q_sqnorm, the measured
- * rounding residuals resid_q / *resid_max and *smax_sq = max squared norm of the bank rows).  Certified queries get
- * idx_out[b, 0..k) (source indices, best first) and done[b] = 1; the others add 1 to *n_pending.  One launch, no
- * host synchronisation.  m <= 64, k <= 64 m; order_stride = entries per query in block_order / block_best_sorted. */
+ * source index).  For every query b that is not yet done: a candidate budget m <= m_cap is sized from the error
+ * bounds of the reduced-precision pass, the rows of its m best 64-row bank blocks (block_order[b, 0..m), ranked by the
+ * NW_EMIT_BLOCK_BEST pass) are gathered from the fp32 source rows (through perm: bank row -> source row, NULL =
+ * identity), scored exactly (the per-pair arithmetic of nw_direct_scores), ranked, and the query is certified: with
+ * beta = block_best_sorted[b, m] (pass score of the best block left out), no row outside the candidates can reach
+ * the exact k-th candidate score (bounds from q_sqnorm, the measured rounding residuals resid_q / *resid_max and
+ * *smax_sq = max squared norm of the bank rows).  Certified queries get idx_out[b, 0..k) (source indices, best
+ * first) and done[b] = 1; the others add 1 to *n_pending.  One launch, no host synchronisation.
+ * m_cap <= 64, k <= 64 m_cap; order_stride = entries per query in block_order / block_best_sorted (> m_cap unless
+ * m_cap == n_blocks; >= k lets the kernel size m below m_cap). */
 NW_API int nw_topk_refine(const float* q, int n_query, int d, const float* source_rows, int64_t n_rows,
                    const int64_t* perm, const int64_t* block_order, const float* block_best_sorted, int order_stride,
-                   int m, int64_t n_blocks, int k, const float* q_sqnorm, const float* resid_q, const float* smax_sq,
+                   int m_cap, int64_t n_blocks, int k, const float* q_sqnorm, const float* resid_q, const float* smax_sq,
                    const float* resid_max, int precision, int32_t* done, int64_t* idx_out, int32_t* n_pending,
                    void* stream);
 

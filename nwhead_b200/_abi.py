@@ -57,6 +57,7 @@ SIGNATURES = {
     "nw_rounding_residual": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "nw_forward_plan": (c_int, [c_int, c_int64, POINTER(ForwardPlan)]),
     "nw_forward_set_clock_probe": (c_int, [c_void_p, c_int64]),
+    "nw_forward_epilogue_sets": (c_int, [c_int]),
     "nw_forward_class_lse": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                      c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "nw_forward_class_lse_peers": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
@@ -82,6 +83,9 @@ SIGNATURES = {
                                    c_size_t, c_void_p]),
     "nw_kmeans_assign": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p,
                                  c_void_p, c_void_p]),
+    "nw_kmeans_seed_dist": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int,
+                                    c_void_p, c_void_p]),
+    "nw_kmeans_seed_pick": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "nw_onehot_argmax": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "nw_support_influence": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int,
                                      c_void_p, c_void_p]),

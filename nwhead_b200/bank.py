@@ -240,8 +240,9 @@ class SupportBank:
         n = len(self)
         plan = _abi.forward_plan(b, n)
         dev = self.device
-        # chunk-boundary partials + room for the second epilogue set's table (used for short GEMMs, d <= 1024)
-        extra = b * self.n_classes if (tables is None and self.row_elems <= 1024) else 0
+        # chunk-boundary partials + room for the further epilogue sets' tables (short GEMMs: 2 sets up to d = 1024,
+        # 4 up to d = 512)
+        extra = (lib.nw_forward_epilogue_sets(self.row_elems) - 1) * b * self.n_classes if tables is None else 0
         side = torch.empty((max(int(plan.side_elems) + extra, 1),), dtype=torch.float32, device=dev)
         epi = _abi.EPI_EUCLID if self.kind in EUCLID_KINDS else _abi.EPI_LINEAR
         if tables is not None:
@@ -338,7 +339,7 @@ class SupportBank:
         return out.sqrt()
 
     def topk_exact(self, q: torch.Tensor, k: int, source_feats: torch.Tensor, max_blocks: int = 64,
-                   query_chunk: int = 2048, first_blocks: int = 16) -> torch.Tensor:
+                   query_chunk: int = 2048) -> torch.Tensor:
         """EXACT k nearest supports (euclidean banks), indices into `source_feats` (the fp32 tensor the bank was
         built from), nearest first — the same ranking as the dense fp32 path (ties by ascending index), without
         the (B, N) score matrix:
@@ -346,7 +347,7 @@ class SupportBank:
           1. tensor-core pass (nw_forward_emit / NW_EMIT_BLOCK_BEST): best reduced-precision score beta_j =
              -distance of every query in every block j of 64 bank rows; the blocks of each query are ranked
              (nw_rank_rows);
-          2. nw_topk_refine, ONE launch per candidate budget m: the rows of the m best blocks are gathered from
+          2. nw_topk_refine, ONE launch: the rows of the m best blocks of every query are gathered from
              `source_feats` and scored with the exact fp32 differences of the dense path (bit for bit), ranked by
              (score, source index) -> tau_c, the exact k-th best candidate score;
           3. certificate, in the same kernel: no row outside the candidates can score >= tau_c.  Such a row has a
@@ -356,10 +357,10 @@ class SupportBank:
              squared distance by at most e2 = 2^-18 (|q|^2 + max|s|^2).  So its true score is at most
              U = -(sqrt(beta_(m+1)^2 - e2) - eta); U < tau_c certifies the query.
 
-        Budgets: m = `first_blocks` for every query, then m = `max_blocks` (at most 64) for the queries the first
-        budget could not certify, then the dense exact path for what is left — so the result is exact for every
-        input, and the only host synchronisation is one read of the count of uncertified queries per chunk
-        (`last_topk_path` counts both routes)."""
+        Every query sizes its own candidate budget m <= `max_blocks` (at most 64) inside the kernel from the same
+        bounds (blocks that could still reach the k-th best block score); queries it cannot certify take the dense
+        exact path — so the result is exact for every input, and the only host synchronisation is one read of the
+        count of uncertified queries per chunk (`last_topk_path` counts both routes)."""
         from .kernel import dense_scores
         from .utils import rank_rows
 
@@ -384,9 +385,7 @@ class SupportBank:
         if getattr(self, "_smax_sq", None) is None:
             self._smax_sq = self.sqnorm.max().reshape(1)
         nblk = (n + 63) // 64
-        max_blocks = max(1, min(int(max_blocks), 64, nblk))
-        budgets = sorted({min(max(int(first_blocks), (k + 63) // 64), max_blocks), max_blocks})
-        budgets = [m for m in budgets if m * 64 >= k]
+        m_cap = max(1, min(int(max_blocks), 64, nblk))
         out = torch.empty((q.shape[0], k), dtype=torch.int64, device=dev)
         self.last_topk_path = {"blocks": 0, "dense": 0}
         for i0 in range(0, q.shape[0], query_chunk):
@@ -394,20 +393,18 @@ class SupportBank:
             b = qc.shape[0]
             done = torch.zeros((b,), dtype=torch.int32, device=dev)
             n_left = b
-            if budgets:
+            if m_cap * 64 >= k:
                 best, q_sq = self.block_best(qc)                     # (b, nblk) scores = -distance
-                width = min(nblk, max_blocks + 1)
+                width = min(nblk, max(m_cap + 1, k))
                 order = rank_rows(best, width)                       # blocks by best score, descending
                 sorted_best = best.gather(1, order)
                 resid_q = self.rounding_residual(qc)
-                idx = out[i0:i0 + b]
-                pending = torch.zeros((len(budgets),), dtype=torch.int32, device=dev)
-                for j, m in enumerate(budgets):
-                    check(lib.nw_topk_refine(ptr(qc), b, d, ptr(src_all), n, ptr(self.perm), ptr(order),
-                                             ptr(sorted_best), width, m, nblk, k, ptr(q_sq), ptr(resid_q),
-                                             ptr(self._smax_sq), ptr(resid_max), self.precision, ptr(done), ptr(idx),
-                                             ptr(pending[j:]), stream_of(dev)), "nw_topk_refine")
-                n_left = int(pending[-1].item())                     # the one host synchronisation of the chunk
+                pending = torch.zeros((1,), dtype=torch.int32, device=dev)
+                check(lib.nw_topk_refine(ptr(qc), b, d, ptr(src_all), n, ptr(self.perm), ptr(order), ptr(sorted_best),
+                                         width, m_cap, nblk, k, ptr(q_sq), ptr(resid_q), ptr(self._smax_sq),
+                                         ptr(resid_max), self.precision, ptr(done), ptr(out[i0:i0 + b]), ptr(pending),
+                                         stream_of(dev)), "nw_topk_refine")
+                n_left = int(pending.item())                         # the one host synchronisation of the chunk
             self.last_topk_path["blocks"] += b - n_left
             if n_left:  # too many near-ties for the candidate budget: dense exact scores for those queries
                 rows = (done == 0).nonzero().flatten()

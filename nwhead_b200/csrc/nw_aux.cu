@@ -262,7 +262,8 @@ __global__ void rank_emit_kernel(const uint64_t* __restrict__ keys, long long pa
 // candidate's score has the bits of the dense (B, N) matrix — the (score, source index) keys are sorted in shared
 // memory, and the query is CERTIFIED in place: a row outside the candidates cannot beat the exact k-th candidate
 // score (bounds in nwhead_b200/bank.py::topk_exact).  Gather, re-score, ranking and certificate are one launch with
-// no host round trip; uncertified queries are only counted (the caller retries them with a larger m, then densely).
+// no host round trip; every query sizes its own candidate budget m <= m_cap from the same bounds; uncertified queries
+// are only counted (the caller takes the dense path for them).
 // ---------------------------------------------------------------------------------------------
 constexpr int TOPK_THREADS = 256;
 constexpr int TOPK_ROWS_PER_WARP = 4;  // candidate rows a warp scores together: 4 independent load streams
@@ -274,18 +275,50 @@ __device__ __forceinline__ float key_score(uint64_t key) {
 
 __global__ void __launch_bounds__(TOPK_THREADS) topk_refine_kernel(
     const float* __restrict__ q, int d, const float* __restrict__ src, long long n, const int64_t* __restrict__ perm,
-    const int64_t* __restrict__ block_order, const float* __restrict__ block_best_sorted, int order_stride, int m,
-    long long n_blocks, int k, int padded, const float* __restrict__ q_sq, const float* __restrict__ resid_q,
+    const int64_t* __restrict__ block_order, const float* __restrict__ block_best_sorted, int order_stride, int m_cap,
+    long long n_blocks, int k, int padded_cap, const float* __restrict__ q_sq, const float* __restrict__ resid_q,
     const float* __restrict__ smax_sq_ptr, const float* __restrict__ resid_max_ptr, int precision,
     int32_t* __restrict__ done, int64_t* __restrict__ idx_out, int32_t* __restrict__ n_pending) {
   extern __shared__ __align__(16) uint8_t topk_smem[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(topk_smem);
-  float* qs = reinterpret_cast<float*>(keys + padded);
+  float* qs = reinterpret_cast<float*>(keys + padded_cap);
+  __shared__ int need_smem;
   const int b = blockIdx.x;
   if (done[b]) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c = threadIdx.x; c < d; c += TOPK_THREADS) qs[c] = q[(long long)b * d + c];
+  // error bounds of the reduced-precision pass for this query (see SupportBank.topk_exact)
+  const float* best_row = block_best_sorted + (long long)b * order_stride;
+  const float up = 1.0f + 0.0078125f;                                      // norms of the rounded rows -> of the rows
+  const float qn = sqrtf(q_sq[b]) * up;
+  const float smax = sqrtf(*smax_sq_ptr) * up;
+  const float e2 = 3.814697265625e-06f * (qn * qn + smax * smax);          // 2^-18: fp32 accumulation of the pass
+  const float eta = (resid_q[b] + *resid_max_ptr) * (1.0f + 0.0009765625f);
+  const float lolo = precision == NW_PREC_BF16 ? 0.0f : (0.00390625f * (qn + smax)) * (0.00390625f * (qn + smax));
+  const float fp32_sum = 1.0f - float(d + 8) * 5.9604644775390625e-08f;    // the exact path's own summation error
+  auto upper = [&](float beta) {  // largest exact score of a row whose pass score is beta
+    return -fmaxf(sqrtf(fmaxf(beta * beta - e2, 0.0f)) - eta, 0.0f) * fp32_sum;
+  };
+  // Candidate budget of THIS query: the k best blocks each hold a row scoring >= lower(beta_(k)); blocks whose best
+  // row cannot reach that are out.  (The certificate below is what guarantees exactness; this only sizes the gather.)
+  if (threadIdx.x == 0) need_smem = 0;
+  __syncthreads();
+  int m = m_cap;
+  if (n_blocks > k && order_stride >= k) {
+    const float bk = best_row[k - 1];
+    const float thr = -(sqrtf(bk * bk + e2 + lolo) + eta) / fp32_sum;
+    int cnt = 0;
+    for (int j = threadIdx.x; j < order_stride; j += TOPK_THREADS) cnt += upper(best_row[j]) >= thr ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0 && cnt) atomicAdd(&need_smem, cnt);
+    __syncthreads();
+    m = need_smem;
+  }
+  m = max(m, (k + 63) / 64);
+  m = min(m, m_cap);
   const int n_cand = m * 64;
+  int padded = 64;
+  while (padded < n_cand) padded <<= 1;
   for (int i = n_cand + threadIdx.x; i < padded; i += TOPK_THREADS) keys[i] = ~uint64_t(0);
   __syncthreads();
   const int64_t* order = block_order + (long long)b * order_stride;
@@ -327,24 +360,11 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_refine_kernel(
       __syncthreads();
     }
   }
-  // certificate (all threads evaluate the same scalars)
+  // certificate (all threads evaluate the same scalars): no row outside the candidates can reach the exact k-th score
   bool ok = true;
   if (m < n_blocks) {
     const uint64_t kth = keys[k - 1];
-    ok = kth != ~uint64_t(0);
-    const float tau = key_score(kth);
-    const float beta = block_best_sorted[(long long)b * order_stride + m];  // best score of the first block left out
-    const float up = 1.0f + 0.0078125f;                                      // norms of the rounded rows -> of the rows
-    const float qn = sqrtf(q_sq[b]) * up;
-    const float smax = sqrtf(*smax_sq_ptr) * up;
-    const float e2 = 3.814697265625e-06f * (qn * qn + smax * smax);          // 2^-18: fp32 accumulation of the pass
-    const float eta = (resid_q[b] + *resid_max_ptr) * (1.0f + 0.0009765625f);
-    const float fp32_sum = 1.0f - float(d + 8) * 5.9604644775390625e-08f;    // the exact path's own summation error
-    const float inner = sqrtf(fmaxf(beta * beta - e2, 0.0f)) - eta;
-    const float upper = -fmaxf(inner, 0.0f) * fp32_sum;  // largest exact score of a row whose pass score is beta
-    ok = ok && (upper < tau);
-    (void)precision;  // (bf16x3 drops lo.lo products: that only LOWERS pass scores' distances, handled by `lower`
-                      //  on the host when sizing m; the upper bound above holds for both precisions)
+    ok = kth != ~uint64_t(0) && upper(best_row[m]) < key_score(kth);  // best_row[m]: best block left out
   }
   if (ok) {
     for (int i = threadIdx.x; i < k; i += TOPK_THREADS) idx_out[(long long)b * k + i] = int64_t(keys[i] & 0xffffffffull);
@@ -521,10 +541,122 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(const float* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k-means++ seeding with scikit-learn's arithmetic (compute_clusters with n_clusters > 1, nwhead/utils.py:230).
+// sklearn centres each class (X -= X.mean(0), float32) and evaluates the squared distances of _kmeans_plusplus in
+// float64, rounded to float32 (_euclidean_distances_upcast).  seed_dist: for every row, the squared distance to
+// each of its class's T candidate rows, with exactly that rounding.  One warp per row, float64 accumulation.
+// ---------------------------------------------------------------------------------------------
+constexpr int SEED_MAX_T = 8;
+
+__global__ void __launch_bounds__(256) kmeans_seed_dist_kernel(const float* __restrict__ rows, int d, long long ld,
+                                                               const int32_t* __restrict__ group,
+                                                               const int64_t* __restrict__ order, long long n_rows,
+                                                               const float* __restrict__ mean,
+                                                               const int64_t* __restrict__ cand, int n_cand,
+                                                               float* __restrict__ dist_out) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < n_rows; p += warps) {
+    const long long r = order ? order[p] : p;
+    const int g = group[r];
+    const float* x = rows + r * ld;
+    const float* m = mean + (size_t)g * d;
+    const float* cp[SEED_MAX_T];
+#pragma unroll
+    for (int t = 0; t < SEED_MAX_T; ++t) cp[t] = rows + cand[(size_t)g * n_cand + (t < n_cand ? t : 0)] * ld;
+    double acc[SEED_MAX_T];
+#pragma unroll
+    for (int t = 0; t < SEED_MAX_T; ++t) acc[t] = 0.0;
+    for (int c = lane; c < d; c += 32) {
+      const float mc = m[c];
+      const double xc = double(__fsub_rn(__ldcs(x + c), mc));  // the float32 value sklearn holds after X -= mean
+#pragma unroll
+      for (int t = 0; t < SEED_MAX_T; ++t) {
+        if (t < n_cand) {
+          const double df = xc - double(__fsub_rn(cp[t][c], mc));
+          acc[t] = fma(df, df, acc[t]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < SEED_MAX_T; ++t) {
+      if (t < n_cand) {
+        double v = acc[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) dist_out[(size_t)t * n_rows + r] = fmaxf(float(v), 0.0f);
+      }
+    }
+  }
+}
+
+// seed_pick: np.searchsorted(np.cumsum(closest_dist_sq), rand_vals) per class — numpy's cumsum of a float32 array
+// is a sequential float32 accumulation, reproduced here by one thread per class walking its rows in class-sorted
+// order.  pos_out[c, t] = source row of the first position whose running sum >= targets[c, t] (clipped to the
+// class's last row, as sklearn clips).
+__global__ void kmeans_seed_pick_kernel(const float* __restrict__ closest, const int64_t* __restrict__ order,
+                                        const int32_t* __restrict__ offsets, int n_classes,
+                                        const double* __restrict__ targets, int n_targets,
+                                        int64_t* __restrict__ pos_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_classes) return;
+  const long long lo = offsets[c], hi = offsets[c + 1];
+  if (hi <= lo) return;
+  long long found[SEED_MAX_T];
+  double tg[SEED_MAX_T];
+  for (int t = 0; t < SEED_MAX_T; ++t) {
+    found[t] = -1;
+    tg[t] = t < n_targets ? targets[(size_t)c * n_targets + t] : 0.0;
+  }
+  float run = 0.0f;
+  int open = n_targets;
+  for (long long p = lo; p < hi && open > 0; ++p) {
+    run = __fadd_rn(run, closest[order ? order[p] : p]);
+    for (int t = 0; t < n_targets; ++t)
+      if (found[t] < 0 && double(run) >= tg[t]) {
+        found[t] = p;
+        --open;
+      }
+  }
+  for (int t = 0; t < n_targets; ++t) {
+    const long long p = found[t] < 0 ? hi - 1 : found[t];
+    pos_out[(size_t)c * n_targets + t] = order ? order[p] : p;
+  }
+}
+
 }  // namespace aux
 }  // namespace nw
 
 using namespace nw;
+
+extern "C" int nw_kmeans_seed_dist(const float* rows, int d, int64_t ld, const int32_t* group, const int64_t* order,
+                                   int64_t n_rows, const float* class_mean, const int64_t* cand_rows, int n_cand,
+                                   float* dist_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(rows && group && class_mean && cand_rows && dist_out, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(d > 0 && ld >= d && n_rows > 0, NW_ERR_INVALID, "bad shape");
+  NW_REQUIRE(n_cand >= 1 && n_cand <= aux::SEED_MAX_T, NW_ERR_INVALID, "n_cand must be in [1, %d]", aux::SEED_MAX_T);
+  const long long want = ceil_div_ll(n_rows, 8);
+  const long long fit = (long long)sm_count() * 8;
+  aux::kmeans_seed_dist_kernel<<<unsigned(want < fit ? want : fit), 256, 0, stream>>>(
+      rows, d, ld, group, order, n_rows, class_mean, cand_rows, n_cand, dist_out);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_kmeans_seed_pick(const float* closest, const int64_t* order, const int32_t* offsets, int n_classes,
+                                   const double* targets, int n_targets, int64_t* pos_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(closest && offsets && targets && pos_out, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n_classes > 0, NW_ERR_INVALID, "n_classes must be positive");
+  NW_REQUIRE(n_targets >= 1 && n_targets <= aux::SEED_MAX_T, NW_ERR_INVALID, "n_targets must be in [1, %d]",
+             aux::SEED_MAX_T);
+  aux::kmeans_seed_pick_kernel<<<ceil_div(n_classes, 64), 64, 0, stream>>>(closest, order, offsets, n_classes, targets,
+                                                                           n_targets, pos_out);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
 
 extern "C" size_t nw_class_centroids_workspace_bytes(int n_classes, int d) {
   if (n_classes <= 0 || d <= 0) return 0;
@@ -679,7 +811,7 @@ extern "C" int nw_rank_rows(const float* scores, int n_rows, int64_t n_cols, int
 
 extern "C" int nw_topk_refine(const float* q, int n_query, int d, const float* source_rows, int64_t n_rows,
                               const int64_t* perm, const int64_t* block_order, const float* block_best_sorted,
-                              int order_stride, int m, int64_t n_blocks, int k, const float* q_sqnorm,
+                              int order_stride, int m_cap, int64_t n_blocks, int k, const float* q_sqnorm,
                               const float* resid_q, const float* smax_sq, const float* resid_max, int precision,
                               int32_t* done, int64_t* idx_out, int32_t* n_pending, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -687,17 +819,18 @@ extern "C" int nw_topk_refine(const float* q, int n_query, int d, const float* s
                  done && idx_out && n_pending,
              NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(n_query > 0 && d > 0 && n_rows > 0 && n_rows < (1ll << 32), NW_ERR_INVALID, "bad shape");
-  NW_REQUIRE(m >= 1 && m <= 64 && m <= n_blocks, NW_ERR_INVALID, "m must be in [1, min(64, n_blocks)]");
-  NW_REQUIRE(m == n_blocks || order_stride > m, NW_ERR_INVALID, "block_order needs m + 1 entries per query");
-  NW_REQUIRE(k >= 1 && k <= m * 64 && k <= n_rows, NW_ERR_INVALID, "k must be in [1, min(64 m, n_rows)]");
-  const int padded = int(aux::next_pow2(m * 64));
+  NW_REQUIRE(m_cap >= 1 && m_cap <= 64 && m_cap <= n_blocks, NW_ERR_INVALID, "m_cap must be in [1, min(64, n_blocks)]");
+  NW_REQUIRE(order_stride >= m_cap && (m_cap == n_blocks || order_stride > m_cap), NW_ERR_INVALID,
+             "block_order needs m_cap + 1 entries per query");
+  NW_REQUIRE(k >= 1 && k <= m_cap * 64 && k <= n_rows, NW_ERR_INVALID, "k must be in [1, min(64 m_cap, n_rows)]");
+  const int padded = int(aux::next_pow2(m_cap * 64));
   const size_t smem = size_t(padded) * sizeof(uint64_t) + size_t(d) * sizeof(float);
   NW_REQUIRE(smem <= 200 * 1024, NW_ERR_UNSUPPORTED, "feature dimension %d too large for the refinement kernel", d);
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)
     NW_CUDA_OK(cudaFuncSetAttribute(aux::topk_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   aux::topk_refine_kernel<<<n_query, aux::TOPK_THREADS, smem, stream>>>(
-      q, d, source_rows, n_rows, perm, block_order, block_best_sorted, order_stride, m, n_blocks, k, padded, q_sqnorm,
-      resid_q, smax_sq, resid_max, precision, done, idx_out, n_pending);
+      q, d, source_rows, n_rows, perm, block_order, block_best_sorted, order_stride, m_cap, n_blocks, k, padded,
+      q_sqnorm, resid_q, smax_sq, resid_max, precision, done, idx_out, n_pending);
   NW_CUDA_OK(cudaGetLastError());
   return NW_OK;
 }

@@ -772,7 +772,7 @@ extern "C" int nw_direct_backward(int kind, float scale, const float* q, int n_q
              NW_DIRECT_BACKWARD_MAX_D_PLUS_C);
   // more than the default 48 KB of dynamic shared memory is an opt-in per kernel (and per device: cheap, idempotent)
   const size_t big = size_t(d + n_classes) * sizeof(float);
-  if (big > 48 * 1024) {
+  if (big > 36 * 1024) {  // (the kernels also hold up to 8.2 KB of static shared memory; the 48 KB default covers both)
     const int cap = NW_DIRECT_BACKWARD_MAX_D_PLUS_C * int(sizeof(float));
     NW_CUDA_OK(cudaFuncSetAttribute(direct::small_coef_gradq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     NW_CUDA_OK(cudaFuncSetAttribute(direct::small_grad_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));

@@ -42,11 +42,17 @@ constexpr int A_BYTES = BM * BK * 2;
 constexpr int EPI_WARP0 = 4;
 constexpr int MAX_EPI_WARPS = 8;
 constexpr int MAX_THREADS = (EPI_WARP0 + MAX_EPI_WARPS) * 32;
+constexpr int QUAD_SETS = 4;  // epilogue sets of the QUAD variant (very short GEMMs, d <= 512)
+constexpr int QUAD_THREADS = (EPI_WARP0 + 4 * QUAD_SETS) * 32;
 // Epilogue warps: one thread per query row (4 warps = 128 TMEM lanes).  A second set of 4 warps (same lane
 // quarters) takes every other pair of 32-column chunks: always in the emit modes (no state along the columns),
 // and in the class-LSE mode when the GEMM is short (d <= 1024) and the epilogue would otherwise be the
 // bottleneck.  There each set keeps its OWN running (max, sum) per class and stores to its OWN table; the two
 // tables are combined afterwards by one log-add-exp pass, so the sets never synchronise with each other.
+// At d <= 512 the two MUFU ops per score take as long as the score's MMAs, and ncu showed both pipes only ~60 %
+// busy with two epilogue warps per scheduler (latency-bound: the epilogue cannot keep the MUFU queue full).  The
+// QUAD variant runs FOUR sets (16 epilogue warps, one 64-column chunk pair of every tile each, one 32-column chunk
+// in registers at a time so that 640 threads fit the register file).
 constexpr int NW_MAX_PEERS = 16;
 
 // NCTA = 1: one CTA computes a 128 x 256 tile (UMMA M=128).
@@ -67,9 +73,9 @@ struct TileMeta {
   int lab[BN + 8];   // labels of the tile's columns plus one look-ahead entry
 };
 
-template <int MODE>
+template <int MODE, bool QUAD = false>
 struct SmemTail {
-  TileMeta meta[2][ACC_STAGES];  // [epilogue set][accumulator stage]: the sets stay independent of each other
+  TileMeta meta[QUAD ? QUAD_SETS : 2][ACC_STAGES];  // [epilogue set][accumulator stage]: the sets stay independent
   float stage[MODE == 0 ? 1 : MAX_EPI_WARPS][32][33];  // emit modes: per-warp 32x32 transpose buffers
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
@@ -78,10 +84,10 @@ struct SmemTail {
   uint32_t tmem_base;
 };
 
-template <int NCTA, int MODE>
+template <int NCTA, int MODE, bool QUAD = false>
 constexpr size_t smem_bytes() {
   return 1024 /*align slack*/ + size_t(Cfg<NCTA, MODE>::STAGES) * Cfg<NCTA, MODE>::STAGE_BYTES +
-         sizeof(SmemTail<MODE>);
+         sizeof(SmemTail<MODE, QUAD>);
 }
 
 struct Params {
@@ -102,7 +108,7 @@ struct Params {
   int chunks;
   int tiles_per_chunk;
   float scale_log2;  // LINEAR: scale * log2(e)
-  int sets;          // epilogue warp sets (1 or 2); class-LSE with 2 sets: set s stores to lse[s]
+  int sets;          // epilogue warp sets (1, 2 or 4); class-LSE with several sets: set s stores to lse[s]
   // ---- MODE_EMIT only: one output value per (query, support) pair
   float* emit_out;           // (B, ld_out)
   long long emit_ld;
@@ -287,8 +293,8 @@ __device__ __forceinline__ float chunk_best(const float (&acc)[32], const float*
   return n_valid > 0 ? best : __int_as_float(0xff800000);
 }
 
-template <int EPI, int NCTA, int MODE>
-__global__ void __launch_bounds__(MAX_THREADS, 1)
+template <int EPI, int NCTA, int MODE, bool QUAD = false>
+__global__ void __launch_bounds__(QUAD ? QUAD_THREADS : MAX_THREADS, 1)
 nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_s,
                   const __grid_constant__ Params p) {
   using C = Cfg<NCTA, MODE>;
@@ -298,7 +304,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;  // 1024-B aligned (swizzle-128B atoms); same offset in both CTAs of a pair
-  SmemTail<MODE>* tail = reinterpret_cast<SmemTail<MODE>*>(smem + size_t(STAGES) * STAGE_BYTES);
+  SmemTail<MODE, QUAD>* tail = reinterpret_cast<SmemTail<MODE, QUAD>*>(smem + size_t(STAGES) * STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -463,8 +469,8 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       flush.row = srow;
       flush.set = eg;
       flush.sets = p.sets;
-      flush.route = p.sets == 2 ? 0 : (p.rows_per_table > 0 ? 1 : (p.n_tables > 1 ? 2 : 0));
-      flush.table = p.lse[p.sets == 2 ? eg : 0];
+      flush.route = p.sets >= 2 ? 0 : (p.rows_per_table > 0 ? 1 : (p.n_tables > 1 ? 2 : 0));
+      flush.table = p.lse[p.sets >= 2 ? eg : 0];
       flush.row_off = size_t(srow) * p.n_classes;
       flush.side_row = p.side + (size_t(g) * p.n_query + srow) * 2 * p.sets;
       const float qn = (EPI == NW_EPI_EUCLID && flush.row_valid) ? __ldg(p.q_sqnorm + row) : 0.0f;
@@ -550,30 +556,44 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                                   n1 - (j0 + (c + 1) * 32), p.emit_vec != 0);
             continue;
           }
-          if (p.sets == 2 && ((c >> 1) & 1) != eg) continue;  // chunk pairs alternate between the two sets
-          float acc0[32], acc1[32];
-          tmem_ld_32x32(t_addr + c * 32, acc0);
-          tmem_ld_32x32(t_addr + (c + 1) * 32, acc1);
-          if (p.sets == 2) {
+          if (p.sets >= 2 && ((c >> 1) % p.sets) != eg) continue;  // chunk pairs are dealt round-robin to the sets
+          if (p.sets >= 2) {
             // this set skipped the columns in between: if they ended the class it was accumulating, close its
-            // partial now (the other set closes its own; the two tables are combined after the kernel)
+            // partial now (the other sets close their own; the tables are combined after the kernel)
             const int first = meta.lab[c * 32];
             if (open_cls >= 0 && first != open_cls) {
               flush(open_cls, m, l);
               l = 0.0f;
             }
           }
-          // class-end masks of both chunks while the TMEM loads are in flight
           const int i0 = c * 32 + lane, i1 = i0 + 32;
           const int ja = j0 + i0, jb = j0 + i1;
-          const uint32_t em0 =
-              __ballot_sync(0xffffffffu, ja < n1 && (ja == n1 - 1 || meta.lab[i0] != meta.lab[i0 + 1]));
-          const uint32_t em1 =
-              __ballot_sync(0xffffffffu, jb < n1 && (jb == n1 - 1 || meta.lab[i1] != meta.lab[i1 + 1]));
-          tmem_ld_wait();
-          epilogue_chunk<EPI>(acc0, meta.cadd + c * 32, meta.lab + c * 32, em0, qn, scale2, m, l, flush);
-          epilogue_chunk<EPI>(acc1, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, em1, qn, scale2, m, l, flush);
-          if (p.sets == 2) {
+          uint32_t em1;
+          if (QUAD) {
+            // one 32-column chunk in registers at a time: 640 threads leave ~100 registers per thread
+            float acc[32];
+            tmem_ld_32x32(t_addr + c * 32, acc);
+            const uint32_t em0 =
+                __ballot_sync(0xffffffffu, ja < n1 && (ja == n1 - 1 || meta.lab[i0] != meta.lab[i0 + 1]));
+            tmem_ld_wait();
+            epilogue_chunk<EPI>(acc, meta.cadd + c * 32, meta.lab + c * 32, em0, qn, scale2, m, l, flush);
+            tmem_ld_32x32(t_addr + (c + 1) * 32, acc);
+            em1 = __ballot_sync(0xffffffffu, jb < n1 && (jb == n1 - 1 || meta.lab[i1] != meta.lab[i1 + 1]));
+            tmem_ld_wait();
+            epilogue_chunk<EPI>(acc, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, em1, qn, scale2, m, l, flush);
+          } else {
+            float acc0[32], acc1[32];
+            tmem_ld_32x32(t_addr + c * 32, acc0);
+            tmem_ld_32x32(t_addr + (c + 1) * 32, acc1);
+            // class-end masks of both chunks while the TMEM loads are in flight
+            const uint32_t em0 =
+                __ballot_sync(0xffffffffu, ja < n1 && (ja == n1 - 1 || meta.lab[i0] != meta.lab[i0 + 1]));
+            em1 = __ballot_sync(0xffffffffu, jb < n1 && (jb == n1 - 1 || meta.lab[i1] != meta.lab[i1 + 1]));
+            tmem_ld_wait();
+            epilogue_chunk<EPI>(acc0, meta.cadd + c * 32, meta.lab + c * 32, em0, qn, scale2, m, l, flush);
+            epilogue_chunk<EPI>(acc1, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, em1, qn, scale2, m, l, flush);
+          }
+          if (p.sets >= 2) {
             // class left open after this pair (none if its last valid column closed a class or is padding)
             const int j_last = j0 + (c + 2) * 32 - 1;
             open_cls = (j_last < n1 && !(em1 >> 31)) ? meta.lab[(c + 2) * 32 - 1] : -1;
@@ -588,7 +608,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
       }
       // two sets: the unit's last columns may belong to the other set; close what this set still holds
-      if (MODE == MODE_CLASS_LSE && p.sets == 2 && open_cls >= 0) flush(open_cls, m, l);
+      if (MODE == MODE_CLASS_LSE && p.sets >= 2 && open_cls >= 0) flush(open_cls, m, l);
     }
     if (probe) {
       atomicAdd(p.clock_probe + 2 * blockIdx.x, (unsigned long long)(clock64() - probe_c0));
@@ -662,7 +682,9 @@ __global__ void __launch_bounds__(MERGE_ROWS_PER_BLOCK * 32) merge_side_kernel(
   for (int base = 0; base < chunks; base += 32) {
     const int g = base + lane;
     int c0 = 0, c1 = 0;
-    float v[4] = {neg_inf, neg_inf, neg_inf, neg_inf};  // [slot][set]
+    float v[2 * QUAD_SETS];  // [slot][set]
+#pragma unroll
+    for (int i = 0; i < 2 * QUAD_SETS; ++i) v[i] = neg_inf;
     if (g < chunks) {
       const int t0 = g * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, s_tiles);
@@ -674,9 +696,9 @@ __global__ void __launch_bounds__(MERGE_ROWS_PER_BLOCK * 32) merge_side_kernel(
     const int cnt = min(32, chunks - base);
     for (int j = 0; j < cnt; ++j) {
       const int jc0 = __shfl_sync(0xffffffffu, c0, j), jc1 = __shfl_sync(0xffffffffu, c1, j);
-      float jv[4];
+      float jv[2 * QUAD_SETS];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) jv[i] = __shfl_sync(0xffffffffu, v[i], j);
+      for (int i = 0; i < 2 * QUAD_SETS; ++i) jv[i] = __shfl_sync(0xffffffffu, v[i], j);
       for (int i = 0; i < sets; ++i) add(jc0, jv[i]);
       for (int i = 0; i < sets; ++i) add(jc1, jv[sets + i]);
     }
@@ -761,6 +783,16 @@ __global__ void lse_merge_kernel(float* __restrict__ a, const float* __restrict_
     a[i] = logaddexp_f(a[i], b[i]);
 }
 
+// a <- log(exp(a) + sum_t exp(b[t * n + .])), t < n_extra: the tables of the further epilogue sets, in set order
+__global__ void lse_merge_sets_kernel(float* __restrict__ a, const float* __restrict__ b, int n_extra, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = a[i];
+    for (int t = 0; t < n_extra; ++t) v = logaddexp_f(v, b[(long long)t * n + i]);
+    a[i] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -828,6 +860,19 @@ static int support_keep_policy(int q_groups) {
   return q_groups >= min_groups ? 1 : 0;
 }
 
+// Epilogue warp sets the fused forward wants for rows of `row_elems` bf16: the epilogue (2 MUFU ops per score) is
+// the bottleneck of short GEMMs.  NW_B200_EPI_SETS=1|2|4 overrides (same-box A/B runs).
+extern "C" int nw_forward_epilogue_sets(int row_elems) {
+  static const int forced = [] {
+    const char* e = getenv("NW_B200_EPI_SETS");
+    const int v = e && *e ? atoi(e) : 0;
+    return (v == 1 || v == 2 || v == 4) ? v : 0;
+  }();
+  if (forced) return forced;
+  const int kblocks = row_elems / k1::BK;
+  return kblocks <= 8 ? k1::QUAD_SETS : (kblocks <= 16 ? 2 : 1);
+}
+
 extern "C" int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t* plan) {
   NW_REQUIRE(plan != nullptr, NW_ERR_INVALID, "plan_out is NULL");
   NW_REQUIRE(n_query > 0 && n_support > 0, NW_ERR_INVALID, "n_query and n_support must be positive");
@@ -863,20 +908,20 @@ extern "C" int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t
   const long long units = (long long)plan->chunks * q_groups;
   plan->grid = int(units < workers ? units : workers) * ncta;
   plan->cta_pair = ncta == 2 ? 1 : 0;
-  // chunk-boundary partials: [chunk][query][2 slots][2 epilogue sets]  (+ room for the second set's table is
-  // added by the caller of the two-set mode, see forward_impl)
-  plan->side_elems = int64_t(plan->chunks) * n_query * 4;
+  // chunk-boundary partials: [chunk][query][2 slots][up to 4 epilogue sets]  (+ room for the further sets' tables
+  // is added by the caller, see nw_forward_epilogue_sets / forward_impl)
+  plan->side_elems = int64_t(plan->chunks) * n_query * 2 * k1::QUAD_SETS;
   return NW_OK;
 }
 
 namespace nw {
 namespace k1 {
-template <int EPI, int NCTA, int MODE = MODE_CLASS_LSE>
+template <int EPI, int NCTA, int MODE = MODE_CLASS_LSE, bool QUAD = false>
 static int launch_forward(const CUtensorMap& map_q, const CUtensorMap& map_s, const Params& p, int grid,
                           cudaStream_t stream) {
   static bool attr_set[64] = {false};  // function attributes are per device
-  auto kern = nw_forward_kernel<EPI, NCTA, MODE>;
-  constexpr size_t smem = smem_bytes<NCTA, MODE>();
+  auto kern = nw_forward_kernel<EPI, NCTA, MODE, QUAD>;
+  constexpr size_t smem = smem_bytes<NCTA, MODE, QUAD>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
   int dev = 0;
   NW_CUDA_OK(cudaGetDevice(&dev));
@@ -930,9 +975,9 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   // Short GEMMs (d <= 1024) are epilogue-bound with one epilogue warp per scheduler: run two independent epilogue
   // sets, each with its own class-LSE table (the second one lives behind the chunk partials in `side`).
   const long long table_elems = (long long)n_query * n_classes;
-  const char* env_sets = getenv("NW_B200_EPI_SETS");
-  int sets = (row_elems / k1::BK <= 16 && n_tables == 1 && side_elems >= plan.side_elems + table_elems) ? 2 : 1;
-  if (env_sets && env_sets[0] == '1') sets = 1;
+  int sets = nw_forward_epilogue_sets(row_elems);
+  // the further sets need their own tables behind the chunk partials; the multi-table (peer GPU) routes use one set
+  while (sets > 1 && (n_tables != 1 || side_elems < plan.side_elems + (sets - 1) * table_elems)) sets >>= 1;
   float* table1 = side + plan.side_elems;
 
   CUtensorMap map_q, map_s;
@@ -942,7 +987,7 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   if (rc != NW_OK) return rc;
 
   k1::fill_kernel<<<sm_count() * 4, 256, 0, stream>>>(tables[0], fill_local ? table_elems : 0, side,
-                                                      (long long)plan.side_elems + (sets == 2 ? table_elems : 0),
+                                                      (long long)plan.side_elems + (sets - 1) * table_elems,
                                                       -INFINITY);
   NW_CUDA_OK(cudaGetLastError());
 
@@ -952,7 +997,7 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.labels = labels;
   k1::TableList tl;
   for (int r = 0; r < k1::NW_MAX_PEERS; ++r) p.lse[r] = tl.t[r] = (r < n_tables ? tables[r] : nullptr);
-  if (sets == 2) p.lse[1] = table1;
+  for (int t = 1; t < sets; ++t) p.lse[t] = table1 + (long long)(t - 1) * table_elems;
   p.n_tables = tl.n = n_tables;
   p.rows_per_table = tl.rows_per_table = rows_per_table;
   p.sets = sets;
@@ -975,17 +1020,22 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.row_lse = p.p_query = nullptr;
   p.qlabel = nullptr;
 
-  if (epilogue == NW_EPI_EUCLID) {
-    rc = ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2>(map_q, map_s, p, plan.grid, stream)
-                   : k1::launch_forward<NW_EPI_EUCLID, 1>(map_q, map_s, p, plan.grid, stream);
+  const bool euc = epilogue == NW_EPI_EUCLID;
+  if (sets == k1::QUAD_SETS) {
+    rc = euc ? (ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2, k1::MODE_CLASS_LSE, true>(map_q, map_s, p, plan.grid, stream)
+                          : k1::launch_forward<NW_EPI_EUCLID, 1, k1::MODE_CLASS_LSE, true>(map_q, map_s, p, plan.grid, stream))
+             : (ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2, k1::MODE_CLASS_LSE, true>(map_q, map_s, p, plan.grid, stream)
+                          : k1::launch_forward<NW_EPI_LINEAR, 1, k1::MODE_CLASS_LSE, true>(map_q, map_s, p, plan.grid, stream));
   } else {
-    rc = ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2>(map_q, map_s, p, plan.grid, stream)
-                   : k1::launch_forward<NW_EPI_LINEAR, 1>(map_q, map_s, p, plan.grid, stream);
+    rc = euc ? (ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2>(map_q, map_s, p, plan.grid, stream)
+                          : k1::launch_forward<NW_EPI_EUCLID, 1>(map_q, map_s, p, plan.grid, stream))
+             : (ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2>(map_q, map_s, p, plan.grid, stream)
+                          : k1::launch_forward<NW_EPI_LINEAR, 1>(map_q, map_s, p, plan.grid, stream));
   }
   if (rc != NW_OK) return rc;
 
-  if (sets == 2) {  // combine the two epilogue sets' tables
-    k1::lse_merge_kernel<<<sm_count() * 4, 256, 0, stream>>>(tables[0], table1, table_elems);
+  if (sets > 1) {  // combine the epilogue sets' tables
+    k1::lse_merge_sets_kernel<<<sm_count() * 4, 256, 0, stream>>>(tables[0], table1, sets - 1, table_elems);
     NW_CUDA_OK(cudaGetLastError());
   }
   if (plan.chunks > 1) {

@@ -260,49 +260,93 @@ def class_centroids(feats, labels):
     return cent, uniq.astype(np.int64)
 
 
-def kmeans_centroids(feats, labels, k, seed=0, max_iter=300):
-    """compute_clusters(..., n_clusters=k > 1) (nwhead/utils.py:227-231): per class, k-means to strict convergence.
+def sklearn_kmeans_restated(x, k, max_iter=300, tol=1e-4):
+    """ONE class of compute_clusters(..., n_clusters=k) (nwhead/utils.py:230:
+    `KMeans(n_clusters=k, random_state=0).fit(x).cluster_centers_`), restated from scikit-learn 1.9.0 — the
+    un-vendored, unpinned third-party dependency that owns this arithmetic; pinned to the installed
+    scikit-learn by oracle/gen_golden.py on ambiguous data.  What is restated, in sklearn's order:
 
-    The reference delegates to scikit-learn's KMeans(random_state=0) (un-vendored, unpinned), whose
-    random stream is not reproducible here: PARITY OF THE SEEDING IS UNPINNED.  What is pinned (gen_golden.py,
-    tests/golden/clusters.npz) is the fixed point: on data whose clustering is unambiguous this function and the
-    reference return the same centroids up to their order within a class.
-    Seeding restated from the k-means++ definition with the product's draw order: RandomState(seed), one uniform
-    per class id in 0..max(labels) for every centre; first centre uniform over the class rows, further centres at
-    the inverse CDF of the squared distance to the nearest chosen centre (rows in class-sorted stable order).
-    Returns (centroids (U*k, d) float64, labels (U*k,))."""
-    feats = _f64(feats)
+      KMeans.fit (_kmeans.py): X -= X.mean(axis=0) in float32; tol_abs = mean(var(X, axis=0)) * tol; n_init = 1
+        ('auto' with k-means++); a FRESH RandomState(0) for every fit — every class sees the same random numbers.
+      _kmeans_plusplus: first centre = rs.choice(n, p=uniform) (one random_sample through the normalised cdf);
+        each further centre: n_local_trials = 2 + int(log k) candidates at searchsorted(cumsum_f32(closest_dist_sq),
+        rs.uniform(size=trials) * current_pot); distances in float64 rounded to float32
+        (_euclidean_distances_upcast); the candidate with the smallest potential wins.
+      _kmeans_single_lloyd: labels = argmin distance (first minimum), centres = means; stop when the labels repeat
+        (strict convergence) or when the total squared centre shift <= tol_abs; max_iter = 300.
+    Not restated: BLAS summation orders (float32 dot / GEMM) and the relocation of emptied clusters — an emptied
+    cluster keeps its centre.  Returns (k, d) float32 centres in sklearn's order."""
+    X = np.array(x, dtype=np.float32, order="C", copy=True)
+    n = len(X)
+    if n < k:
+        raise ValueError("a class has fewer rows than n_clusters")
+    mean = X.mean(axis=0)
+    X -= mean
+    tol_abs = float(np.mean(np.var(X, axis=0)) * tol)
+    rs = np.random.RandomState(0)
+    w = np.ones(n, dtype=np.float32)
+    Xd = X.astype(np.float64)
+
+    def dist2(rows):  # float64 arithmetic, rounded to float32, clipped at zero
+        rd = Xd[rows]
+        d2 = (rd * rd).sum(1)[:, None] + (Xd * Xd).sum(1)[None, :] - 2.0 * rd @ Xd.T
+        return np.maximum(d2.astype(np.float32), 0)
+
+    trials = 2 + int(np.log(k))
+    ids = [int(rs.choice(n, p=w / w.sum()))]
+    closest = dist2([ids[0]])[0]
+    pot = np.float32(closest.astype(np.float64).sum())
+    for _ in range(1, k):
+        rand_vals = rs.uniform(size=trials) * pot
+        cand = np.searchsorted(np.cumsum(w * closest), rand_vals)
+        np.clip(cand, None, n - 1, out=cand)
+        dc = np.minimum(closest, dist2(cand))
+        cpot = dc.astype(np.float64).sum(1).astype(np.float32)
+        best = int(np.argmin(cpot))
+        pot, closest = cpot[best], dc[best]
+        ids.append(int(cand[best]))
+    cent = Xd[ids].copy()
+    labels_old = np.full(n, -1)
+    for _ in range(max_iter):
+        d2 = (Xd * Xd).sum(1)[:, None] + (cent * cent).sum(1)[None, :] - 2.0 * Xd @ cent.T
+        labels = d2.argmin(1)
+        new = cent.copy()
+        for j in range(k):
+            if (labels == j).any():
+                new[j] = X[labels == j].astype(np.float64).mean(0)
+        shift = float(((new - cent) ** 2).sum())
+        cent = new
+        if np.array_equal(labels, labels_old) or shift <= tol_abs:
+            break
+        labels_old = labels
+    return (cent + mean.astype(np.float64)).astype(np.float32)
+
+
+def kmeans_centroids(feats, labels, k):
+    """compute_clusters(feats, labels, k > 1) (nwhead/utils.py:218-233, closest=False) through
+    sklearn_kmeans_restated: (centroids (U*k, d) float32, labels (U*k,)) over the sorted unique labels, the rows of a
+    class in dataset order, the centroids of a class in scikit-learn's order.  PINNED: gen_golden.py asserts equality
+    with the reference (scikit-learn) row for row on unambiguous AND on overlapping clusters."""
+    feats = np.asarray(feats, dtype=np.float32)
     labels = np.asarray(labels)
-    n_classes = int(labels.max()) + 1
-    order = np.argsort(labels, kind="stable")
-    rng = np.random.RandomState(seed)
-    draws = [rng.random_sample(n_classes) for _ in range(k)]
     out, out_y = [], []
     for c in np.unique(labels):
-        x = feats[order[labels[order] == c]]
-        if len(x) < k:
-            raise ValueError("a class has fewer rows than n_clusters")
-        cent = [x[min(int(np.floor(draws[0][c] * len(x))), len(x) - 1)]]
-        mind = np.full(len(x), np.inf)
-        for j in range(1, k):
-            mind = np.minimum(mind, ((x - cent[-1]) ** 2).sum(1))
-            cs = np.cumsum(mind)
-            pos = min(int(np.searchsorted(cs, draws[j][c] * cs[-1], side="right")), len(x) - 1)
-            cent.append(x[pos])
-        cent = np.stack(cent)
-        prev = None
-        for _ in range(max_iter):
-            d2 = ((x[:, None, :] - cent[None, :, :]) ** 2).sum(-1)
-            assign = d2.argmin(1)
-            if prev is not None and np.array_equal(assign, prev):
-                break
-            prev = assign
-            for j in range(k):
-                if (assign == j).any():
-                    cent[j] = x[assign == j].mean(0)
-        out.append(cent)
+        out.append(sklearn_kmeans_restated(feats[labels == c], k))
         out_y += [c] * k
     return np.concatenate(out), np.asarray(out_y, dtype=np.int64)
+
+
+def kmeans_inertia(feats, labels, centroids, k):
+    """Sum over rows of the squared distance to the nearest of their class's k centroids (the k-means objective);
+    centroids (U*k, d) over the sorted unique labels.  Returns one value per class."""
+    feats, centroids = _f64(feats), _f64(centroids)
+    labels = np.asarray(labels)
+    out = []
+    for i, c in enumerate(np.unique(labels)):
+        x = feats[labels == c]
+        d2 = ((x[:, None, :] - centroids[None, i * k:(i + 1) * k, :]) ** 2).sum(-1)
+        out.append(d2.min(1).sum())
+    return np.asarray(out)
 
 
 def match_centroid_sets(a, b, k):

@@ -66,19 +66,28 @@ def test_class_centroids_shapes(cuda_lib, shape):
 
 
 def test_kmeans_clusters_golden(cuda_lib, golden_clusters):
-    """compute_clusters(n_clusters=3) on the GPU: same seeding and trajectory as the oracle restatement (centroids
-    in the same order, 1e-5), the reference's (scikit-learn's) centroids up to order within a class, the reference's
-    head output over them, and closest=True rows."""
+    """compute_clusters(n_clusters > 1) on the GPU follows scikit-learn's seeding stream and stopping rule: the
+    REFERENCE's centroids row for row — on unambiguous clusters (k3) and on heavily overlapping ones (amb2 / amb4),
+    where the answer depends on the seeding — plus the reference's head output over them, and closest=True rows."""
     from nwhead_b200 import NWHead, compute_clusters, get_kernel
 
     g = golden_clusters
+    for tag, ka in (("amb2", 2), ("amb4", 4)):
+        fa, ya = torch.from_numpy(g[f"{tag}_f"]).to(DEV), torch.from_numpy(g[f"{tag}_y"]).to(DEV)
+        ca, cya = compute_clusters(fa, ya, ka)
+        assert np.array_equal(cya.cpu().numpy(), g[f"{tag}_cy"])
+        err = np.abs(ca.cpu().numpy() - g[f"{tag}_cf"]).max(axis=1).reshape(-1, ka).max(axis=1)   # per class
+        assert (err < 1e-4).all(), f"{tag}: classes off the reference's centroids: {np.flatnonzero(err >= 1e-4)} {err}"
+        gap = O.kmeans_inertia(g[f"{tag}_f"], g[f"{tag}_y"], ca.cpu().numpy(), ka) / \
+            O.kmeans_inertia(g[f"{tag}_f"], g[f"{tag}_y"], g[f"{tag}_cf"], ka)
+        assert np.abs(gap - 1).max() < 1e-5
     k = 3
     f, y = torch.from_numpy(g["k3_f"]).to(DEV), torch.from_numpy(g["k3_y"]).to(DEV)
     cf, cy = compute_clusters(f, y, k)
     assert np.array_equal(cy.cpu().numpy(), g["k3_cy"])
     oc, _ = O.kmeans_centroids(g["k3_f"], g["k3_y"], k)
     assert np.abs(cf.cpu().numpy() - oc).max() < 1e-5
-    assert O.match_centroid_sets(cf.cpu().numpy(), g["k3_cf"], k) < 1e-5
+    assert np.abs(cf.cpu().numpy() - g["k3_cf"]).max() < 1e-5
     logp = NWHead(get_kernel("euclidean"), 7)(torch.from_numpy(g["k3_q"]).to(DEV), cf, cy)
     assert np.abs(np.exp(logp.cpu().numpy()) - np.exp(g["k3_logp"])).max() < 1e-5
     cl, cly = compute_clusters(f, y, k, closest=True)
@@ -96,8 +105,9 @@ def test_kmeans_clusters_golden(cuda_lib, golden_clusters):
 
 @pytest.mark.parametrize("shape", [(4000, 64, 12, 4), (3000, 30, 5, 11), (20000, 2048, 8, 2)])
 def test_kmeans_clusters_against_oracle(cuda_lib, shape):
-    """Overlapping clusters, unsorted labels, d not a multiple of 4, k > 8 (two centroid passes): the GPU run follows
-    the oracle's trajectory (same seeding draws), so the centroids agree row for row; the objective is not worse."""
+    """Overlapping clusters, unsorted labels, d not a multiple of 4, k > 8 (two centroid passes), d = 2048: the GPU
+    run follows the oracle's (scikit-learn's) seeding and trajectory, so the centroids agree row for row except
+    where a fp32-vs-float64 near-tie flipped a row and let the trajectories part; the objective may not suffer."""
     from nwhead_b200 import compute_clusters
 
     N, d, C, k = shape
@@ -109,18 +119,10 @@ def test_kmeans_clusters_against_oracle(cuda_lib, shape):
     cf = cf.cpu().numpy()
     oc, oy = O.kmeans_centroids(f, y, k)
     assert np.array_equal(cy.cpu().numpy(), oy)
-
-    def inertia(cent):
-        tot = 0.0
-        for i, c in enumerate(np.unique(y)):
-            x = f[y == c].astype(np.float64)
-            tot += ((x[:, None] - cent[i * k:(i + 1) * k][None]) ** 2).sum(-1).min(1).sum()
-        return tot
-
-    # fp32-vs-float64 near-ties may flip single rows and let the trajectories part; the objective may not suffer
-    assert inertia(cf.astype(np.float64)) <= inertia(oc) * (1 + 1e-3)
-    if d <= 64:
-        assert np.abs(cf - oc).max() < 1e-4
+    ratio = O.kmeans_inertia(f, y, cf, k) / O.kmeans_inertia(f, y, oc, k)
+    assert (ratio <= 1 + 1e-3).all(), ratio
+    same = np.abs(cf - oc).max(axis=1).reshape(-1, k).max(axis=1) < 1e-4
+    assert same.mean() >= 0.75, f"only {same.sum()} of {len(same)} classes follow the oracle's trajectory"
 
 
 def test_support_influence_golden(cuda_lib, golden_influence):

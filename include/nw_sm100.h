@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NW_ABI_VERSION 1
+#define NW_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NW_API __attribute__((visibility("default")))
@@ -252,7 +252,7 @@ NW_API int nw_direct_forward(int kind, float scale, const float* q, int n_query,
  * grad_q (B, d) and grad_s ((N, d) or (B, N, d)) may each be NULL when not needed.
  * grad_scale_rows (B) receives per-query partial sums of d/d(logit_scale) for NW_KIND_CLIP (may be
  * NULL).  Coincident points contribute zero gradient, as torch.cdist's backward does. */
-NW_API int64_t nw_direct_backward_workspace_elems(int n_query, int64_t n_support, int support_batched);
+NW_API int64_t nw_direct_backward_workspace_elems(int n_query, int d, int64_t n_support, int support_batched);
 NW_API int nw_direct_backward(int kind, float scale, const float* q, int n_query, int d, const float* s,
                        int64_t n_support, int support_batched, const int64_t* labels, int labels_batched,
                        int n_classes, const float* scores, const float* row_lse, const float* logp,

@@ -74,7 +74,7 @@ SIGNATURES = {
                                     c_void_p, c_void_p]),
     "nw_direct_forward": (c_int, [c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p, c_int,
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "nw_direct_backward_workspace_elems": (c_int64, [c_int, c_int64, c_int]),
+    "nw_direct_backward_workspace_elems": (c_int64, [c_int, c_int, c_int64, c_int]),
     "nw_direct_backward": (c_int, [c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p,
                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
@@ -152,7 +152,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.nw_abi_version() != 1:
+    if lib.nw_abi_version() != 2:
         raise NWLibraryError("libnw_sm100.so ABI version mismatch")
     _lib = _DeviceBoundLib(lib)
     return _lib

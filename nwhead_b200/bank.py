@@ -436,6 +436,33 @@ class SupportBank:
         """log(softmax-weighted label aggregation + 1e-12): NWHead.forward (nwhead/nw.py:266-289)."""
         return logp_from_class_lse(self.class_lse(q, scale))
 
+    # Small banks (cluster centroids, CUB-sized full banks) make predict launch-bound: five kernel launches and four
+    # ctypes calls for a few microseconds of GPU work.  forward_auto replays the step as ONE CUDA graph once the same
+    # (batch, scale) has been seen twice on this bank; the result is copied out of the graph's static buffer, so it
+    # is an ordinary tensor.  NW_B200_GRAPHS=0 switches it off.
+    GRAPH_MAX_BANK_ELEMS = 1 << 24
+    GRAPH_MAX_BATCH = 8192
+    GRAPH_CACHE = 4
+
+    def forward_auto(self, q: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        b = q.shape[0]
+        if (len(self) * self.row_elems > self.GRAPH_MAX_BANK_ELEMS or not 0 < b <= self.GRAPH_MAX_BATCH
+                or q.dtype != torch.float32 or q.dim() != 2 or q.shape[1] != self.d
+                or self.device.index != torch.cuda.current_device()
+                or torch.cuda.is_current_stream_capturing() or os.environ.get("NW_B200_GRAPHS", "1") == "0"):
+            return self.forward(q, scale)
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        key = (b, float(scale))
+        entry = cache.get(key)
+        if entry is None:
+            if len(cache) >= self.GRAPH_CACHE:
+                cache.pop(next(iter(cache)))
+            cache[key] = 1                       # seen once: capture on the next call with this shape
+            return self.forward(q, scale)
+        if entry == 1:
+            entry = cache[key] = GraphedForward(self, b, scale)
+        return entry(q).clone()
+
 
 class GraphedForward:
     """SupportBank.forward for a fixed batch size captured in a CUDA graph: query prep, -inf fill, fused forward,

@@ -279,6 +279,43 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const float* __restrict_
   }
 }
 
+// Same result for LONG rows (n_support > AGG_BINS_MIN_N): the per-class loop above is O(N * C / 256) per thread
+// (seconds at N = 1.28M, C = 1000); here every thread walks its supports once and adds exp(score - max) into a
+// shared-memory class bin.  The float atomics make the summation order — not the value beyond the last bits — vary
+// from run to run; short rows keep the fixed-order loop.
+constexpr int AGG_BINS_MIN_N = 4096;
+constexpr int AGG_BINS_MAX_C = 8192;
+
+__global__ void __launch_bounds__(256) aggregate_bins_kernel(const float* __restrict__ scores,
+                                                             const int64_t* __restrict__ labels, int labels_batched,
+                                                             long long n_support, int n_classes,
+                                                             float* __restrict__ logp, float* __restrict__ row_lse,
+                                                             int32_t* __restrict__ status) {
+  extern __shared__ float bins[];  // n_classes floats
+  __shared__ float red[8];
+  const long long b = blockIdx.x;
+  const float* sc = scores + b * n_support;
+  const int64_t* lab = labels + (labels_batched ? b * n_support : 0);
+  for (int c = threadIdx.x; c < n_classes; c += blockDim.x) bins[c] = 0.f;
+  float mx = __int_as_float(0xff800000);
+  for (long long j = threadIdx.x; j < n_support; j += blockDim.x) mx = fmaxf(mx, sc[j]);
+  mx = block_max(mx, red);  // (its barriers also publish the zeroed bins)
+  float sum = 0.f;
+  bool bad = false;
+  for (long long j = threadIdx.x; j < n_support; j += blockDim.x) {
+    const float e = expf(sc[j] - mx);
+    sum += e;
+    const long long y = lab[j];
+    if (y >= 0 && y < n_classes) atomicAdd(&bins[y], e);
+    else bad = true;
+  }
+  if (bad) *reinterpret_cast<volatile int32_t*>(status) = 1;
+  sum = block_sum(sum, red);
+  if (threadIdx.x == 0) row_lse[b] = mx + logf(sum);
+  const float inv = 1.0f / sum;
+  for (int c = threadIdx.x; c < n_classes; c += blockDim.x) logp[b * n_classes + c] = logf(bins[c] * inv + 1e-12f);
+}
+
 // one block per query: coef[b,j] = dL/dscore[b,j] (linear kinds, times scale) or dL/dscore / dist (euclid kinds)
 __global__ void __launch_bounds__(256) coef_kernel(int kind, float scale, const float* __restrict__ scores,
                                                    const float* __restrict__ row_lse,
@@ -401,6 +438,128 @@ __global__ void __launch_bounds__(256) grad_s_shared_kernel(int kind, const floa
     }
   } else {
     for (int c = threadIdx.x; c < d; c += blockDim.x) grad_s[j * d + c] = row[c];
+  }
+}
+
+// ---- large shared supports: grad_q as a split reduction -------------------------------------------------------
+// grad_q_kernel above gives every query ONE block that walks all N supports: B blocks on a 148-SM GPU, each
+// streaming the whole support (100 ms at N = 1.28M, d = 2048, B = 8).  Here a block owns a chunk of GQ_CHUNK
+// supports and 256 columns and accumulates A[b, c] = sum_j w'[b, j] s[j, c] for GQ_BT queries at a time
+// (w' = coef, times 1/|s_j| for the normalised kinds), so the support is read from HBM once; the per-chunk partials
+// are summed in chunk order by grad_q_finish_kernel (deterministic), which also applies the euclidean "- rowsum(R) q"
+// term and the normalisation Jacobian exactly as grad_q_kernel does.
+constexpr int GQ_CHUNK = 1024;
+constexpr int GQ_BT = 8;
+
+__global__ void __launch_bounds__(256) grad_q_split_kernel(const float* __restrict__ s, long long n_support, int d,
+                                                           const float* __restrict__ coef,
+                                                           const float* __restrict__ inv_s, int n_query,
+                                                           float* __restrict__ partial) {
+  __shared__ float w[GQ_BT][GQ_CHUNK];
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  const long long j0 = (long long)blockIdx.x * GQ_CHUNK;
+  const int nj = int(min((long long)GQ_CHUNK, n_support - j0));
+  for (int b0 = 0; b0 < n_query; b0 += GQ_BT) {
+    const int nb = min(GQ_BT, n_query - b0);
+    for (int i = threadIdx.x; i < GQ_BT * GQ_CHUNK; i += 256) {
+      const int t = i / GQ_CHUNK, j = i - t * GQ_CHUNK;
+      float v = 0.f;
+      if (t < nb && j < nj) {
+        v = coef[(long long)(b0 + t) * n_support + j0 + j];
+        if (inv_s) v *= inv_s[j0 + j];
+      }
+      w[t][j] = v;
+    }
+    __syncthreads();
+    if (c < d) {
+      float acc[GQ_BT];
+#pragma unroll
+      for (int t = 0; t < GQ_BT; ++t) acc[t] = 0.f;
+      const float* sp = s + j0 * d + c;
+#pragma unroll 4
+      for (int j = 0; j < nj; ++j) {
+        const float sv = __ldcs(sp + (long long)j * d);
+#pragma unroll
+        for (int t = 0; t < GQ_BT; ++t) acc[t] = fmaf(w[t][j], sv, acc[t]);
+      }
+      for (int t = 0; t < nb; ++t) partial[((long long)blockIdx.x * n_query + b0 + t) * d + c] = acc[t];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) grad_q_finish_kernel(int kind, const float* __restrict__ q, int d,
+                                                            long long n_support, const float* __restrict__ coef,
+                                                            const float* __restrict__ inv_q,
+                                                            const float* __restrict__ partial, int n_chunks,
+                                                            int n_query, float* __restrict__ grad_q) {
+  extern __shared__ float row[];  // d floats
+  __shared__ float red[8];
+  const long long b = blockIdx.x;
+  const bool norm = kind_normalised(kind);
+  const bool euc = kind_euclid(kind);
+  const float iq = norm ? inv_q[b] : 1.0f;
+  float csum = 0.f;
+  if (euc) {
+    const float* cf = coef + b * n_support;
+    for (long long j = threadIdx.x; j < n_support; j += 256) csum += cf[j];
+    csum = block_sum(csum, red);
+  }
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < d; c += 256) {
+    float acc = 0.f;
+    for (int g = 0; g < n_chunks; ++g) acc += partial[((long long)g * n_query + b) * d + c];
+    const float qv = q[b * d + c] * iq;
+    if (euc) acc -= csum * qv;  // sum_j r_bj (s_j - q_b)
+    row[c] = acc;
+    dot += acc * qv;
+  }
+  if (norm) {
+    dot = block_sum(dot, red);
+    for (int c = threadIdx.x; c < d; c += 256) grad_q[b * d + c] = (row[c] - dot * (q[b * d + c] * iq)) * iq;
+  } else {
+    for (int c = threadIdx.x; c < d; c += 256) grad_q[b * d + c] = row[c];
+  }
+}
+
+// grad_s for a shared support, several rows per block: grad_s_shared_kernel launches one 256-thread block per
+// support row for 64 FMAs per thread; with millions of rows the block turnover, not HBM, was the bound.
+constexpr int GS_ROWS = 16;
+
+__global__ void __launch_bounds__(256) grad_s_rows_kernel(int kind, const float* __restrict__ q, int n_query, int d,
+                                                          const float* __restrict__ s, long long n_support,
+                                                          const float* __restrict__ coef,
+                                                          const float* __restrict__ inv_q,
+                                                          const float* __restrict__ inv_s,
+                                                          float* __restrict__ grad_s) {
+  extern __shared__ float row[];  // d floats
+  __shared__ float red[8];
+  const bool norm = kind_normalised(kind);
+  const bool euc = kind_euclid(kind);
+  const long long j_end = min((long long)(blockIdx.x + 1) * GS_ROWS, n_support);
+  for (long long j = (long long)blockIdx.x * GS_ROWS; j < j_end; ++j) {
+    const float is = norm ? inv_s[j] : 1.0f;
+    float dot = 0.f;
+    for (int c = threadIdx.x; c < d; c += 256) {
+      const float sv = s[j * d + c] * is;
+      float acc = 0.f, csum = 0.f;
+      for (int b = 0; b < n_query; ++b) {
+        const float w = coef[(long long)b * n_support + j];
+        const float qv = q[(long long)b * d + c] * (norm ? inv_q[b] : 1.0f);
+        acc = fmaf(w, qv, acc);
+        csum += w;
+      }
+      if (euc) acc -= csum * sv;  // sum_b r_bj (q_b - s_j)
+      row[c] = acc;
+      dot += acc * sv;
+    }
+    if (norm) {
+      dot = block_sum(dot, red);
+      for (int c = threadIdx.x; c < d; c += 256) grad_s[j * d + c] = (row[c] - dot * (s[j * d + c] * is)) * is;
+      __syncthreads();  // row[] and red[] are reused by the next support row
+    } else {
+      for (int c = threadIdx.x; c < d; c += 256) grad_s[j * d + c] = row[c];
+    }
   }
 }
 
@@ -720,8 +879,12 @@ extern "C" int nw_direct_aggregate(const float* scores, const int64_t* labels, i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NW_REQUIRE(scores && labels && logp && row_lse && status_out, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(n_query > 0 && n_support > 0 && n_classes > 0, NW_ERR_INVALID, "shapes must be positive");
-  direct::aggregate_kernel<<<n_query, 256, 0, stream>>>(scores, labels, labels_batched, n_support, n_classes, logp,
-                                                        row_lse, status_out);
+  if (n_support > direct::AGG_BINS_MIN_N && n_classes <= direct::AGG_BINS_MAX_C)
+    direct::aggregate_bins_kernel<<<n_query, 256, n_classes * sizeof(float), stream>>>(
+        scores, labels, labels_batched, n_support, n_classes, logp, row_lse, status_out);
+  else
+    direct::aggregate_kernel<<<n_query, 256, 0, stream>>>(scores, labels, labels_batched, n_support, n_classes, logp,
+                                                          row_lse, status_out);
   NW_CUDA_OK(cudaGetLastError());
   return NW_OK;
 }
@@ -744,15 +907,18 @@ extern "C" int nw_direct_forward(int kind, float scale, const float* q, int n_qu
   }
   rc = nw_direct_scores(kind, scale, q, n_query, d, s, n_support, support_batched, scores, stream_);
   if (rc != NW_OK) return rc;
-  direct::aggregate_kernel<<<n_query, 256, 0, stream>>>(scores, labels, labels_batched, n_support, n_classes, logp,
-                                                        row_lse, status_flag);
-  NW_CUDA_OK(cudaGetLastError());
-  return NW_OK;
+  return nw_direct_aggregate(scores, labels, labels_batched, n_query, n_support, n_classes, logp, row_lse, status_flag,
+                             stream_);
 }
 
-extern "C" int64_t nw_direct_backward_workspace_elems(int n_query, int64_t n_support, int support_batched) {
+// workspace: coefficients (B*N) | 1/|s| (N or B*N) | 1/|q| (B) | split grad_q partials [chunk][query][d] (large
+// shared supports only)
+extern "C" int64_t nw_direct_backward_workspace_elems(int n_query, int d, int64_t n_support, int support_batched) {
   const int64_t pairs = int64_t(n_query) * n_support;
-  return pairs + (support_batched ? pairs : n_support) + n_query;
+  int64_t elems = pairs + (support_batched ? pairs : n_support) + n_query;
+  if (!support_batched && n_support > direct::SMALL_N)
+    elems += ceil_div_ll(n_support, direct::GQ_CHUNK) * int64_t(n_query) * d;
+  return elems;
 }
 
 extern "C" int nw_direct_backward(int kind, float scale, const float* q, int n_query, int d, const float* s,
@@ -799,6 +965,7 @@ extern "C" int nw_direct_backward(int kind, float scale, const float* q, int n_q
   }
   float* inv_s = workspace + pairs;
   float* inv_q = inv_s + (support_batched ? pairs : n_support);
+  float* split_workspace = (!support_batched && n_support > direct::SMALL_N) ? inv_q + n_query : nullptr;
   const bool norm = direct::kind_normalised(kind);
   if (norm) {
     const long long srows = support_batched ? pairs : n_support;
@@ -811,8 +978,19 @@ extern "C" int nw_direct_backward(int kind, float scale, const float* q, int n_q
       kind == NW_KIND_CLIP ? grad_scale_rows : nullptr);
   NW_CUDA_OK(cudaGetLastError());
   if (grad_q) {
-    direct::grad_q_kernel<<<n_query, 256, d * sizeof(float), stream>>>(kind, q, d, s, n_support, support_batched,
-                                                                       coef, inv_q, inv_s, grad_q);
+    if (!support_batched && split_workspace != nullptr) {
+      // large shared support: split reduction over support chunks (the support is read from HBM once)
+      const int n_chunks = int(ceil_div_ll(n_support, direct::GQ_CHUNK));
+      dim3 grid(n_chunks, ceil_div(d, 256));
+      direct::grad_q_split_kernel<<<grid, 256, 0, stream>>>(s, n_support, d, coef, norm ? inv_s : nullptr, n_query,
+                                                            split_workspace);
+      NW_CUDA_OK(cudaGetLastError());
+      direct::grad_q_finish_kernel<<<n_query, 256, d * sizeof(float), stream>>>(
+          kind, q, d, n_support, coef, inv_q, split_workspace, n_chunks, n_query, grad_q);
+    } else {
+      direct::grad_q_kernel<<<n_query, 256, d * sizeof(float), stream>>>(kind, q, d, s, n_support, support_batched,
+                                                                         coef, inv_q, inv_s, grad_q);
+    }
     NW_CUDA_OK(cudaGetLastError());
   }
   if (grad_s) {
@@ -820,7 +998,7 @@ extern "C" int nw_direct_backward(int kind, float scale, const float* q, int n_q
       direct::grad_s_batched_kernel<<<unsigned(pairs), 128, 0, stream>>>(kind, q, d, s, n_support, coef, inv_q,
                                                                          inv_s, grad_s);
     else
-      direct::grad_s_shared_kernel<<<unsigned(n_support), 256, d * sizeof(float), stream>>>(
+      direct::grad_s_rows_kernel<<<unsigned(ceil_div_ll(n_support, direct::GS_ROWS)), 256, d * sizeof(float), stream>>>(
           kind, q, n_query, d, s, n_support, coef, inv_q, inv_s, grad_s);
     NW_CUDA_OK(cudaGetLastError());
   }

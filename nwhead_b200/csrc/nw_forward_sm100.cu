@@ -172,7 +172,7 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
       acc[i] = fmaf(-2.0f, acc[i], qn + cadd[i]);  // squared distance
       dmin = fminf(dmin, acc[i]);
     }
-    mx = -sqrt_approx(fmaxf(dmin, 0.0f)) * kLog2e;
+    mx = neg_dist_log2e(dmin);
   } else {
     mx = __int_as_float(0xff800000);
 #pragma unroll
@@ -190,7 +190,7 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       float e;
-      if (EPI == NW_EPI_EUCLID) e = ex2_approx(fmaf(sqrt_approx(fmaxf(acc[i], 0.0f)), -kLog2e, -m));
+      if (EPI == NW_EPI_EUCLID) e = ex2_approx(neg_dist_log2e(acc[i]) - m);
       else e = ex2_approx(acc[i] - m);
       part[i & 3] += e;
     }
@@ -199,7 +199,7 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       float arg;  // score * log2(e) - m
-      if (EPI == NW_EPI_EUCLID) arg = fmaf(sqrt_approx(fmaxf(acc[i], 0.0f)), -kLog2e, -m);
+      if (EPI == NW_EPI_EUCLID) arg = neg_dist_log2e(acc[i]) - m;
       else arg = acc[i] - m;
       l += ex2_approx(arg);
       if (emask & (1u << i)) {  // warp-uniform: column i is the last row of its class (in this unit)

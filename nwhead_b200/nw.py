@@ -85,7 +85,10 @@ class _NWDirectFunction(torch.autograd.Function):
         guard.check()
         logp = torch.empty((b, n_classes), dtype=torch.float32, device=dev)
         # scratch: scores (b*n) | row_lse (b) | backward workspace (nw_direct_backward_workspace_elems)
-        ws = pairs + (pairs if batched else n) + b if any(ctx.needs_input_grad) else 0
+        ws = 0
+        if any(ctx.needs_input_grad):  # nw_direct_backward_workspace_elems; the episodic case needs no library call
+            ws = (pairs + (pairs if batched else n) + b if n <= 1024 else
+                  lib.nw_direct_backward_workspace_elems(b, d, n, int(batched)))
         aux = torch.empty((pairs + b + ws,), dtype=torch.float32, device=dev)
         p_aux = aux.data_ptr()
         check(lib.nw_direct_forward(KIND[kind], scale, xq.data_ptr(), b, d, sxd.data_ptr(), n, int(batched),
@@ -184,7 +187,7 @@ class NWHead(nn.Module):
             if torch.is_grad_enabled() and x.requires_grad:
                 raise RuntimeError("a SupportBank is inference-only; pass the raw (sx, sy) support tensors for a "
                                    "differentiable call (NWNet.predict does this automatically)")
-            return sx.forward(x, self.kernel.scale_value())
+            return sx.forward_auto(x, self.kernel.scale_value())
         _abi.require_cuda(x, sx, sy)
         if sx.dtype in _HALF_DTYPES:
             sx = sx.float()

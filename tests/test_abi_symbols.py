@@ -42,16 +42,18 @@ def test_ctypes_table_matches_header():
 
 def test_pure_host_entry_points(lib):
     lib.nw_row_elems.restype = ctypes.c_int
-    assert lib.nw_abi_version() == 1
+    assert lib.nw_abi_version() == 2
     assert lib.nw_row_elems(2048, 1) == 2048
     assert lib.nw_row_elems(512, 3) == 1536
     assert lib.nw_row_elems(16, 1) == 64
     assert lib.nw_row_elems(100, 3) == 320
     assert lib.nw_row_elems(0, 1) < 0 and lib.nw_row_elems(8, 2) < 0
     lib.nw_direct_backward_workspace_elems.restype = ctypes.c_int64
-    lib.nw_direct_backward_workspace_elems.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int]
-    assert lib.nw_direct_backward_workspace_elems(8, 10, 0) == 80 + 10 + 8
-    assert lib.nw_direct_backward_workspace_elems(8, 10, 1) == 80 + 80 + 8
+    lib.nw_direct_backward_workspace_elems.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int]
+    assert lib.nw_direct_backward_workspace_elems(8, 512, 10, 0) == 80 + 10 + 8
+    assert lib.nw_direct_backward_workspace_elems(8, 512, 10, 1) == 80 + 80 + 8
+    # large shared support: + the split grad_q partials, one (8, 512) slab per chunk of 1024 supports
+    assert lib.nw_direct_backward_workspace_elems(8, 512, 5000, 0) == 8 * 5000 + 5000 + 8 + 5 * 8 * 512
 
 
 def test_errors_are_reported_not_swallowed(lib):

@@ -35,6 +35,29 @@ def main():
             print(f"dense scores alone {t_sc:.1f} ms = {2e-9 * b * n * d / t_sc:.1f} TFLOP/s (sub+fma per element)", flush=True)
         print(f"{prec}: N={n} d={d} B={b} k={k}  topk_exact {t_fast:.1f} ms (block_best {t_bb:.1f} ms)  "
               f"dense {t_dense:.1f} ms  equal={torch.equal(got, want)} paths={bank.last_topk_path}", flush=True)
+        # where the rest goes: block ranking, gathers, residuals, the refinement kernel
+        from nwhead_b200._abi import check, load, ptr, stream_of
+        lib = load()
+        best, q_sq = bb
+        nblk = best.shape[1]
+        width = min(nblk, max(65, k))
+        order, t_rank = timed(lambda: rank_rows(best, width))
+        sorted_best, t_gather = timed(lambda: best.gather(1, order))
+        resid_q, t_resid = timed(lambda: bank.rounding_residual(q))
+        done = torch.zeros(b, dtype=torch.int32, device=dev)
+        out = torch.empty((b, k), dtype=torch.int64, device=dev)
+        pending = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def refine():
+            done.zero_()
+            check(lib.nw_topk_refine(ptr(q), b, d, ptr(feats), n, ptr(bank.perm), ptr(order), ptr(sorted_best), width,
+                                     min(64, nblk), nblk, k, ptr(q_sq), ptr(resid_q), ptr(bank._smax_sq),
+                                     ptr(bank._resid_of[2]), bank.precision, ptr(done), ptr(out), ptr(pending),
+                                     stream_of(dev)), "nw_topk_refine")
+
+        _, t_refine = timed(refine)
+        print(f"    breakdown: block ranking {t_rank:.2f} ms, gather {t_gather:.2f} ms, query residual {t_resid:.2f} ms, "
+              f"refine kernel {t_refine:.2f} ms", flush=True)
         del bank
 
 

@@ -265,7 +265,7 @@ __global__ void rank_emit_kernel(const uint64_t* __restrict__ keys, long long pa
 // no host round trip; every query sizes its own candidate budget m <= m_cap from the same bounds; uncertified queries
 // are only counted (the caller takes the dense path for them).
 // ---------------------------------------------------------------------------------------------
-constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_THREADS = 1024;  // 32 warps x 16 row-slab loads in flight: the gather is HBM-latency bound otherwise
 constexpr int TOPK_ROWS_PER_WARP = 4;  // candidate rows a warp scores together: 4 independent load streams
 
 __device__ __forceinline__ float key_score(uint64_t key) {

@@ -277,26 +277,8 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float rsqrt_approx(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// -log2(e) * sqrt(max(d2, 0)) for the exp2-domain softmax of euclidean scores.  MUFU.SQRT occupies the MUFU pipe for
-// two issue slots on sm_100 (measured: the d = 512 forward sat at 60 % MUFU instruction rate with the tensor pipe
-// at 58 %, and more epilogue warps did not help), MUFU.RSQ for one: sqrt(x) = x * rsqrt(x) with x clamped to a
-// tiny positive value (a zero distance gives 1e-15, which the softmax cannot tell from 0).
-#ifndef NW_EPI_RSQRT
-#define NW_EPI_RSQRT 1
-#endif
-__device__ __forceinline__ float neg_dist_log2e(float d2) {
-#if NW_EPI_RSQRT
-  const float t = fmaxf(d2, 1e-30f);
-  return t * (rsqrt_approx(t) * -kLog2e);
-#else
-  return sqrt_approx(fmaxf(d2, 0.0f)) * -kLog2e;
-#endif
-}
+// (x * rsqrt(x) instead of sqrt(x) was measured at d = 512 on the same box: 1124 vs 1141 TFLOP/s — MUFU.SQRT is
+//  not the slower instruction, and the extra FMUL costs an issue slot; sqrt.approx stays.)
 // support influence of one (query, support) pair — reference util/metric.py:47:
 //   log((p - p*w) / (p - w*indicator)), IEEE division, +inf / nan preserved.
 // The ratio is 1 + x with x = w*(indicator - p) / (p - w*indicator); for the usual |x| << 1 (w ~ 1/N) the log1p

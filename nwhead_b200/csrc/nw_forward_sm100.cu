@@ -68,7 +68,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 };
 
-struct TileMeta {
+struct __align__(16) TileMeta {
   float cadd[BN];    // per-column additive term: |s|^2 (EUCLID) or 0 (LINEAR); +inf / -inf for padding columns
   int lab[BN + 8];   // labels of the tile's columns plus one look-ahead entry
 };
@@ -160,19 +160,82 @@ struct Flusher {
 };
 
 // One 32-column chunk of the accumulator for one query row.
+//
+// The epilogue is instruction-issue bound for short GEMMs (ncu at d = 512: ~11 thread instructions per score, issue
+// slots 40 % busy with the fixed-latency `wait` stall on top, MUFU 60 %, tensor pipe 58 %; neither more epilogue
+// warps nor a cheaper square root moved it), so the common path is written for few instructions per score:
+//   * the running maximum m is LAZY.  exp2(score - m) only needs m close to the true maximum, not equal to it
+//     (scores above m give terms > 1, which fp32 holds up to 2^127), so a chunk is summed against the current m
+//     right away and m is raised — with the exact chunk maximum, and the open sum rescaled — only when the chunk
+//     sum says a score exceeded m by more than ~15 in the exp2 domain (or m is still -inf: the first chunk).
+//     This removes the per-chunk min/max pass and the sqrt -> compare -> exp2 chain every chunk used to start with;
+//   * sqrt(|d2|) instead of sqrt(max(d2, 0)): the absolute value is a free operand modifier of MUFU.SQRT, and a
+//     slightly negative d2 (rounding of near-duplicates) is as close to zero either way;
+//   * the per-column additive terms are read as float4.
+// Chunks in which a class ends (warp-uniform, 1 in ~40 at 1280 rows per class) take the exact-maximum path.
+constexpr float kRaiseMax = 1048576.0f;  // chunk sum above which m is raised (some term exceeded 2^15)
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __restrict__ cadd,
                                                const int* __restrict__ lab, uint32_t emask, float qn,
                                                float scale2, float& m, float& l, const Flusher& flush) {
+  const float4* __restrict__ cadd4 = reinterpret_cast<const float4*>(cadd);
+  if (emask == 0u) {  // warp-uniform fast path: no class ends inside this chunk
+    float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // four independent partial sums: no 32-long FADD chain
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+      const float4 c = cadd4[i4];
+      const float cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i4 * 4 + k;
+        if (EPI == NW_EPI_EUCLID) {
+          acc[i] = sqrt_approx(fabsf(fmaf(-2.0f, acc[i], qn + cc[k])));  // distance (kept for a possible redo)
+          part[k] += ex2_approx(fmaf(acc[i], -kLog2e, -m));
+        } else {
+          acc[i] = fmaf(acc[i], scale2, cc[k]);  // score * log2(e)  (or -inf on padding columns)
+          part[k] += ex2_approx(acc[i] - m);
+        }
+      }
+    }
+    float sum = (part[0] + part[1]) + (part[2] + part[3]);
+    if (!(sum < kRaiseMax)) {  // rare (also inf / NaN while m is -inf): raise m to the exact maximum and redo
+      float mx;
+      if (EPI == NW_EPI_EUCLID) {
+        float dmin = acc[0];
+#pragma unroll
+        for (int i = 1; i < 32; ++i) dmin = fminf(dmin, acc[i]);
+        mx = -dmin * kLog2e;
+      } else {
+        mx = acc[0];
+#pragma unroll
+        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, acc[i]);
+      }
+      if (mx > m) {
+        l *= ex2_approx(m - mx);
+        m = mx;
+      }
+      float p2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (EPI == NW_EPI_EUCLID) p2[i & 3] += ex2_approx(fmaf(acc[i], -kLog2e, -m));
+        else p2[i & 3] += ex2_approx(acc[i] - m);
+      }
+      sum = (p2[0] + p2[1]) + (p2[2] + p2[3]);
+    }
+    l += sum;
+    return;
+  }
+  // a class ends inside this chunk: exact chunk maximum first, then column by column with flushes
   float mx;
   if (EPI == NW_EPI_EUCLID) {
     float dmin = __int_as_float(0x7f800000);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      acc[i] = fmaf(-2.0f, acc[i], qn + cadd[i]);  // squared distance
+      acc[i] = fabsf(fmaf(-2.0f, acc[i], qn + cadd[i]));  // squared distance
       dmin = fminf(dmin, acc[i]);
     }
-    mx = neg_dist_log2e(dmin);
+    mx = -sqrt_approx(dmin) * kLog2e;
   } else {
     mx = __int_as_float(0xff800000);
 #pragma unroll
@@ -185,33 +248,21 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
     l *= ex2_approx(m - mx);
     m = mx;
   }
-  if (emask == 0u) {  // warp-uniform fast path: no class ends inside this chunk
-    float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // four independent partial sums: no 32-long FADD chain
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float e;
-      if (EPI == NW_EPI_EUCLID) e = ex2_approx(neg_dist_log2e(acc[i]) - m);
-      else e = ex2_approx(acc[i] - m);
-      part[i & 3] += e;
-    }
-    l += (part[0] + part[1]) + (part[2] + part[3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float arg;  // score * log2(e) - m
-      if (EPI == NW_EPI_EUCLID) arg = neg_dist_log2e(acc[i]) - m;
-      else arg = acc[i] - m;
-      l += ex2_approx(arg);
-      if (emask & (1u << i)) {  // warp-uniform: column i is the last row of its class (in this unit)
-        if (i > 0 && (emask & (1u << (i - 1))) && !(flush.tail_cut && lab[i] == flush.cl)) {
-          // the previous column closed its class too, so this class has ONE row here (cluster / random mode
-          // banks: one support per class): its log-sum-exp is simply its score; stored inline, no call
-          flush.single(lab[i], (arg + m) * kLn2);
-        } else {
-          flush(lab[i], m, l);
-        }
-        l = 0.0f;
+  for (int i = 0; i < 32; ++i) {
+    float arg;  // score * log2(e) - m
+    if (EPI == NW_EPI_EUCLID) arg = fmaf(sqrt_approx(acc[i]), -kLog2e, -m);
+    else arg = acc[i] - m;
+    l += ex2_approx(arg);
+    if (emask & (1u << i)) {  // warp-uniform: column i is the last row of its class (in this unit)
+      if (i > 0 && (emask & (1u << (i - 1))) && !(flush.tail_cut && lab[i] == flush.cl)) {
+        // the previous column closed its class too, so this class has ONE row here (cluster / random mode
+        // banks: one support per class): its log-sum-exp is simply its score; stored inline, no call
+        flush.single(lab[i], (arg + m) * kLn2);
+      } else {
+        flush(lab[i], m, l);
       }
+      l = 0.0f;
     }
   }
 }

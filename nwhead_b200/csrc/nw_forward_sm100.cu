@@ -109,6 +109,8 @@ struct Params {
   int tiles_per_chunk;
   float scale_log2;  // LINEAR: scale * log2(e)
   int sets;          // epilogue warp sets (1, 2 or 4); class-LSE with several sets: set s stores to lse[s]
+  int debug_skip_epilogue;  // developer probe (NW_B200_DEBUG_SKIP_EPI=1): accumulators are released unread -> the
+                            // speed of the TMA + MMA mainloop alone (results are garbage)
   // ---- MODE_EMIT only: one output value per (query, support) pair
   float* emit_out;           // (B, ld_out)
   long long emit_ld;
@@ -173,6 +175,9 @@ struct Flusher {
 //     slightly negative d2 (rounding of near-duplicates) is as close to zero either way;
 //   * the per-column additive terms are read as float4.
 // Chunks in which a class ends (warp-uniform, 1 in ~40 at 1280 rows per class) take the exact-maximum path.
+#ifndef NW_EPI_RSQRT
+#define NW_EPI_RSQRT 0
+#endif
 constexpr float kRaiseMax = 1048576.0f;  // chunk sum above which m is raised (some term exceeded 2^15)
 
 template <int EPI>
@@ -190,7 +195,14 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
       for (int k = 0; k < 4; ++k) {
         const int i = i4 * 4 + k;
         if (EPI == NW_EPI_EUCLID) {
+#if NW_EPI_RSQRT  // A/B build only: sqrt(x) as x * rsqrt(x)
+          const float t = fmaxf(fabsf(fmaf(-2.0f, acc[i], qn + cc[k])), 1e-30f);
+          float r;
+          asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+          acc[i] = t * r;
+#else
           acc[i] = sqrt_approx(fabsf(fmaf(-2.0f, acc[i], qn + cc[k])));  // distance (kept for a possible redo)
+#endif
           part[k] += ex2_approx(fmaf(acc[i], -kLog2e, -m));
         } else {
           acc[i] = fmaf(acc[i], scale2, cc[k]);  // score * log2(e)  (or -inf on padding columns)
@@ -607,7 +619,8 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                                   n1 - (j0 + (c + 1) * 32), p.emit_vec != 0);
             continue;
           }
-          if (p.sets >= 2 && ((c >> 1) % p.sets) != eg) continue;  // chunk pairs are dealt round-robin to the sets
+          if (((c >> 1) & (p.sets - 1)) != eg) continue;  // chunk pairs are dealt round-robin to the 1 / 2 / 4 sets
+          if (p.debug_skip_epilogue) continue;
           if (p.sets >= 2) {
             // this set skipped the columns in between: if they ended the class it was accumulating, close its
             // partial now (the other sets close their own; the tables are combined after the kernel)
@@ -1068,6 +1081,13 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.emit_kind = 0;
   p.emit_vec = 0;
   p.clock_probe = (g_clock_probe && plan.grid <= g_clock_probe_ctas) ? g_clock_probe : nullptr;
+  {
+    static const int skip = [] {
+      const char* e = getenv("NW_B200_DEBUG_SKIP_EPI");
+      return e && e[0] == '1' ? 1 : 0;
+    }();
+    p.debug_skip_epilogue = skip;
+  }
   p.row_lse = p.p_query = nullptr;
   p.qlabel = nullptr;
 

@@ -93,9 +93,13 @@ class SupportBank:
     @staticmethod
     def build(feats: torch.Tensor, labels: torch.Tensor, n_classes: int, kind: str = "euclidean",
               precision: str = "auto", center: Optional[torch.Tensor] = None, use_center: bool = True,
-              class_range=None) -> "SupportBank":
+              class_range=None, labels_validated: bool = False) -> "SupportBank":
         """feats (N, d) fp32 CUDA, labels (N,) int64 CUDA (any order).  Raises like F.one_hot
-        (nwhead/nw.py:276) when a label is outside [0, n_classes)."""
+        (nwhead/nw.py:276) when a label is outside [0, n_classes).
+        labels_validated=True: the labels are known to be inside [0, n_classes) (e.g. rows gathered from a bank that
+        was validated when it was built — knn mode builds such a support for every batch): the support is class-
+        sorted unconditionally and NO host synchronisation takes place (the check and the "already sorted?" probe are
+        what needs one: an invalid label must never reach the fused forward's class-indexed stores)."""
         if kind not in KIND:
             raise NotImplementedError(kind)
         dev = _abi.require_cuda(feats, labels)
@@ -116,9 +120,12 @@ class SupportBank:
 
         labels_i32 = torch.empty((n,), dtype=torch.int32, device=dev)
         status = torch.empty((2,), dtype=torch.int32, device=dev)
-        check(lib.nw_labels_to_i32(ptr(labels), None, n, n_classes, ptr(labels_i32), ptr(status), st),
-              "nw_labels_to_i32")
-        bad, descents = status.tolist()
+        if labels_validated:
+            bad, descents = 0, 1
+        else:
+            check(lib.nw_labels_to_i32(ptr(labels), None, n, n_classes, ptr(labels_i32), ptr(status), st),
+                  "nw_labels_to_i32")
+            bad, descents = status.tolist()
         if bad:
             raise RuntimeError("Class values must be smaller than num_classes.")
         perm = None

@@ -117,7 +117,8 @@ class SupportSetEval(SupportSet):
 
     def get_support(self, mode, x=None, raw=False):
         '''Returns the support for an inference mode: a SupportBank for 'full' / 'cluster' / 'random', a list of
-        per-environment SupportBanks for 'ensemble', a (features, labels) pair for 'knn'.
+        per-environment SupportBanks for 'ensemble'; 'knn' / 'hnsw': a SupportBank over the neighbours (a (features,
+        labels) pair when they are fewer than 26).
         raw=True returns the fp32 (features, labels) tensors the banks were built from instead (differentiable
         predict: the direct path needs the unrounded rows).'''
         try:
@@ -133,7 +134,7 @@ class SupportSetEval(SupportSet):
             elif mode == 'cluster':
                 return (self.cluster_feat, self.cluster_y) if raw else self.cluster_bank
             elif mode == 'knn':
-                return self.knn(x)
+                return self.knn(x, None if raw else (self.n_classes, self.kernel_type, self.precision))
             elif mode == 'ensemble':
                 if raw:
                     if self.env_banks is None:
@@ -141,7 +142,7 @@ class SupportSetEval(SupportSet):
                     return list(zip(self.full_feat_sep, self.full_y_sep))
                 return self.env_banks if self.env_banks is not None else [self.full_bank]
             elif mode == 'hnsw':
-                return self.hnsw(x)
+                return self.hnsw(x, None if raw else (self.n_classes, self.kernel_type, self.precision))
             else:
                 raise NotImplementedError
         except AttributeError:

@@ -89,10 +89,13 @@ def test_kernel_modules_return_dense_scores(cuda_lib, golden_head):
 
 
 @pytest.mark.parametrize("kind", ["euclidean", "cosine", "clip", "hypersphere_euclidean", "dotproduct"])
-@pytest.mark.parametrize("shape", [(16, 1500, 48, 20, False), (300, 12, 40, 9, False), (3, 1100, 24, 7, True)])
+@pytest.mark.parametrize("shape", [(16, 1500, 48, 20, False), (300, 12, 40, 9, False), (3, 1100, 24, 7, True),
+                                   (12, 5000, 40, 300, False), (20, 4500, 300, 11, False)])
 def test_large_direct_path_against_oracle(cuda_lib, shape, kind):
     """Shapes that leave the fused small-support kernels (N > 1024 supports, or more than 256 queries):
-    the generic scores / aggregate / coefficient / gradient kernels, forward and backward vs the float64 oracle."""
+    the generic scores / aggregate / coefficient / gradient kernels, forward and backward vs the float64 oracle.
+    N > 1024 shared supports take the split grad_q reduction (several chunks, more than 8 queries, d below and above
+    one 256-column tile) and the multi-row grad_s kernel; N > 4096 the shared-memory class bins of the aggregation."""
     import nwhead_b200
 
     B, N, d, C, batched = shape

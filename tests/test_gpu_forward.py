@@ -317,3 +317,36 @@ def test_exact_topk_via_block_candidates(cuda_lib, precision):
     blk_max = torch.full((B, bb.shape[1] * 64), float("-inf"), device=DEV)
     blk_max[:, :N] = dense if bank.perm is None else dense[:, bank.perm]
     assert (bb - blk_max.view(B, -1, 64).amax(2)).abs().max().item() < (0.05 if precision == "bf16" else 1e-3)
+
+
+def test_small_bank_graph_replay_is_transparent(cuda_lib):
+    """NWHead replays a CUDA graph for launch-bound banks once a batch size has been seen twice
+    (SupportBank.forward_auto).  Results must be bit-identical to the eager path, independent tensors (no aliasing
+    of the graph's static output), and a changed batch size or NW_B200_GRAPHS=0 must keep working."""
+    import os
+
+    import nwhead_b200
+
+    q, s, y, _ = clustered_features(10, 30, 64, 24, seed=21)
+    bank = nwhead_b200.SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), 10, "euclidean", "bf16")
+    head = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), 10)
+    qt = torch.from_numpy(q).to(DEV)
+    want = bank.forward(qt)
+    with torch.no_grad():
+        outs = [head(qt, bank) for _ in range(4)]          # call 3 onwards replays the captured graph
+        assert isinstance(bank._graph_cache[(24, 1.0)], nwhead_b200.bank.GraphedForward)
+        other = head(qt.flip(0), bank)                      # same shape, other data: must not disturb earlier results
+        small = head(qt[:5], bank)                          # another batch size: eager again, then its own graph
+        small2 = head(qt[:5], bank)
+        small3 = head(qt[:5], bank)
+    for o in outs:
+        assert torch.equal(o, want)
+    assert outs[2].data_ptr() != outs[3].data_ptr()
+    assert torch.equal(other, want.flip(0))
+    assert torch.allclose(small, want[:5], atol=1e-5) and torch.equal(small2, small) and torch.equal(small3, small)
+    os.environ["NW_B200_GRAPHS"] = "0"
+    try:
+        with torch.no_grad():
+            assert torch.equal(head(qt, bank), want)
+    finally:
+        del os.environ["NW_B200_GRAPHS"]

@@ -112,3 +112,20 @@ def test_environment_split_matches_reference_semantics():
     assert len(sy) == 2 * len(set(sy.tolist()))             # n_shot items of every class of that environment
     se = SupportSetEval(ds, 5, 1, 3, env_array=env)
     assert len(se.support_loaders) == 3
+
+
+def test_kmeans_first_seed_matches_numpy_choice():
+    """The first k-means++ centre of every class is `RandomState(0).choice(n, p=uniform)` in scikit-learn
+    (_kmeans_plusplus); the product draws the uniform once and maps it through numpy's normalised-cdf search for every
+    class size (nwhead_b200.utils._first_seed_offsets)."""
+    sizes = [1, 2, 3, 7, 29, 30, 100, 1279, 1280, 1281, 4096, 50001]
+    rs = np.random.RandomState(0)
+    u0 = rs.random_sample()
+    got = U._first_seed_offsets(sizes, u0)
+    for n in sizes:
+        w = np.ones(n, dtype=np.float32)
+        assert got[n] == np.random.RandomState(0).choice(n, p=w / w.sum()), n
+    # the draws that follow are plain uniforms: rs.uniform(size=t) continues the same stream
+    ref = np.random.RandomState(0)
+    ref.choice(5, p=np.ones(5) / 5)
+    assert np.array_equal(rs.uniform(size=3), ref.uniform(size=3))

@@ -45,16 +45,23 @@ def main():
         torch.cuda.synchronize()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         iters = 5
+        # SM clock measured inside the kernel (clock64 / globaltimer per CTA, summed over the launches)
+        probe = torch.zeros((2 * plan.grid,), dtype=torch.int64, device=dev)
+        _abi.check(_abi.load().nw_forward_set_clock_probe(_abi.ptr(probe), plan.grid), "set_clock_probe")
         ev[0].record()
         for _ in range(iters):
             lse = bank.class_lse_prepared(qb, qs)
         ev[1].record()
         torch.cuda.synchronize()
+        _abi.load().nw_forward_set_clock_probe(None, 0)
+        pv = probe.view(-1, 2).double()
+        mhz = float((pv[:, 0] / pv[:, 1].clamp_min(1) * 1e3).median())
         ms = ev[0].elapsed_time(ev[1]) / iters
         logp = logp_from_class_lse(lse)
         acc = (logp.argmax(1) == qy).float().mean().item()
         tf = 2.0 * B * N * d / (ms * 1e-3) / 1e12
         print(f"B={B} N={N} d={d} C={C}: {ms:.3f} ms/batch  {B / (ms * 1e-3):.0f} q/s  {tf:.1f} TFLOP/s  "
+              f"SM {mhz:.0f} MHz -> {2.0 * B * N * d / (ms * 1e-3 * mhz * 1e6 * 148 * 8192):.3f} of the tensor pipe  "
               f"plan(chunks={plan.chunks}, tpc={plan.tiles_per_chunk}, grid={plan.grid})  build {t_build:.2f}s  "
               f"top1-vs-label {acc:.3f}  psum {logp.exp().sum(1).mean().item():.6f}", flush=True)
         del bank

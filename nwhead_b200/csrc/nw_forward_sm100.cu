@@ -178,9 +178,27 @@ struct Flusher {
 #ifndef NW_EPI_RSQRT
 #define NW_EPI_RSQRT 0
 #endif
+#ifndef NW_EPI_POLY_EVERY
+#define NW_EPI_POLY_EVERY 0  // k > 0: every k-th exp2 of the QUAD (d <= 512) fast path runs on the FMA pipe
+#endif
 constexpr float kRaiseMax = 1048576.0f;  // chunk sum above which m is raised (some term exceeded 2^15)
 
-template <int EPI>
+// 2^x on the FMA pipe (the FlashAttention-4 trick for MUFU-bound softmax): round-to-nearest range reduction by the
+// 1.5 * 2^23 magic add, degree-4 polynomial on [-0.5, 0.5] (relative error 7e-6), exponent patched in with integer
+// arithmetic.  x is clamped to [-126, 126]: -inf / NaN (padding, m still -inf) give ~1e-38, +inf gives 2^126, which
+// the caller's "chunk sum too large" test still catches.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fminf(fmaxf(x, -126.0f), 126.0f);
+  const float r = x + 12582912.0f;
+  const float f = x - (r - 12582912.0f);
+  float p = fmaf(0.009666374f, f, 0.05583834f);
+  p = fmaf(p, f, 0.24022349f);
+  p = fmaf(p, f, 0.69313673f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
+template <int EPI, int POLY = 0>
 __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __restrict__ cadd,
                                                const int* __restrict__ lab, uint32_t emask, float qn,
                                                float scale2, float& m, float& l, const Flusher& flush) {
@@ -203,10 +221,12 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
 #else
           acc[i] = sqrt_approx(fabsf(fmaf(-2.0f, acc[i], qn + cc[k])));  // distance (kept for a possible redo)
 #endif
-          part[k] += ex2_approx(fmaf(acc[i], -kLog2e, -m));
+          if (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == POLY - 1) part[k] += exp2_poly(fmaf(acc[i], -kLog2e, -m));
+          else part[k] += ex2_approx(fmaf(acc[i], -kLog2e, -m));
         } else {
           acc[i] = fmaf(acc[i], scale2, cc[k]);  // score * log2(e)  (or -inf on padding columns)
-          part[k] += ex2_approx(acc[i] - m);
+          if (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == POLY - 1) part[k] += exp2_poly(acc[i] - m);
+          else part[k] += ex2_approx(acc[i] - m);
         }
       }
     }
@@ -640,11 +660,12 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             const uint32_t em0 =
                 __ballot_sync(0xffffffffu, ja < n1 && (ja == n1 - 1 || meta.lab[i0] != meta.lab[i0 + 1]));
             tmem_ld_wait();
-            epilogue_chunk<EPI>(acc, meta.cadd + c * 32, meta.lab + c * 32, em0, qn, scale2, m, l, flush);
+            epilogue_chunk<EPI, NW_EPI_POLY_EVERY>(acc, meta.cadd + c * 32, meta.lab + c * 32, em0, qn, scale2, m, l, flush);
             tmem_ld_32x32(t_addr + (c + 1) * 32, acc);
             em1 = __ballot_sync(0xffffffffu, jb < n1 && (jb == n1 - 1 || meta.lab[i1] != meta.lab[i1 + 1]));
             tmem_ld_wait();
-            epilogue_chunk<EPI>(acc, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, em1, qn, scale2, m, l, flush);
+            epilogue_chunk<EPI, NW_EPI_POLY_EVERY>(acc, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, em1, qn, scale2, m, l,
+                                                   flush);
           } else {
             float acc0[32], acc1[32];
             tmem_ld_32x32(t_addr + c * 32, acc0);

@@ -61,3 +61,42 @@ def test_class_ranges_partition_all_classes():
             spans = [class_range(r, world, C) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == C
             assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+
+
+class _FakeShard:
+    """Stands in for a SupportBank shard in the host-side plan validation (no GPU, no kernels)."""
+
+    def __init__(self, rows):
+        self.rows, self.device, self.n_classes = rows, torch.device("cpu"), 4
+
+    def __len__(self):
+        return self.rows
+
+
+def _plan_worker(rank, world, port, rows, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nwhead_b200.dist import ShardedBank
+
+    try:
+        ShardedBank(_FakeShard(rows[rank]), exchange="nccl")
+        ret[rank] = "ok"
+    except ValueError as e:
+        ret[rank] = "ValueError" if "owns no support rows" in str(e) else repr(e)
+    try:
+        ShardedBank(_FakeShard(5), exchange="peer", max_batch=0)
+        ret[f"peer{rank}"] = "ok"
+    except ValueError as e:
+        ret[f"peer{rank}"] = "ValueError" if "max_batch" in str(e) else repr(e)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("rows,want", [((5, 7), "ok"), ((5, 0), "ValueError")])
+def test_shard_plan_is_validated_on_every_rank(rows, want):
+    """a rank that owns no support rows must make EVERY rank raise (the others would wait in the next
+    collective forever), and the peer exchange must refuse max_batch = 0 instead of allocating empty tables."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_plan_worker, args=(world, _free_port(), rows, ret), nprocs=world, join=True)
+    assert ret[0] == want and ret[1] == want
+    assert ret["peer0"] == "ValueError" and ret["peer1"] == "ValueError"

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) scores_kernel(int kind, float scale, cons
     for (int j = 0; j < TS; ++j) acc[i][j] = 0.f;
   const bool euclid = direct::kind_euclid(kind);
   if (!direct::kind_normalised(kind)) {
+#pragma unroll 4  // several support-row loads in flight per lane (the loop is load-latency bound); same order per pair
     for (int c = lane; c < d; c += 32) {
       float qv[TQ], sv[TS];
 #pragma unroll
@@ -286,13 +287,13 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const float* __restrict_
 constexpr int AGG_BINS_MIN_N = 4096;
 constexpr int AGG_BINS_MAX_C = 8192;
 
-__global__ void __launch_bounds__(256) aggregate_bins_kernel(const float* __restrict__ scores,
+__global__ void __launch_bounds__(1024) aggregate_bins_kernel(const float* __restrict__ scores,
                                                              const int64_t* __restrict__ labels, int labels_batched,
                                                              long long n_support, int n_classes,
                                                              float* __restrict__ logp, float* __restrict__ row_lse,
                                                              int32_t* __restrict__ status) {
   extern __shared__ float bins[];  // n_classes floats
-  __shared__ float red[8];
+  __shared__ float red[32];
   const long long b = blockIdx.x;
   const float* sc = scores + b * n_support;
   const int64_t* lab = labels + (labels_batched ? b * n_support : 0);
@@ -302,12 +303,23 @@ __global__ void __launch_bounds__(256) aggregate_bins_kernel(const float* __rest
   mx = block_max(mx, red);  // (its barriers also publish the zeroed bins)
   float sum = 0.f;
   bool bad = false;
-  for (long long j = threadIdx.x; j < n_support; j += blockDim.x) {
-    const float e = expf(sc[j] - mx);
+  // whole warps walk the row together so that a warp whose 32 supports share one class (the usual case: supports
+  // come class-sorted or in long runs) adds ONE value to the bin instead of 32 contended ones
+  const long long n_round = (n_support + blockDim.x - 1) / blockDim.x * blockDim.x;
+  for (long long j = threadIdx.x; j < n_round; j += blockDim.x) {
+    const bool in = j < n_support;
+    const float e = in ? expf(sc[j] - mx) : 0.f;
+    const long long y = in ? lab[j] : -1;
     sum += e;
-    const long long y = lab[j];
-    if (y >= 0 && y < n_classes) atomicAdd(&bins[y], e);
-    else bad = true;
+    const bool ok = y >= 0 && y < n_classes;
+    bad |= in && !ok;
+    const long long y0 = __shfl_sync(0xffffffffu, y, 0);
+    if (__all_sync(0xffffffffu, y == y0)) {
+      const float w = warp_sum(e);
+      if ((threadIdx.x & 31) == 0 && ok) atomicAdd(&bins[y], w);
+    } else if (ok) {
+      atomicAdd(&bins[y], e);
+    }
   }
   if (bad) *reinterpret_cast<volatile int32_t*>(status) = 1;
   sum = block_sum(sum, red);
@@ -341,7 +353,11 @@ __global__ void __launch_bounds__(256) coef_kernel(int kind, float scale, const 
   const int64_t* lab = labels + (labels_batched ? b * n_support : 0);
   const float z = row_lse[b];
   float gscale = 0.f;
-  for (long long j = threadIdx.x; j < n_support; j += blockDim.x) {
+  // gridDim.y slices of the support axis (long rows: one block per query would leave the GPU to B blocks); every
+  // slice recomputes the O(C) prologue above.  grad_scale_rows is only produced with a single slice.
+  const long long per = (n_support + gridDim.y - 1) / gridDim.y;
+  const long long j_lo = (long long)blockIdx.y * per, j_hi = min(j_lo + per, n_support);
+  for (long long j = j_lo + threadIdx.x; j < j_hi; j += blockDim.x) {
     const float s = sc[j];
     const float p = expf(s - z);
     // an out-of-range label (rejected by the forward's status flag) contributes to no class: never index gP with it
@@ -476,11 +492,16 @@ __global__ void __launch_bounds__(256) grad_q_split_kernel(const float* __restri
 #pragma unroll
       for (int t = 0; t < GQ_BT; ++t) acc[t] = 0.f;
       const float* sp = s + j0 * d + c;
-#pragma unroll 4
-      for (int j = 0; j < nj; ++j) {
-        const float sv = __ldcs(sp + (long long)j * d);
+      // 8 support values in flight per thread before any is consumed (load-latency bound otherwise)
+      for (int jb = 0; jb < nj; jb += 8) {
+        float sv[8];
 #pragma unroll
-        for (int t = 0; t < GQ_BT; ++t) acc[t] = fmaf(w[t][j], sv, acc[t]);
+        for (int u = 0; u < 8; ++u) sv[u] = jb + u < nj ? __ldcs(sp + (long long)(jb + u) * d) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+          for (int t = 0; t < GQ_BT; ++t) acc[t] = fmaf(w[t][(jb + u) & (GQ_CHUNK - 1)], sv[u], acc[t]);
+        }
       }
       for (int t = 0; t < nb; ++t) partial[((long long)blockIdx.x * n_query + b0 + t) * d + c] = acc[t];
     }
@@ -560,6 +581,54 @@ __global__ void __launch_bounds__(256) grad_s_rows_kernel(int kind, const float*
     } else {
       for (int c = threadIdx.x; c < d; c += 256) grad_s[j * d + c] = row[c];
     }
+  }
+}
+
+// grad_s for a shared support and the kinds without normalisation (euclidean, dot product): a block owns GS_TILE
+// support rows x 256 columns.  The coefficients of those rows (all queries) and the query tile are staged in shared
+// memory once; every thread then issues the loads of its column for ALL rows of the tile before consuming any
+// (the row-at-a-time kernel above is load-latency bound: 1.5 TB/s at N = 160k, d = 2048).
+constexpr int GS_TILE = 16;
+constexpr int GS_BQ = 32;  // queries staged per pass
+
+__global__ void __launch_bounds__(256) grad_s_tile_kernel(int euclid, const float* __restrict__ q, int n_query, int d,
+                                                          const float* __restrict__ s, long long n_support,
+                                                          const float* __restrict__ coef,
+                                                          float* __restrict__ grad_s) {
+  __shared__ float w[GS_BQ][GS_TILE];
+  __shared__ float qt[GS_BQ][256];
+  const long long j0 = (long long)blockIdx.x * GS_TILE;
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  const int nj = int(min((long long)GS_TILE, n_support - j0));
+  float sv[GS_TILE], acc[GS_TILE], csum[GS_TILE];
+#pragma unroll
+  for (int j = 0; j < GS_TILE; ++j) {
+    sv[j] = (c < d && j < nj) ? __ldcs(s + (j0 + j) * d + c) : 0.f;
+    acc[j] = 0.f;
+    csum[j] = 0.f;
+  }
+  for (int b0 = 0; b0 < n_query; b0 += GS_BQ) {
+    const int nb = min(GS_BQ, n_query - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < GS_BQ * GS_TILE; i += 256) {
+      const int b = i / GS_TILE, j = i - b * GS_TILE;
+      w[b][j] = (b < nb && j < nj) ? coef[(long long)(b0 + b) * n_support + j0 + j] : 0.f;
+    }
+    for (int b = 0; b < nb; ++b) qt[b][threadIdx.x] = c < d ? q[(long long)(b0 + b) * d + c] : 0.f;
+    __syncthreads();
+    for (int b = 0; b < nb; ++b) {  // queries in ascending order: the summation order of grad_s_shared_kernel
+      const float qv = qt[b][threadIdx.x];
+#pragma unroll
+      for (int j = 0; j < GS_TILE; ++j) {
+        acc[j] = fmaf(w[b][j], qv, acc[j]);
+        csum[j] += w[b][j];
+      }
+    }
+  }
+  if (c < d) {
+#pragma unroll
+    for (int j = 0; j < GS_TILE; ++j)
+      if (j < nj) grad_s[(j0 + j) * d + c] = euclid ? acc[j] - csum[j] * sv[j] : acc[j];  // sum_b r_bj (q_b - s_j)
   }
 }
 
@@ -880,7 +949,7 @@ extern "C" int nw_direct_aggregate(const float* scores, const int64_t* labels, i
   NW_REQUIRE(scores && labels && logp && row_lse && status_out, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(n_query > 0 && n_support > 0 && n_classes > 0, NW_ERR_INVALID, "shapes must be positive");
   if (n_support > direct::AGG_BINS_MIN_N && n_classes <= direct::AGG_BINS_MAX_C)
-    direct::aggregate_bins_kernel<<<n_query, 256, n_classes * sizeof(float), stream>>>(
+    direct::aggregate_bins_kernel<<<n_query, 1024, n_classes * sizeof(float), stream>>>(
         scores, labels, labels_batched, n_support, n_classes, logp, row_lse, status_out);
   else
     direct::aggregate_kernel<<<n_query, 256, 0, stream>>>(scores, labels, labels_batched, n_support, n_classes, logp,
@@ -973,9 +1042,13 @@ extern "C" int nw_direct_backward(int kind, float scale, const float* q, int n_q
     direct::inv_norm_kernel<<<unsigned(ceil_div(n_query, 8)), 256, 0, stream>>>(q, n_query, d, inv_q);
     NW_CUDA_OK(cudaGetLastError());
   }
-  direct::coef_kernel<<<n_query, 256, n_classes * sizeof(float), stream>>>(
-      kind, scale, scores, row_lse, logp, grad_out, labels, labels_batched, n_support, n_classes, coef,
-      kind == NW_KIND_CLIP ? grad_scale_rows : nullptr);
+  {
+    const bool want_scale = kind == NW_KIND_CLIP && grad_scale_rows != nullptr;
+    const int slices = want_scale ? 1 : int(ceil_div_ll(n_support, 32768) < 64 ? ceil_div_ll(n_support, 32768) : 64);
+    direct::coef_kernel<<<dim3(n_query, slices), 256, n_classes * sizeof(float), stream>>>(
+        kind, scale, scores, row_lse, logp, grad_out, labels, labels_batched, n_support, n_classes, coef,
+        want_scale ? grad_scale_rows : nullptr);
+  }
   NW_CUDA_OK(cudaGetLastError());
   if (grad_q) {
     if (!support_batched && split_workspace != nullptr) {
@@ -997,7 +1070,11 @@ extern "C" int nw_direct_backward(int kind, float scale, const float* q, int n_q
     if (support_batched)
       direct::grad_s_batched_kernel<<<unsigned(pairs), 128, 0, stream>>>(kind, q, d, s, n_support, coef, inv_q,
                                                                          inv_s, grad_s);
-    else
+    else if (!norm) {
+      dim3 grid(unsigned(ceil_div_ll(n_support, direct::GS_TILE)), ceil_div(d, 256));
+      direct::grad_s_tile_kernel<<<grid, 256, 0, stream>>>(direct::kind_euclid(kind) ? 1 : 0, q, n_query, d, s,
+                                                           n_support, coef, grad_s);
+    } else
       direct::grad_s_rows_kernel<<<unsigned(ceil_div_ll(n_support, direct::GS_ROWS)), 256, d * sizeof(float), stream>>>(
           kind, q, n_query, d, s, n_support, coef, inv_q, inv_s, grad_s);
     NW_CUDA_OK(cudaGetLastError());

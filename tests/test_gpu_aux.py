@@ -180,8 +180,10 @@ def test_rank_rows_bit_exact(cuda_lib, n):
 
 @pytest.mark.parametrize("n,k", [(4097, 1), (5800, 20), (70000, 1024), (300001, 20), (300001, 1000), (5000, 1025)])
 def test_rank_rows_selection_equals_full_sort(cuda_lib, n, k):
-    """k <= 1024 over more than one sort chunk takes the selection path: the first k of the full stable ranking,
-    including ties (scores quantised to 50 levels -> ascending index inside a tie) and -inf / +inf entries."""
+    """k <= 1024 over more than one sort chunk takes the selection paths: the first k of the full stable ranking,
+    including ties and -inf / +inf entries.  Row 2 (normal scores) is finished by the radix selection; the rows
+    quantised to 50 levels hold thousands of keys tied at the threshold (more than the 4096 the radix kernel keeps),
+    so they are flagged and ranked by the sort-and-keep-k levels — ascending index inside a tie either way."""
     from nwhead_b200.utils import rank_rows
 
     rng = np.random.default_rng(n + k)

@@ -57,7 +57,6 @@ class PeerTables:
         self.group = group if group is not None else dist.group.WORLD
         self.max_batch, self.n_classes = max_batch, n_classes
         self.tables, self.handles, self.ptr_arrays = [], [], []
-        rank = dist.get_rank(self.group)
         for _ in range(2):
             t = symm_mem.empty((max_batch, n_classes), dtype=torch.float32, device=device)
             t.fill_(float("-inf"))

@@ -986,6 +986,14 @@ extern "C" int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t
     }
     if (G == s_tiles) break;
   }
+  {
+    // developer override for scheduling experiments (NW_B200_FORCE_CHUNKS=<chunks>)
+    static const int forced = [] {
+      const char* e = getenv("NW_B200_FORCE_CHUNKS");
+      return e && *e ? atoi(e) : 0;
+    }();
+    if (forced > 0) best_tpc = ceil_div(s_tiles, forced < s_tiles ? forced : s_tiles);
+  }
   plan->q_tiles = q_groups;
   plan->s_tiles = s_tiles;
   plan->tiles_per_chunk = best_tpc;

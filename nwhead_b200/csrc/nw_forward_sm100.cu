@@ -109,6 +109,7 @@ struct Params {
   int tiles_per_chunk;
   float scale_log2;  // LINEAR: scale * log2(e)
   int sets;          // epilogue warp sets (1, 2 or 4); class-LSE with several sets: set s stores to lse[s]
+  int stagger_ns;           // developer probe (NW_B200_STAGGER_NS): query group g delays its first load by g * this
   int debug_skip_epilogue;  // developer probe (NW_B200_DEBUG_SKIP_EPI=1): accumulators are released unread -> the
                             // speed of the TMA + MMA mainloop alone (results are garbage)
   // ---- MODE_EMIT only: one output value per (query, support) pair
@@ -438,6 +439,12 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const uint64_t pol_q = l2_policy_evict_last();
       const uint64_t pol_s = p.s_keep ? l2_policy_evict_last() : l2_policy_evict_normal();
       uint32_t it = 0;
+      if (p.stagger_ns > 0 && worker < n_units) {
+        const unsigned long long wait_ns = (unsigned long long)(worker % p.q_groups) * p.stagger_ns;
+        const unsigned long long t_start = globaltimer_ns();
+        while (globaltimer_ns() - t_start < wait_ns) {
+        }
+      }
       for (int u = worker; u < n_units; u += n_workers) {
         const int g = u / p.q_groups;
         const int qg = u - g * p.q_groups;
@@ -1116,6 +1123,18 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
       return e && e[0] == '1' ? 1 : 0;
     }();
     p.debug_skip_epilogue = skip;
+    static const int persist_mb = [] {  // developer probe: L2 set-aside for evict_last (persisting) lines
+      const char* e = getenv("NW_B200_PERSIST_L2_MB");
+      const int mb = e && *e ? atoi(e) : -1;
+      if (mb >= 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(mb) << 20);
+      return mb;
+    }();
+    (void)persist_mb;
+    static const int stagger = [] {
+      const char* e = getenv("NW_B200_STAGGER_NS");
+      return e && *e ? atoi(e) : 0;
+    }();
+    p.stagger_ns = stagger;
   }
   p.row_lse = p.p_query = nullptr;
   p.qlabel = nullptr;

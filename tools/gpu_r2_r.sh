@@ -10,9 +10,8 @@ run() {
   grep "TFLOP" gpurun_out/sched_tmp.log | awk '{print $1,$2,$3,$4,$5,$6,$7,$8,$9,$10,$11}' >> gpurun_out/r2_sched.log
 }
 run "NW_X=0"
-run "NW_B200_S_KEEP_MIN_GROUPS=99"
-run "NW_B200_FORCE_CHUNKS=74"
-run "NW_B200_FORCE_CHUNKS=148"
-run "NW_B200_FORCE_CHUNKS=19"
-run "NW_B200_FORCE_CHUNKS=74 NW_B200_S_KEEP_MIN_GROUPS=99"
+run "NW_B200_STAGGER_NS=500"
+run "NW_B200_STAGGER_NS=2000"
+run "NW_B200_STAGGER_NS=8000"
 cat gpurun_out/r2_sched.log
+for st in 0 2000 8000 0 2000; do echo "== stagger $st (no ncu)"; NW_B200_STAGGER_NS=$st python tools/probe_perf.py 4096,1280000,2048,1000 | awk '{print $1,$2,$3,$4,$5,$6,$7,$8,$9,$10,$11,$12,$13,$14,$15,$16,$17,$18,$19}'; done

@@ -73,9 +73,20 @@ struct __align__(16) TileMeta {
   int lab[BN + 8];   // labels of the tile's columns plus one look-ahead entry
 };
 
+// What the class-end stores need to know about the unit a set is working on; written once per unit by one thread
+// of the set (double-buffered by unit parity), read from shared memory at class ends.  It used to live in a
+// per-thread struct in LOCAL memory: with 219 KB of shared memory the L1 is a few KB, every class end paid four
+// dependent L2 round trips (~880 cycles, 6.5 % of the epilogue at d = 256 in ncu's source view).
+struct __align__(16) UnitInfo {
+  int cf, cl;  // first / last class of the unit's support range
+  int cuts;    // bit 0: class cf continues from the previous chunk; bit 1: class cl continues into the next chunk
+  int g;       // chunk index (row block of `side`)
+};
+
 template <int MODE, bool QUAD = false>
 struct SmemTail {
   TileMeta meta[QUAD ? QUAD_SETS : 2][ACC_STAGES];  // [epilogue set][accumulator stage]: the sets stay independent
+  UnitInfo unit[QUAD ? QUAD_SETS : 2][2];           // [epilogue set][unit parity]
   float stage[MODE == 0 ? 1 : MAX_EPI_WARPS][32][33];  // emit modes: per-warp 32x32 transpose buffers
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
@@ -130,35 +141,52 @@ constexpr int MODE_EMIT_BLOCKBEST = 3;  // best score of every block of 64 suppo
 // (the emit kind is a template parameter: one kernel with a runtime switch and logf inlined 64 times was > 64 KB
 //  of SASS and ran 4x slower on instruction fetch)
 
+// Class-end stores.  Rare (once per class per row), kept out of line so the unrolled column loop stays compact, and
+// fed with scalars only: nothing of this lives in local memory.
+// A class that lies completely inside the unit is final: it is stored to the local table (this set's table when
+// several epilogue sets run) AND, for bank-sharded predict, to the peer GPUs' tables — the exchange happens here,
+// tile by tile, as NVLink peer stores that overlap the MMAs.  Classes cut by a chunk boundary go through `side`:
+// side[((chunk * B + row) * 2 + slot) * sets + set], slot 0 = head-cut class, slot 1 = tail-cut class.
+__device__ __noinline__ void store_class(const Params* p, int row, int set, int cls, float v) {
+  const size_t off = size_t(row) * p->n_classes + cls;
+  if (p->sets >= 2) p->lse[set][off] = v;
+  else if (p->rows_per_table > 0) p->lse[row / p->rows_per_table][off] = v;
+  else
+    for (int r = 0; r < p->n_tables; ++r) p->lse[r][off] = v;
+}
+
+__device__ __forceinline__ int4 lds_int4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+__device__ __noinline__ void flush_class(const Params* p, uint32_t unit_addr, int row, int set, int cls, float m,
+                                         float l) {
+  if (row < 0) return;
+  const float v = (m + lg2_approx(l)) * kLn2;
+  const int4 u = lds_int4(unit_addr);  // cf, cl, cuts, chunk
+  if (cls == u.x && (u.z & 1)) p->side[((size_t(u.w) * p->n_query + row) * 2) * p->sets + set] = v;
+  else if (cls == u.y && (u.z & 2)) p->side[((size_t(u.w) * p->n_query + row) * 2 + 1) * p->sets + set] = v;
+  else store_class(p, row, set, cls, v);
+}
+
 struct Flusher {
-  const Params* p;   // only dereferenced on the multi-table (peer GPU) routes
-  float* table;      // the one table this thread stores to when route == 0 (local table, or this set's table)
-  size_t row_off;    // row * C
-  float* side_row;   // side + ((chunk * B + row) * 2) * sets: [slot 0 = head-cut class | slot 1 = tail-cut class][set]
-  int cf, cl;
-  bool head_cut, tail_cut, row_valid;
-  int row, set, sets;
-  int route;         // 0: `table`; 1: table[row / rows_per_table]; 2: every table (peer all-gather)
-  // Rare path (once per class per row), kept out of line so the unrolled column loop stays compact.
-  // A class that lies completely inside this unit is final: store it to the local table AND (bank-sharded predict)
-  // to the peer GPUs' tables — the exchange happens here, tile by tile, as NVLink peer stores that overlap the
-  // MMAs.  Classes cut by a chunk boundary go through `side`.
-  __device__ __noinline__ void operator()(int cls, float m, float l) const {
-    const float v = (m + lg2_approx(l)) * kLn2;
-    if (!row_valid) return;
-    if (cls == cf && head_cut) side_row[set] = v;
-    else if (cls == cl && tail_cut) side_row[sets + set] = v;
-    else store(cls, v);
+  const Params* p;
+  uint32_t unit_addr;  // shared-memory address of this unit's UnitInfo
+  int row;             // query row, -1 when it is beyond the batch
+  int set;
+  __device__ __forceinline__ void operator()(int cls, float m, float l) const {
+    flush_class(p, unit_addr, row, set, cls, m, l);
   }
   // single-row class that lies inside the unit: its class log-sum-exp is the score itself
   __device__ __forceinline__ void single(int cls, float v) const {
-    if (row_valid) store(cls, v);
+    if (row >= 0) store_class(p, row, set, cls, v);
   }
-  __device__ __noinline__ void store(int cls, float v) const {
-    if (route == 0) table[row_off + cls] = v;
-    else if (route == 1) p->lse[row / p->rows_per_table][row_off + cls] = v;
-    else
-      for (int r = 0; r < p->n_tables; ++r) p->lse[r][row_off + cls] = v;
+  // the class of column label `cls` continues into the next chunk (its sum is not final here)
+  __device__ __forceinline__ bool tail_cut_class(int cls) const {
+    const int4 u = lds_int4(unit_addr);
+    return (u.z & 2) && cls == u.y;
   }
 };
 
@@ -178,6 +206,9 @@ struct Flusher {
 // Chunks in which a class ends (warp-uniform, 1 in ~40 at 1280 rows per class) take the exact-maximum path.
 #ifndef NW_EPI_RSQRT
 #define NW_EPI_RSQRT 0
+#endif
+#ifndef NW_EPI_DEBUG
+#define NW_EPI_DEBUG 0  // 2 / 3: developer builds that isolate the TMEM loads / the math of the QUAD epilogue
 #endif
 #ifndef NW_EPI_POLY_EVERY
 #define NW_EPI_POLY_EVERY 0  // k > 0: every k-th exp2 of the QUAD (d <= 512) fast path runs on the FMA pipe
@@ -259,16 +290,20 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
     l += sum;
     return;
   }
-  // a class ends inside this chunk: exact chunk maximum first, then column by column with flushes
+  // A class ends inside this chunk: exact chunk maximum first, then the exponent arguments of all 32 columns in one
+  // branch-free pass (the MUFU latencies overlap), then groups of four columns: exp2 of the group, and either one
+  // tree add (no class end in the group) or column by column with the class-end stores.  (The first version did
+  // sqrt -> exp2 -> add -> branch per column, a ~55-cycle dependent chain 32 times over: banks with ~100 rows per
+  // class, where every fourth chunk comes here, ran 1.6x slower than banks with 1280.)
   float mx;
   if (EPI == NW_EPI_EUCLID) {
     float dmin = __int_as_float(0x7f800000);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      acc[i] = fabsf(fmaf(-2.0f, acc[i], qn + cadd[i]));  // squared distance
+      acc[i] = sqrt_approx(fabsf(fmaf(-2.0f, acc[i], qn + cadd[i])));  // distance
       dmin = fminf(dmin, acc[i]);
     }
-    mx = -sqrt_approx(dmin) * kLog2e;
+    mx = -dmin * kLog2e;
   } else {
     mx = __int_as_float(0xff800000);
 #pragma unroll
@@ -282,20 +317,33 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
     m = mx;
   }
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float arg;  // score * log2(e) - m
-    if (EPI == NW_EPI_EUCLID) arg = fmaf(sqrt_approx(acc[i]), -kLog2e, -m);
-    else arg = acc[i] - m;
-    l += ex2_approx(arg);
-    if (emask & (1u << i)) {  // warp-uniform: column i is the last row of its class (in this unit)
-      if (i > 0 && (emask & (1u << (i - 1))) && !(flush.tail_cut && lab[i] == flush.cl)) {
-        // the previous column closed its class too, so this class has ONE row here (cluster / random mode
-        // banks: one support per class): its log-sum-exp is simply its score; stored inline, no call
-        flush.single(lab[i], (arg + m) * kLn2);
-      } else {
-        flush(lab[i], m, l);
+  for (int i = 0; i < 32; ++i) {  // score * log2(e) - m
+    if (EPI == NW_EPI_EUCLID) acc[i] = fmaf(acc[i], -kLog2e, -m);
+    else acc[i] = acc[i] - m;
+  }
+#pragma unroll
+  for (int i4 = 0; i4 < 32; i4 += 4) {
+    float e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e[k] = ex2_approx(acc[i4 + k]);
+    if (((emask >> i4) & 0xfu) == 0u) {  // warp-uniform
+      l += (e[0] + e[1]) + (e[2] + e[3]);
+      continue;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i4 + k;
+      l += e[k];
+      if (emask & (1u << i)) {  // warp-uniform: column i is the last row of its class (in this unit)
+        if (i > 0 && (emask & (1u << (i - 1))) && !flush.tail_cut_class(lab[i])) {
+          // the previous column closed its class too, so this class has ONE row here (cluster / random mode
+          // banks: one support per class): its log-sum-exp is simply its score; stored inline, no call
+          flush.single(lab[i], (acc[i] + m) * kLn2);
+        } else {
+          flush(lab[i], m, l);
+        }
+        l = 0.0f;
       }
-      l = 0.0f;
     }
   }
 }
@@ -526,7 +574,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const float scale2 = p.scale_log2;
     const float neg_inf = __int_as_float(0xff800000);
     const float pos_inf = __int_as_float(0x7f800000);
-    uint32_t tc = 0;
+    uint32_t tc = 0, uc = 0;  // tiles / units this CTA has worked on
     // Effective SM clock of this launch, measured in the kernel: SM cycles (clock64) over wall time (globaltimer)
     // across the whole epilogue role of one thread per CTA, accumulated per CTA so that a series of launches
     // yields the time-weighted mean.  nvidia-smi / NVML clocks are instantaneous samples; this is the integral.
@@ -537,7 +585,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       probe_c0 = clock64();
       probe_t0 = globaltimer_ns();
     }
-    for (int u = worker; u < n_units; u += n_workers) {
+    for (int u = worker; u < n_units; u += n_workers, ++uc) {
       const int g = u / p.q_groups;
       const int qg = u - g * p.q_groups;
       const int t0 = g * p.tiles_per_chunk;
@@ -546,29 +594,26 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const int n1 = min(t1 * BN, p.n_support);
       const int row = (qg * NCTA + int(cta_rank)) * BM + ew * 32 + lane;
 
+      const bool row_valid = row < p.n_query;
       Flusher flush;
-      flush.row_valid = row < p.n_query;
-      flush.cf = flush.cl = -1;
-      flush.head_cut = flush.tail_cut = false;
-      if (MODE == MODE_CLASS_LSE) {
-        flush.cf = __ldg(p.labels + n0);
-        flush.cl = __ldg(p.labels + n1 - 1);
-        flush.head_cut = n0 > 0 && __ldg(p.labels + n0 - 1) == flush.cf;
-        flush.tail_cut = n1 < p.n_support && __ldg(p.labels + n1) == flush.cl;
-      }
-      const int srow = flush.row_valid ? row : 0;
       flush.p = &p;
-      flush.row = srow;
+      flush.unit_addr = smem_u32(&tail->unit[eg][uc & 1u]);
+      flush.row = row_valid ? row : -1;
       flush.set = eg;
-      flush.sets = p.sets;
-      flush.route = p.sets >= 2 ? 0 : (p.rows_per_table > 0 ? 1 : (p.n_tables > 1 ? 2 : 0));
-      flush.table = p.lse[p.sets >= 2 ? eg : 0];
-      flush.row_off = size_t(srow) * p.n_classes;
-      flush.side_row = p.side + (size_t(g) * p.n_query + srow) * 2 * p.sets;
-      const float qn = (EPI == NW_EPI_EUCLID && flush.row_valid) ? __ldg(p.q_sqnorm + row) : 0.0f;
+      if (MODE == MODE_CLASS_LSE && et == 0) {
+        // visible to the set's other threads after the first tile's named barrier (no class ends before that)
+        UnitInfo ui;
+        ui.cf = __ldg(p.labels + n0);
+        ui.cl = __ldg(p.labels + n1 - 1);
+        ui.cuts = ((n0 > 0 && __ldg(p.labels + n0 - 1) == ui.cf) ? 1 : 0) |
+                  ((n1 < p.n_support && __ldg(p.labels + n1) == ui.cl) ? 2 : 0);
+        ui.g = g;
+        tail->unit[eg][uc & 1u] = ui;
+      }
+      const float qn = (EPI == NW_EPI_EUCLID && row_valid) ? __ldg(p.q_sqnorm + row) : 0.0f;
       float e_z = 0.0f, e_p = 0.0f;
       int e_qy = -1;
-      if (MODE == MODE_EMIT_INFLUENCE && flush.row_valid) {
+      if (MODE == MODE_EMIT_INFLUENCE && row_valid) {
         e_z = __ldg(p.row_lse + row);
         e_p = __ldg(p.p_query + row);
         e_qy = __ldg(p.qlabel + row);
@@ -612,8 +657,12 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           }
         }
         if (et == 0) meta.lab[BN] = pre_lab_next;
+#if NW_EPI_DEBUG != 4 && NW_EPI_DEBUG != 5  // developer builds 4 / 5: no per-tile barrier / no barrier and no metadata prefetch
         named_bar_sync(1 + eg, epi_threads);
+#endif
+#if NW_EPI_DEBUG != 5
         if (t + 1 < t1) load_meta(t + 1);
+#endif
 
         mbar_wait(smem_u32(&tail->tfull[as]), aph);
         tc_fence_after();
@@ -621,11 +670,12 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // Two 32-column chunks per iteration, NOT unrolled further: the epilogue body is ~1.5k instructions and
         // a fully unrolled tile (8 chunks x 2 paths) overflows the instruction cache (stall_no_inst in ncu).
         // (Software-pipelining the TMEM loads one chunk ahead was measured: no gain, +40 registers.)
+        // chunk pairs are dealt round-robin to the epilogue sets (class-LSE: 1 / 2 / 4 of them; emit modes: 2)
+        const int c_step = 2 * (MODE == MODE_CLASS_LSE ? p.sets : 2);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; c += 2) {
+        for (int c = 2 * eg; c < BN / 32; c += c_step) {
           if (MODE != MODE_CLASS_LSE) {
             constexpr bool INFL = MODE == MODE_EMIT_INFLUENCE;
-            if (((c >> 1) & 1) != eg) continue;  // chunk pairs alternate between the two epilogue warp sets
             float acc0[32], acc1[32];
             tmem_ld_32x32(t_addr + c * 32, acc0);
             tmem_ld_32x32(t_addr + (c + 1) * 32, acc1);
@@ -635,7 +685,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
               const float b1 = chunk_best<EPI>(acc1, meta.cadd + (c + 1) * 32, qn, p.scale_log2 * kLn2,
                                                n1 - (j0 + (c + 1) * 32));
               // out[block][query]: 32 consecutive query rows per warp -> one coalesced 128-byte store
-              if (flush.row_valid) p.emit_out[(long long)(t * (BN / 64) + (c >> 1)) * p.emit_ld + row] = fmaxf(b0, b1);
+              if (row_valid) p.emit_out[(long long)(t * (BN / 64) + (c >> 1)) * p.emit_ld + row] = fmaxf(b0, b1);
               continue;
             }
             const int row0 = (qg * NCTA + int(cta_rank)) * BM + ew * 32;
@@ -648,8 +698,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                                   n1 - (j0 + (c + 1) * 32), p.emit_vec != 0);
             continue;
           }
-          if (((c >> 1) & (p.sets - 1)) != eg) continue;  // chunk pairs are dealt round-robin to the 1 / 2 / 4 sets
-          if (p.debug_skip_epilogue) continue;
+          if (p.debug_skip_epilogue == 1) continue;
           if (p.sets >= 2) {
             // this set skipped the columns in between: if they ended the class it was accumulating, close its
             // partial now (the other sets close their own; the tables are combined after the kernel)
@@ -665,16 +714,38 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           if (QUAD) {
             // one 32-column chunk in registers at a time: 640 threads leave ~100 registers per thread
             float acc[32];
+#if NW_EPI_DEBUG == 3  // developer build: the math on register data, no TMEM loads
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = float(i) + qn;
+#else
             tmem_ld_32x32(t_addr + c * 32, acc);
+#endif
             const uint32_t em0 =
                 __ballot_sync(0xffffffffu, ja < n1 && (ja == n1 - 1 || meta.lab[i0] != meta.lab[i0 + 1]));
+#if NW_EPI_DEBUG != 3
             tmem_ld_wait();
+#endif
+#if NW_EPI_DEBUG == 2  // developer build: the TMEM loads only, no math
+            l += acc[0] + acc[31];
+#else
             epilogue_chunk<EPI, NW_EPI_POLY_EVERY>(acc, meta.cadd + c * 32, meta.lab + c * 32, em0, qn, scale2, m, l, flush);
+#endif
+#if NW_EPI_DEBUG == 3
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = float(i) + l;
+#else
             tmem_ld_32x32(t_addr + (c + 1) * 32, acc);
+#endif
             em1 = __ballot_sync(0xffffffffu, jb < n1 && (jb == n1 - 1 || meta.lab[i1] != meta.lab[i1 + 1]));
+#if NW_EPI_DEBUG != 3
             tmem_ld_wait();
+#endif
+#if NW_EPI_DEBUG == 2
+            l += acc[0] + acc[31];
+#else
             epilogue_chunk<EPI, NW_EPI_POLY_EVERY>(acc, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, em1, qn, scale2, m, l,
                                                    flush);
+#endif
           } else {
             float acc0[32], acc1[32];
             tmem_ld_32x32(t_addr + c * 32, acc0);
@@ -1122,7 +1193,7 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   {
     static const int skip = [] {
       const char* e = getenv("NW_B200_DEBUG_SKIP_EPI");
-      return e && e[0] == '1' ? 1 : 0;
+      return e && *e ? atoi(e) : 0;
     }();
     p.debug_skip_epilogue = skip;
     static const int persist_mb = [] {  // developer probe: L2 set-aside for evict_last (persisting) lines

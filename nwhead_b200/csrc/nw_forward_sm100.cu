@@ -68,6 +68,15 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 };
 
+// Tile metadata slots filled by the TMA producer with two bulk copies per tile (class-LSE mode, 16-byte aligned
+// s_sqnorm / labels, tiles that lie completely inside the bank).  The epilogue sets then only wait on an mbarrier:
+// the per-set staging below (4 global loads + 5 shared stores per thread, a named barrier and the prefetch of the
+// next tile, 11 % of the epilogue's warp time at d = 256 in ncu's source view) remains for edge tiles, unaligned
+// arrays and the emit modes.
+constexpr int META_SLOTS = 4;
+constexpr uint32_t META_CADD_BYTES = BN * 4;
+constexpr uint32_t META_LAB_BYTES = (BN + 4) * 4;  // + the look-ahead label, rounded up to 16 bytes
+
 struct __align__(16) TileMeta {
   float cadd[BN];    // per-column additive term: |s|^2 (EUCLID) or 0 (LINEAR); +inf / -inf for padding columns
   int lab[BN + 8];   // labels of the tile's columns plus one look-ahead entry
@@ -87,6 +96,9 @@ template <int MODE, bool QUAD = false>
 struct SmemTail {
   TileMeta meta[QUAD ? QUAD_SETS : 2][ACC_STAGES];  // [epilogue set][accumulator stage]: the sets stay independent
   UnitInfo unit[QUAD ? QUAD_SETS : 2][2];           // [epilogue set][unit parity]
+  TileMeta mslot[META_SLOTS];                       // class-LSE: tile metadata delivered by the producer (bulk copies)
+  uint64_t mfull[META_SLOTS];
+  uint64_t mempty[META_SLOTS];
   float stage[MODE == 0 ? 1 : MAX_EPI_WARPS][32][33];  // emit modes: per-warp 32x32 transpose buffers
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
@@ -120,6 +132,7 @@ struct Params {
   int tiles_per_chunk;
   float scale_log2;  // LINEAR: scale * log2(e)
   int sets;          // epilogue warp sets (1, 2 or 4); class-LSE with several sets: set s stores to lse[s]
+  int meta_bulk;     // class-LSE: the producer delivers the metadata of interior tiles (see META_SLOTS)
   int stagger_ns;           // developer probe (NW_B200_STAGGER_NS): query group g delays its first load by g * this
   int debug_skip_epilogue;  // developer probe (NW_B200_DEBUG_SKIP_EPI=1): accumulators are released unread -> the
                             // speed of the TMA + MMA mainloop alone (results are garbage)
@@ -447,6 +460,8 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int worker = blockIdx.x / NCTA;
   const int n_workers = gridDim.x / NCTA;
   const int n_units = p.chunks * p.q_groups;
+  // epilogue sets: they share every tile by columns (a compile-time constant where the epilogue is the bottleneck)
+  const int n_sets = QUAD ? QUAD_SETS : (MODE == MODE_CLASS_LSE ? p.sets : 2);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -457,9 +472,13 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       mbar_init(smem_u32(&tail->full[i]), 1);
       mbar_init(smem_u32(&tail->empty[i]), 1);
     }
+    for (int i = 0; i < META_SLOTS; ++i) {
+      mbar_init(smem_u32(&tail->mfull[i]), 1);
+      mbar_init(smem_u32(&tail->mempty[i]), 4 * n_sets);  // the epilogue warps of THIS CTA
+    }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(smem_u32(&tail->tfull[i]), 1);
-      mbar_init(smem_u32(&tail->tempty[i]), NCTA * 4 * p.sets);
+      mbar_init(smem_u32(&tail->tempty[i]), NCTA * 4 * n_sets);
     }
     fence_mbar_init();
   }
@@ -472,11 +491,17 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       tmem_relinquish();
     }
   }
+  if (EPI != NW_EPI_EUCLID && MODE == MODE_CLASS_LSE && p.meta_bulk) {
+    // LINEAR scores have no additive term: the slots' cadd stay zero, only the labels are copied per tile
+    for (int i = threadIdx.x; i < META_SLOTS * BN; i += blockDim.x) tail->mslot[i / BN].cadd[i % BN] = 0.0f;
+  }
   tc_fence_before();
   if (NCTA == 2) cluster_sync_all();
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
+  // tile whose metadata the producer delivers: completely inside the bank, look-ahead label included
+  auto bulk_tile = [&](int t) { return MODE == MODE_CLASS_LSE && p.meta_bulk != 0 && t * BN + BN + 4 <= p.n_support; };
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -488,7 +513,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       // evict_last there cost 3-9 % at B <= 256.
       const uint64_t pol_q = l2_policy_evict_last();
       const uint64_t pol_s = p.s_keep ? l2_policy_evict_last() : l2_policy_evict_normal();
-      uint32_t it = 0;
+      uint32_t it = 0, mc = 0;  // ring stages / metadata slots filled so far
       if (p.stagger_ns > 0 && worker < n_units) {
         const unsigned long long wait_ns = (unsigned long long)(worker % p.q_groups) * p.stagger_ns;
         const unsigned long long t_start = globaltimer_ns();
@@ -503,6 +528,15 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int q_row0 = (qg * NCTA + int(cta_rank)) * BM;
         for (int t = t0; t < t1; ++t) {
           const int s_row0 = t * BN + int(cta_rank) * C::B_ROWS;
+          if (bulk_tile(t)) {
+            const uint32_t ms = mc % META_SLOTS;
+            mbar_wait(smem_u32(&tail->mempty[ms]), ((mc / META_SLOTS) & 1u) ^ 1u);
+            const uint32_t bar = smem_u32(&tail->mfull[ms]);
+            mbar_arrive_expect_tx(bar, (EPI == NW_EPI_EUCLID ? META_CADD_BYTES : 0u) + META_LAB_BYTES);
+            if (EPI == NW_EPI_EUCLID) bulk_load_1d(smem_u32(tail->mslot[ms].cadd), p.s_sqnorm + t * BN, META_CADD_BYTES, bar);
+            bulk_load_1d(smem_u32(tail->mslot[ms].lab), p.labels + t * BN, META_LAB_BYTES, bar);
+            ++mc;
+          }
           for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
             const uint32_t s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
@@ -565,7 +599,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
     }
     __syncwarp();
-  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4 * p.sets) {
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4 * n_sets) {
     // ===================================== epilogue ==========================================
     constexpr int epi_threads = 128;         // threads of ONE epilogue set (each set stages its own metadata)
     const int ew = (warp - EPI_WARP0) & 3;   // == warp % 4: TMEM lane quarter this warp may read
@@ -574,7 +608,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const float scale2 = p.scale_log2;
     const float neg_inf = __int_as_float(0xff800000);
     const float pos_inf = __int_as_float(0x7f800000);
-    uint32_t tc = 0, uc = 0;  // tiles / units this CTA has worked on
+    uint32_t tc = 0, uc = 0, mc = 0;  // tiles / units / producer-delivered metadata slots this CTA has worked on
     // Effective SM clock of this launch, measured in the kernel: SM cycles (clock64) over wall time (globaltimer)
     // across the whole epilogue role of one thread per CTA, accumulated per CTA so that a series of launches
     // yields the time-weighted mean.  nvidia-smi / NVML clocks are instantaneous samples; this is the integral.
@@ -610,6 +644,9 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         ui.g = g;
         tail->unit[eg][uc & 1u] = ui;
       }
+      // UnitInfo visible to the whole set before its first class end; also keeps any thread from running two units
+      // ahead of another (the double buffer above, and the reuse of meta[eg][] by edge tiles, rely on that)
+      if (MODE == MODE_CLASS_LSE) named_bar_sync(1 + eg, epi_threads);
       const float qn = (EPI == NW_EPI_EUCLID && row_valid) ? __ldg(p.q_sqnorm + row) : 0.0f;
       float e_z = 0.0f, e_p = 0.0f;
       int e_qy = -1;
@@ -637,31 +674,37 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
         if (et == 0) pre_lab_next = (p.labels != nullptr && (j0 + BN) < p.n_support) ? __ldg(p.labels + j0 + BN) : -1;
       };
-      load_meta(t0);
+      if (!bulk_tile(t0)) load_meta(t0);
 
       float m = neg_inf, l = 0.0f;
       int open_cls = -1;  // two sets: class whose partial this set currently holds (warp-uniform)
       for (int t = t0; t < t1; ++t, ++tc) {
         const uint32_t as = tc & 1u;
         const uint32_t aph = (tc >> 1) & 1u;
-        TileMeta& meta = tail->meta[eg][as];
         const int j0 = t * BN;
-        // publish this tile's column metadata (fetched into registers one tile ahead, so the global-load
-        // latency is hidden behind the previous tile's epilogue math)
+        const bool bulk = bulk_tile(t);  // CTA-uniform
+        const uint32_t ms = mc % META_SLOTS;
+        TileMeta& meta = bulk ? tail->mslot[ms] : tail->meta[eg][as];
+        if (bulk) {
+          mbar_wait(smem_u32(&tail->mfull[ms]), (mc / META_SLOTS) & 1u);
+        } else {
+          // publish this tile's column metadata (fetched into registers one tile ahead, so the global-load
+          // latency is hidden behind the previous tile's epilogue math)
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int i = et + r * epi_threads;
-          if (i < BN) {
-            meta.cadd[i] = pre_cadd[r];
-            meta.lab[i] = pre_lab[r];
+          for (int r = 0; r < 2; ++r) {
+            const int i = et + r * epi_threads;
+            if (i < BN) {
+              meta.cadd[i] = pre_cadd[r];
+              meta.lab[i] = pre_lab[r];
+            }
           }
-        }
-        if (et == 0) meta.lab[BN] = pre_lab_next;
+          if (et == 0) meta.lab[BN] = pre_lab_next;
 #if NW_EPI_DEBUG != 4 && NW_EPI_DEBUG != 5  // developer builds 4 / 5: no per-tile barrier / no barrier and no metadata prefetch
-        named_bar_sync(1 + eg, epi_threads);
+          named_bar_sync(1 + eg, epi_threads);
 #endif
+        }
 #if NW_EPI_DEBUG != 5
-        if (t + 1 < t1) load_meta(t + 1);
+        if (t + 1 < t1 && !bulk_tile(t + 1)) load_meta(t + 1);
 #endif
 
         mbar_wait(smem_u32(&tail->tfull[as]), aph);
@@ -671,7 +714,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // a fully unrolled tile (8 chunks x 2 paths) overflows the instruction cache (stall_no_inst in ncu).
         // (Software-pipelining the TMEM loads one chunk ahead was measured: no gain, +40 registers.)
         // chunk pairs are dealt round-robin to the epilogue sets (class-LSE: 1 / 2 / 4 of them; emit modes: 2)
-        const int c_step = 2 * (MODE == MODE_CLASS_LSE ? p.sets : 2);
+        const int c_step = 2 * n_sets;
 #pragma unroll 1
         for (int c = 2 * eg; c < BN / 32; c += c_step) {
           if (MODE != MODE_CLASS_LSE) {
@@ -699,7 +742,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             continue;
           }
           if (p.debug_skip_epilogue == 1) continue;
-          if (p.sets >= 2) {
+          if (n_sets >= 2) {
             // this set skipped the columns in between: if they ended the class it was accumulating, close its
             // partial now (the other sets close their own; the tables are combined after the kernel)
             const int first = meta.lab[c * 32];
@@ -708,6 +751,9 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
               l = 0.0f;
             }
           }
+          // (Deriving "no class ends in this chunk" from three warp-uniform label reads per pair — a class is one
+          //  contiguous run of rows — instead of the per-lane comparison + vote below was measured 2 % SLOWER: the
+          //  vote overlaps the TMEM load, the uniform test sits in front of it.)
           const int i0 = c * 32 + lane, i1 = i0 + 32;
           const int ja = j0 + i0, jb = j0 + i1;
           uint32_t em1;
@@ -758,22 +804,25 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             epilogue_chunk<EPI>(acc0, meta.cadd + c * 32, meta.lab + c * 32, em0, qn, scale2, m, l, flush);
             epilogue_chunk<EPI>(acc1, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, em1, qn, scale2, m, l, flush);
           }
-          if (p.sets >= 2) {
+          if (n_sets >= 2) {
             // class left open after this pair (none if its last valid column closed a class or is padding)
             const int j_last = j0 + (c + 2) * 32 - 1;
             open_cls = (j_last < n1 && !(em1 >> 31)) ? meta.lab[(c + 2) * 32 - 1] : -1;
           }
         }
-        // all TMEM reads of this accumulator are complete -> hand it back to the (leader's) MMA warp
+        // all TMEM reads of this accumulator are complete -> hand it back to the (leader's) MMA warp, and the
+        // metadata slot to the producer
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (NCTA == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tempty[as]), 0));
           else mbar_arrive(smem_u32(&tail->tempty[as]));
+          if (bulk) mbar_arrive(smem_u32(&tail->mempty[ms]));
         }
+        if (bulk) ++mc;
       }
       // two sets: the unit's last columns may belong to the other set; close what this set still holds
-      if (MODE == MODE_CLASS_LSE && p.sets >= 2 && open_cls >= 0) flush(open_cls, m, l);
+      if (MODE == MODE_CLASS_LSE && n_sets >= 2 && open_cls >= 0) flush(open_cls, m, l);
     }
     if (probe) {
       atomicAdd(p.clock_probe + 2 * blockIdx.x, (unsigned long long)(clock64() - probe_c0));
@@ -1208,6 +1257,14 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
       return e && *e ? atoi(e) : 0;
     }();
     p.stagger_ns = stagger;
+    static const int bulk_meta = [] {  // developer knob: 0 = every tile's metadata staged by the epilogue sets
+      const char* e = getenv("NW_B200_META_BULK");
+      return e && *e ? atoi(e) : 1;
+    }();
+    // bulk copies need 16-byte aligned sources (tile offsets are multiples of 1 KB)
+    const bool aligned = (reinterpret_cast<uintptr_t>(labels) & 15u) == 0 &&
+                         (epilogue != NW_EPI_EUCLID || (reinterpret_cast<uintptr_t>(s_sqnorm) & 15u) == 0);
+    p.meta_bulk = (bulk_meta != 0 && aligned) ? 1 : 0;
   }
   p.row_lse = p.p_query = nullptr;
   p.qlabel = nullptr;
@@ -1305,6 +1362,7 @@ extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, co
   p.tiles_per_chunk = plan.tiles_per_chunk;
   p.scale_log2 = scale * kLog2e;
   p.sets = 2;
+  p.meta_bulk = 0;
   p.emit_out = out;
   p.emit_ld = ld_out;
   p.emit_kind = emit_kind;

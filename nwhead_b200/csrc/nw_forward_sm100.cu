@@ -59,10 +59,11 @@ constexpr int NW_MAX_PEERS = 16;
 // NCTA = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x 256 tile (UMMA M=256); each CTA stages
 //           its own 128 query rows and HALF of the support tile, so L2->SM traffic and shared-memory operand
 //           reads per FLOP drop by a third and the smaller stages allow a 6-deep TMA ring.
-template <int NCTA, int MODE = 0>
+template <int NCTA, int MODE = 0, bool QUAD = false>
 struct Cfg {
-  // the emit modes give one ring stage up for the per-warp transpose buffers of their epilogue
-  static constexpr int STAGES = (NCTA == 1 ? 4 : 6) - (MODE == 0 ? 0 : 1);
+  // the emit modes give ring stages up for the per-warp transpose buffers of their epilogue (8 warps: one stage,
+  // the 16 warps of the QUAD variant: two)
+  static constexpr int STAGES = (NCTA == 1 ? 4 : 6) - (MODE == 0 ? 0 : (QUAD ? 2 : 1));
   static constexpr int B_ROWS = BN / NCTA;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -99,7 +100,7 @@ struct SmemTail {
   TileMeta mslot[META_SLOTS];                       // class-LSE: tile metadata delivered by the producer (bulk copies)
   uint64_t mfull[META_SLOTS];
   uint64_t mempty[META_SLOTS];
-  float stage[MODE == 0 ? 1 : MAX_EPI_WARPS][32][33];  // emit modes: per-warp 32x32 transpose buffers
+  float stage[MODE == 0 ? 1 : (QUAD ? 4 * QUAD_SETS : MAX_EPI_WARPS)][32][33];  // emit modes: per-warp 32x32 transpose buffers
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
   uint64_t tfull[ACC_STAGES];
@@ -109,7 +110,7 @@ struct SmemTail {
 
 template <int NCTA, int MODE, bool QUAD = false>
 constexpr size_t smem_bytes() {
-  return 1024 /*align slack*/ + size_t(Cfg<NCTA, MODE>::STAGES) * Cfg<NCTA, MODE>::STAGE_BYTES +
+  return 1024 /*align slack*/ + size_t(Cfg<NCTA, MODE, QUAD>::STAGES) * Cfg<NCTA, MODE, QUAD>::STAGE_BYTES +
          sizeof(SmemTail<MODE, QUAD>);
 }
 
@@ -444,7 +445,7 @@ template <int EPI, int NCTA, int MODE, bool QUAD = false>
 __global__ void __launch_bounds__(QUAD ? QUAD_THREADS : MAX_THREADS, 1)
 nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_s,
                   const __grid_constant__ Params p) {
-  using C = Cfg<NCTA, MODE>;
+  using C = Cfg<NCTA, MODE, QUAD>;
   constexpr int STAGES = C::STAGES;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -719,6 +720,21 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int c = 2 * eg; c < BN / 32; c += c_step) {
           if (MODE != MODE_CLASS_LSE) {
             constexpr bool INFL = MODE == MODE_EMIT_INFLUENCE;
+            if (QUAD) {
+              // 16 epilogue warps, 96 registers: one 32-column chunk in registers at a time
+              const int row0 = (qg * NCTA + int(cta_rank)) * BM + ew * 32;
+              float(*stg)[33] = tail->stage[warp - EPI_WARP0];
+#pragma unroll 1
+              for (int cc = c; cc < c + 2; ++cc) {
+                float acc[32];
+                tmem_ld_32x32(t_addr + cc * 32, acc);
+                tmem_ld_wait();
+                emit_chunk<EPI, INFL>(acc, meta.cadd + cc * 32, meta.lab + cc * 32, qn, p.scale_log2 * kLn2, e_z, e_p, e_qy,
+                                      stg, lane, p.emit_out, p.emit_ld, row0, p.n_query, j0 + cc * 32, n1 - (j0 + cc * 32),
+                                      p.emit_vec != 0);
+              }
+              continue;
+            }
             float acc0[32], acc1[32];
             tmem_ld_32x32(t_addr + c * 32, acc0);
             tmem_ld_32x32(t_addr + (c + 1) * 32, acc1);
@@ -1376,9 +1392,25 @@ extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, co
                         : k1::launch_forward<NW_EPI_EUCLID, 1, MODE_>(map_q, map_s, p, plan.grid, stream))          \
            : (ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2, MODE_>(map_q, map_s, p, plan.grid, stream)           \
                         : k1::launch_forward<NW_EPI_LINEAR, 1, MODE_>(map_q, map_s, p, plan.grid, stream))
+  static const int emit_sets = [] {  // developer knob: 2 = the influence emit runs the 8-warp epilogue as well
+    const char* e = getenv("NW_B200_EMIT_SETS");
+    return e && *e ? atoi(e) : 4;
+  }();
+  // The influence transform (exp, reciprocal, polynomial per pair) is latency-bound with two warps per scheduler:
+  // four epilogue sets, at the price of two ring stages (config 5 from features, bf16: 2.29 -> 1.70 ms).  Dense
+  // scores keep two sets: four gave +4.5 % with one bf16 pass and -7 % with the three passes of bf16x3.
+#define NW_LAUNCH_EMIT4(MODE_)                                                                                         \
+  rc = euc ? (ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2, MODE_, true>(map_q, map_s, p, plan.grid, stream)           \
+                        : k1::launch_forward<NW_EPI_EUCLID, 1, MODE_, true>(map_q, map_s, p, plan.grid, stream))          \
+           : (ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2, MODE_, true>(map_q, map_s, p, plan.grid, stream)           \
+                        : k1::launch_forward<NW_EPI_LINEAR, 1, MODE_, true>(map_q, map_s, p, plan.grid, stream))
   if (emit_kind == NW_EMIT_SCORES) NW_LAUNCH_EMIT(k1::MODE_EMIT_SCORES);
-  else if (emit_kind == NW_EMIT_INFLUENCE) NW_LAUNCH_EMIT(k1::MODE_EMIT_INFLUENCE);
+  else if (emit_kind == NW_EMIT_INFLUENCE && emit_sets == 4) {
+    p.sets = k1::QUAD_SETS;
+    NW_LAUNCH_EMIT4(k1::MODE_EMIT_INFLUENCE);
+  } else if (emit_kind == NW_EMIT_INFLUENCE) NW_LAUNCH_EMIT(k1::MODE_EMIT_INFLUENCE);
   else NW_LAUNCH_EMIT(k1::MODE_EMIT_BLOCKBEST);
+#undef NW_LAUNCH_EMIT4
 #undef NW_LAUNCH_EMIT
   return rc;
 }

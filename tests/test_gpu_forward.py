@@ -164,16 +164,18 @@ def test_dense_scores_on_tensor_cores(cuda_lib, kind):
     assert np.abs(got1 - ref).max() < 0.08 * max(1.0, np.abs(ref).max() / 8)
 
 
-def test_support_influence_from_features(cuda_lib):
+@pytest.mark.parametrize("case", [(20, 50, 512, 96, "euclidean"), (20, 51, 512, 300, "euclidean"),
+                                  (12, 77, 128, 300, "cosine"), (6, 300, 2048, 130, "euclidean")])
+def test_support_influence_from_features(cuda_lib, case):
     """Influence computed from features (two tensor-core passes) == the reference formula fed with the exact
-    softmax weights (oracle), BASELINE config 5 shapes scaled down."""
+    softmax weights (oracle), BASELINE config 5 shapes scaled down; single CTAs and CTA pairs, ragged last tile."""
     from nwhead_b200 import SupportBank
 
-    C, per, d, B = 20, 50, 512, 96
+    C, per, d, B, kind = case
     q, s, y, qy = clustered_features(C, per, d, B, seed=21)
-    bank = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, "euclidean", "bf16x3")
+    bank = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, kind, "bf16x3")
     got = bank.support_influence(torch.from_numpy(q).to(DEV), torch.from_numpy(qy).to(DEV)).cpu().numpy()
-    sc = O.pairwise_scores(q, s, "euclidean")
+    sc = O.pairwise_scores(q, s, kind)
     w = np.exp(sc - sc.max(1, keepdims=True))
     w /= w.sum(1, keepdims=True)
     P = np.zeros((B, C))
@@ -350,3 +352,30 @@ def test_small_bank_graph_replay_is_transparent(cuda_lib):
             assert torch.equal(head(qt, bank), want)
     finally:
         del os.environ["NW_B200_GRAPHS"]
+
+
+@pytest.mark.parametrize("kind", ["euclidean", "cosine"])
+@pytest.mark.parametrize("shape", [(300, 9, 400, 128), (40, 9, 400, 512), (300, 9, 400, 1024), (300, 5, 700, 2048)])
+def test_tile_metadata_paths_agree(cuda_lib, shape, kind):
+    """Interior tiles get their |s|^2 / labels from the TMA producer (bulk copies, 16-byte aligned arrays); edge
+    tiles and unaligned arrays are staged by the epilogue sets.  Both must give the same bits, for 1 / 2 / 4
+    epilogue sets and for the single-CTA schedule."""
+    from nwhead_b200 import SupportBank
+
+    B, C, per, d = shape
+    q, s, y, _ = clustered_features(C, per, d, B, seed=17 + d)
+    bank = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), C, kind, "bf16")
+    qd = torch.from_numpy(q).to(DEV)
+    aligned = bank.forward(qd).clone()
+    assert bank.sqnorm.data_ptr() % 16 == 0 and bank.labels.data_ptr() % 16 == 0
+    n = bank.labels.numel()
+    sq = torch.empty(n + 1, dtype=bank.sqnorm.dtype, device=DEV)
+    lab = torch.empty(n + 1, dtype=bank.labels.dtype, device=DEV)
+    sq[1:].copy_(bank.sqnorm)
+    lab[1:].copy_(bank.labels)
+    bank.sqnorm, bank.labels = sq[1:], lab[1:]  # same values, 4 bytes off alignment -> staged path for every tile
+    assert bank.labels.data_ptr() % 16 == 4
+    staged = bank.forward(qd)
+    torch.cuda.synchronize()
+    assert torch.equal(aligned, staged)
+    assert_head_parity(aligned, O.nw_forward(q, s, y, C, kind))

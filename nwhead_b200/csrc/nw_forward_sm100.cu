@@ -869,13 +869,15 @@ __device__ __forceinline__ float logaddexp_f(float a, float b) {
   return mx + log1pf(expf(-fabsf(a - b)));
 }
 
-// Apply the chunk-boundary partials in chunk order (fixed order => bitwise reproducible).
-// A class that is cut by a chunk boundary receives ALL of its mass through `side` (never a direct store), and
-// the cut classes appear in non-decreasing order along the chunks, so the (class, value) pairs are run-length
-// merged in registers and each class is written once: no read-modify-write chain through global memory.
-// One WARP per query row: the lanes fetch the entries of 32 chunks at once (one memory latency per 32 chunks —
-// with one thread per row the 148 dependent round trips of a small-batch step cost 170 us of its 950), then
-// every lane replays the same in-order merge from registers through shuffles and lane 0 stores.
+// Apply the chunk-boundary partials (fixed combination order => bitwise reproducible).
+// A class that is cut by a chunk boundary receives ALL of its mass through `side` (never a direct store): every chunk
+// contributes two entries, (first class, head partial) and (last class, tail partial), each split over the epilogue
+// sets.  Along the chunks the entries of one class are adjacent (a class is one contiguous run of support rows), so
+// the merge is a SEGMENTED SCAN: one warp per query row, one entry per lane (the lane folds the sets' partials of
+// its entry), five shuffle steps per 32 entries, every segment's last lane stores its class, and a segment that
+// continues into the next 32 entries is carried.  (History: one thread per row paid one memory round trip per chunk
+// — 170 us of a 950 us small-batch step; a warp replaying the entries serially through log1pf(expf()) was 22 us of a
+// 50 us config-1 head call, 9.8 us with the sets pre-combined.)
 struct TableList {
   float* t[NW_MAX_PEERS];
   int n;
@@ -892,65 +894,53 @@ __global__ void __launch_bounds__(MERGE_ROWS_PER_BLOCK * 32) merge_side_kernel(
   if (b >= n_query) return;  // uniform per warp
   const size_t row_off = size_t(b) * n_classes;
   const float neg_inf = __int_as_float(0xff800000);
-  int cur = -1;
-  float acc = neg_inf;
-  auto put = [&](int cls, float v) {
-    if (lane != 0) return;
+  // log(exp(a) + exp(b)), -inf = "nothing"; fast intrinsics (absolute error < 5e-7), symmetric in its arguments
+  auto lae = [&](float x, float y) {
+    if (x == neg_inf) return y;
+    if (y == neg_inf) return x;
+    return fmaxf(x, y) + __logf(1.0f + __expf(-fabsf(x - y)));
+  };
+  auto put = [&](int cls, float v) {  // by the calling lane
     if (tables.rows_per_table > 0) tables.t[b / tables.rows_per_table][row_off + cls] = v;
     else
       for (int r = 0; r < tables.n; ++r) tables.t[r][row_off + cls] = v;
   };
-  // log(exp(a) + exp(b)) for finite a, b with the fast intrinsics (absolute error < 5e-7): this is the serial part
-  auto lae = [](float a, float b) { return fmaxf(a, b) + __logf(1.0f + __expf(-fabsf(a - b))); };
-  auto add = [&](int cls, float v) {
-    if (v == neg_inf) return;
-    if (cls != cur) {
-      if (cur >= 0) put(cur, acc);
-      cur = cls;
-      acc = v;  // first entry of the class: nothing to combine with
-    } else {
-      acc = lae(acc, v);
-    }
-  };
-  for (int base = 0; base < chunks; base += 32) {
-    const int g = base + lane;
-    int c0 = 0, c1 = 0;
-    float v[2 * QUAD_SETS];  // [slot][set]
-#pragma unroll
-    for (int i = 0; i < 2 * QUAD_SETS; ++i) v[i] = neg_inf;
-    if (g < chunks) {
+  const int n_entries = 2 * chunks;
+  int carry_cls = -1;
+  float carry_val = neg_inf;
+  for (int base = 0; base < n_entries; base += 32) {
+    const int e = base + lane;
+    int cls = -2;  // lanes past the last entry: a class nobody has, nothing to add
+    float val = neg_inf;
+    if (e < n_entries) {
+      const int g = e >> 1, slot = e & 1;
       const int t0 = g * tiles_per_chunk;
       const int t1 = min(t0 + tiles_per_chunk, s_tiles);
-      c0 = __ldg(labels + size_t(t0) * BN);
-      c1 = __ldg(labels + min(size_t(t1) * BN, size_t(n_support)) - 1);
-      const float* sr = side + (size_t(g) * n_query + b) * 2 * sets;
+      cls = slot ? __ldg(labels + min(size_t(t1) * BN, size_t(n_support)) - 1) : __ldg(labels + size_t(t0) * BN);
+      const float* sr = side + ((size_t(g) * n_query + b) * 2 + slot) * sets;
 #pragma unroll
-      for (int i = 0; i < QUAD_SETS; ++i) {
-        if (i < sets) {
-          v[i] = sr[i];
-          v[QUAD_SETS + i] = sr[sets + i];
-        }
+      for (int i = 0; i < QUAD_SETS; ++i)
+        if (i < sets) val = lae(val, sr[i]);
+    }
+    if (carry_cls >= 0) {  // warp-uniform: the previous 32 entries ended inside a class
+      if (__shfl_sync(0xffffffffu, cls, 0) == carry_cls) {
+        if (lane == 0) val = lae(carry_val, val);
+      } else if (lane == 0 && carry_val != neg_inf) {
+        put(carry_cls, carry_val);
       }
     }
-    // the epilogue sets' partials of a chunk's two cut classes are combined by the chunk's own lane (all lanes in
-    // parallel); only the walk along the chunks is serial.  (Replaying every set's entry serially, each through
-    // log1pf(expf()), made this kernel 22 us of a 50 us config-1 head call.)
-    float s0 = neg_inf, s1 = neg_inf;
 #pragma unroll
-    for (int i = 0; i < QUAD_SETS; ++i) {  // unused sets stay -inf
-      const float a = v[i], c = v[QUAD_SETS + i];
-      if (a != neg_inf) s0 = s0 == neg_inf ? a : lae(s0, a);
-      if (c != neg_inf) s1 = s1 == neg_inf ? c : lae(s1, c);
+    for (int off = 1; off < 32; off <<= 1) {
+      const int oc = __shfl_up_sync(0xffffffffu, cls, off);
+      const float ov = __shfl_up_sync(0xffffffffu, val, off);
+      if (lane >= off && oc == cls) val = lae(ov, val);
     }
-    const int cnt = min(32, chunks - base);
-    for (int j = 0; j < cnt; ++j) {
-      const int jc0 = __shfl_sync(0xffffffffu, c0, j), jc1 = __shfl_sync(0xffffffffu, c1, j);
-      const float js0 = __shfl_sync(0xffffffffu, s0, j), js1 = __shfl_sync(0xffffffffu, s1, j);
-      add(jc0, js0);
-      add(jc1, js1);
-    }
+    const int next_cls = __shfl_down_sync(0xffffffffu, cls, 1);
+    if (lane < 31 && next_cls != cls && cls >= 0 && val != neg_inf) put(cls, val);  // last entry of its class
+    carry_cls = __shfl_sync(0xffffffffu, cls, 31);
+    carry_val = __shfl_sync(0xffffffffu, val, 31);
   }
-  if (cur >= 0) put(cur, acc);
+  if (lane == 0 && carry_cls >= 0 && carry_val != neg_inf) put(carry_cls, carry_val);
 }
 
 // logp[b,c] = log(exp(L[b,c] - logsumexp_c L[b,:]) + 1e-12)   (reference nwhead/nw.py:285-289)

@@ -197,6 +197,14 @@ struct Flusher {
   __device__ __forceinline__ void single(int cls, float v) const {
     if (row >= 0) store_class(p, row, set, cls, v);
   }
+  // This row of the ONE table every final class value of this thread goes to, or NULL (peer-GPU routes, row beyond
+  // the batch): lets the one-row-per-class path store inline.
+  __device__ __forceinline__ float* local_row_table() const {
+    if (row < 0) return nullptr;
+    if (p->sets >= 2) return p->lse[set] + size_t(row) * p->n_classes;
+    if (p->rows_per_table == 0 && p->n_tables == 1) return p->lse[0] + size_t(row) * p->n_classes;
+    return nullptr;
+  }
   // the class of column label `cls` continues into the next chunk (its sum is not final here)
   __device__ __forceinline__ bool tail_cut_class(int cls) const {
     const int4 u = lds_int4(unit_addr);
@@ -335,6 +343,9 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
     if (EPI == NW_EPI_EUCLID) acc[i] = fmaf(acc[i], -kLog2e, -m);
     else acc[i] = acc[i] - m;
   }
+  // cluster / random mode banks hold ONE support per class: every column is a class end, and a call per column
+  // (256 per tile and thread) made the config-4 predict kernel 121 us for 9 us of MMAs; those values are stored inline
+  float* const row_tab = (emask & (emask >> 1)) != 0u ? flush.local_row_table() : nullptr;
 #pragma unroll
   for (int i4 = 0; i4 < 32; i4 += 4) {
     float e[4];
@@ -352,7 +363,8 @@ __device__ __forceinline__ void epilogue_chunk(float (&acc)[32], const float* __
         if (i > 0 && (emask & (1u << (i - 1))) && !flush.tail_cut_class(lab[i])) {
           // the previous column closed its class too, so this class has ONE row here (cluster / random mode
           // banks: one support per class): its log-sum-exp is simply its score; stored inline, no call
-          flush.single(lab[i], (acc[i] + m) * kLn2);
+          if (row_tab != nullptr) row_tab[lab[i]] = (acc[i] + m) * kLn2;
+          else flush.single(lab[i], (acc[i] + m) * kLn2);
         } else {
           flush(lab[i], m, l);
         }

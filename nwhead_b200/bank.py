@@ -69,6 +69,9 @@ class SupportBank:
         self.precision = precision
         self.d = d
         self.n_classes = n_classes
+        # row j is the one support of class j (cluster / random mode banks, nwhead/support.py:117-129 with one
+        # centroid or sample per class): the class log-sum-exp IS the score matrix, see class_lse_prepared
+        self.identity_classes = False
 
     def __len__(self):
         return self.feats_bf16.shape[1]
@@ -146,7 +149,11 @@ class SupportBank:
             center = None
         feats_bf16, sqnorm = rows_to_bf16(feats, perm=perm, center=center, normalize=kind in NORMALISED_KINDS,
                                           layout=_abi.ROWS_BANK, precision=prec)
-        return SupportBank(feats_bf16, sqnorm, labels_i32, offsets, perm, center, kind, prec, d, n_classes)
+        bank = SupportBank(feats_bf16, sqnorm, labels_i32, offsets, perm, center, kind, prec, d, n_classes)
+        if n == n_classes and not labels_validated:  # this path has synchronised already (label check above)
+            bank.identity_classes = bool(torch.equal(
+                offsets, torch.arange(n_classes + 1, dtype=torch.int32, device=dev)))
+        return bank
 
     # ------------------------------------------------------------------------------------------
     def subset(self, bank_rows: torch.Tensor) -> "SupportBank":
@@ -262,6 +269,17 @@ class SupportBank:
             )
             return None
         out = torch.empty((b, self.n_classes), dtype=torch.float32, device=dev)
+        if self.identity_classes:
+            # one support per class, in class order: L[b, c] = score(b, c).  The dense-score epilogue writes the
+            # table with coalesced 16-byte stores (config-4 predict: 57 us in the class-indexed epilogue, which
+            # stores one value per class end and thread)
+            check(
+                lib.nw_forward_emit(epi, float(scale), ptr(q_bf16), ptr(q_sq), b, ptr(self.feats_bf16),
+                                    ptr(self.sqnorm), None, n, self.row_elems, _abi.EMIT_SCORES, None, None, None,
+                                    ptr(out), self.n_classes, stream_of(dev)),
+                "nw_forward_emit",
+            )
+            return out
         check(
             lib.nw_forward_class_lse(epi, float(scale), ptr(q_bf16), ptr(q_sq), b, ptr(self.feats_bf16),
                                      ptr(self.sqnorm), ptr(self.labels), n, self.row_elems, self.n_classes,

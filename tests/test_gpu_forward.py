@@ -379,3 +379,26 @@ def test_tile_metadata_paths_agree(cuda_lib, shape, kind):
     torch.cuda.synchronize()
     assert torch.equal(aligned, staged)
     assert_head_parity(aligned, O.nw_forward(q, s, y, C, kind))
+
+
+def test_one_support_per_class_shortcut_and_its_near_miss(cuda_lib):
+    """N == C with every class present once: the class table is the score matrix (dense-score epilogue).  N == C with
+    one class twice and one absent must NOT take that route (absent class: exactly log(1e-12))."""
+    from nwhead_b200 import SupportBank
+
+    C, d, B = 300, 192, 70
+    q, s, y, _ = clustered_features(C, 1, d, B, seed=5, spread=0.25)
+    rng = np.random.default_rng(0)
+    order = rng.permutation(C)  # unsorted support: the bank sorts it
+    bank = SupportBank.build(torch.from_numpy(s[order]).to(DEV), torch.from_numpy(y[order]).to(DEV), C, "euclidean", "bf16")
+    assert bank.identity_classes
+    out = bank.forward(torch.from_numpy(q).to(DEV))
+    assert_head_parity(out, O.nw_forward(q, s[order], y[order], C, "euclidean"))
+    y2 = y.copy()
+    y2[7] = 8  # class 7 absent, class 8 twice
+    bank2 = SupportBank.build(torch.from_numpy(s).to(DEV), torch.from_numpy(y2).to(DEV), C, "euclidean", "bf16")
+    assert not bank2.identity_classes
+    out2 = bank2.forward(torch.from_numpy(q).to(DEV))
+    ref2 = O.nw_forward(q, s, y2, C, "euclidean")
+    assert_head_parity(out2, ref2)
+    assert np.allclose(out2[:, 7].cpu().numpy(), np.log(1e-12), atol=1e-5)

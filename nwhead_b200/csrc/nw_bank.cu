@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restri
   const int seg_lo = (layout == NW_ROWS_BANK) ? 2 * d : d;
   float sq = 0.f;
   if (VEC) {
+#pragma unroll 4  // several 16-byte loads in flight per lane: a 2048-wide row is 16 iterations
     for (int c = lane * 4; c < d; c += 128) {
       float4 v = *reinterpret_cast<const float4*>(src + c);
       if (center) {

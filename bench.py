@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--sustained-seconds", type=float, default=3.0)
+    ap.add_argument("--warmup-seconds", type=float, default=1.0,
+                    help="keep warming up (beyond --warmup steps) until this much wall time has passed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the bounded config 2/4/5 measurements (N=1)")
     ap.add_argument("--no-alt", action="store_true", help="skip the query-sharded / replicated-bank arm (N>1)")
@@ -591,17 +593,35 @@ def main():
         barrier()
         win = (w0, time.time())
         total = max_over_ranks(s0.elapsed_time(s1))
-        kern = max_over_ranks(statistics.mean(a.elapsed_time(b) for a, b in events))
+        per_step = [a.elapsed_time(b) for a, b in events]
+        kern = max_over_ranks(statistics.mean(per_step))
+        trace.append({"steps": n_steps, "window": win, "kernel_ms_per_step": per_step})
         return out, total, kern, win
 
+    trace = []  # per-step kernel times of every timed region (NW_BENCH_TRACE=<file> dumps them with the NVML samples)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     probe = ClockProbe(_abi, dev, plan.grid)
 
     # ---- device-resident throughput: the contract's number, exactly --steps steps
-    for _ in range(max(args.warmup, 3)):
-        logp, _ = step_resident()
+    # Warm-up: at least --warmup (>= 3) steps AND at least --warmup-seconds of back-to-back steps, so that the
+    # timed region starts at the GPU's operating point (memory and SM clocks up, power at its cap) and not
+    # somewhere on the ramp from idle; the count actually run is what the line reports as "warmup".
+    warm_events, warm_t0, n_warm = [], time.perf_counter(), 0
+    while True:
+        for _ in range(max(args.warmup, 3) if n_warm == 0 else 4):
+            logp, ev = step_resident()
+            warm_events.append(ev)
+            n_warm += 1
+        torch.cuda.synchronize()
+        more = torch.tensor([1 if time.perf_counter() - warm_t0 < args.warmup_seconds else 0], device=dev)
+        if world > 1:  # every rank must run the same number of steps (the exchange is collective)
+            dist.all_reduce(more, op=dist.ReduceOp.MAX)
+        if not int(more.item()):
+            break
+    trace.append({"steps": n_warm, "window": None, "what": "warm-up",
+                  "kernel_ms_per_step": [a.elapsed_time(b) for a, b in warm_events]})
     with probe:
         logp, total_ms, kern_ms, win_value = timed_resident(args.steps)
         mhz_value = probe.mhz()
@@ -709,7 +729,7 @@ def main():
         sus_tflops = flops_launch / (sus_kern_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": B * args.steps / (total_ms * 1e-3), "unit": "queries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
                 "workload": f"NWHead full-mode inference: support N={N} d={d} C={C}, query batch B={B} (half of the "
@@ -729,7 +749,9 @@ def main():
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": "nw_forward_kernel<EUCLID> (+ its -inf fill and chunk-boundary merge launches)",
-                         "kernel_ms": kern_ms, "flops_per_launch": flops_launch,
+                         "kernel_ms": kern_ms, "kernel_ms_min_max": [min(trace[1]["kernel_ms_per_step"]),
+                                                                     max(trace[1]["kernel_ms_per_step"])],
+                         "flops_per_launch": flops_launch,
                          "peak_kind": f"{peak_kind} cuBLAS bf16, {peaks['source']}",
                          "sm_mhz_in_kernel": mhz_value,
                          "tensor_pipe_busy_at_that_clock": pipe_frac(kern_ms, mhz_value)},
@@ -755,6 +777,9 @@ def main():
             except Exception as e:  # the secondary measurements must never cost the headline line
                 line["aux"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         print(json.dumps(line), flush=True)
+        if os.environ.get("NW_BENCH_TRACE"):
+            with open(os.environ["NW_BENCH_TRACE"], "w") as f:
+                json.dump({"regions": trace, "nvml": [[r[0], r[1], r[2], r[3]] for r in sampler.rows]}, f)
         for msg in failed:
             print(f"bench: CHECK FAILED — {msg}", file=sys.stderr, flush=True)
     fail_flag = torch.tensor([1 if failed else 0], device=dev)

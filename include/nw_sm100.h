@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NW_ABI_VERSION 2
+#define NW_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define NW_API __attribute__((visibility("default")))
@@ -202,6 +202,35 @@ NW_API int nw_forward_emit(int epilogue, float scale, const void* q_bf16, const 
                     const void* bank_bf16, const float* s_sqnorm, const int32_t* labels, int64_t n_support,
                     int row_elems, int emit_kind, const float* row_lse, const float* p_query,
                     const int32_t* qlabel, float* out, int64_t ld_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core backward of NWHead.forward against a large shared support (the autograd of
+ * nwhead/nw.py:266-289 as triggered at train.py:414) in three tensor-core passes:
+ *   1. nw_backward_coefficients, orientation 0 and / or 1: recompute the scores (same GEMM as the forward) and turn
+ *      each into w(b, j) = dL/dscore(b, j) [/ distance], rounded to bf16, stored as the A operand of step 2;
+ *   2. nw_dense_products: grad_q = W S - rowsum(W) q  and  grad_s = W^t Q - colsum(W) s   (euclidean), or
+ *      grad_q = W S, grad_s = W^t Q (linear scores), with split-K for skinny problems.
+ * With P(b, c) = exp(class_lse[b, c] - row_lse[b]) and g = dL/dlogp, the caller supplies the table
+ *   T(b, c) = g(b, c) / (P(b, c) + 1e-12) - sum_c' g(b, c') P(b, c') / (P(b, c') + 1e-12)
+ * (orientation 0: T as (B, table_ld); orientation 1: its transpose (C, table_ld >= B)).
+ *
+ * rows / cols: the two operands in the fused forward's k-block-major bf16 layout with their squared norms
+ * (euclidean).  Orientation 0: rows = queries (row_lse (B) required), cols = class-sorted bank (col_labels int32
+ * required).  Orientation 1: rows = bank (row_labels required), cols = queries (col_lse required).
+ * out_bf16: (ceil(n_cols / 64), n_rows, 64) bf16, ZEROED by the caller (padding columns are not written):
+ * out[j / 64][r][j % 64] = w(r, j). */
+NW_API int nw_backward_coefficients(int epilogue, float scale, int orientation, const void* rows_bf16,
+                             const float* rows_sqnorm, int64_t n_rows, const void* cols_bf16,
+                             const float* cols_sqnorm, int64_t n_cols, int row_elems, const float* row_lse,
+                             const int32_t* row_labels, const float* col_lse, const int32_t* col_labels,
+                             const float* table, int64_t table_ld, void* out_bf16, void* stream);
+
+/* out[ks][r][c] = sum over the k-blocks of K slice ks of a[r][k] * b[c][k]; a (k_elems/64, n_a, 64) and
+ * b (k_elems/64, n_b, 64) bf16 k-block-major, out fp32 row-major (n_a, ld_out >= n_b) per slice, slices
+ * slice_stride floats apart.  The number of slices actually written is ceil(kblocks / ceil(kblocks / kslices))
+ * (no slice is empty); the caller sums them. */
+NW_API int nw_dense_products(const void* a_bf16, int64_t n_a, const void* b_bf16, int64_t n_b, int k_elems,
+                      int kslices, float* out, int64_t ld_out, int64_t slice_stride, void* stream);
 
 /* logp[b, c] = log( exp(class_lse[b,c] - logsumexp_c class_lse[b,:]) + 1e-12 )  (nwhead/nw.py:285-289).
  * With a sharded bank, all-reduce class_lse with MAX across ranks first (each class is owned by one

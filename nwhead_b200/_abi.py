@@ -65,6 +65,11 @@ SIGNATURES = {
                                            c_int64, c_void_p]),
     "nw_forward_emit": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "nw_backward_coefficients": (c_int, [c_int, c_float, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                         c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                         c_void_p, c_void_p]),
+    "nw_dense_products": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int64,
+                                  c_void_p]),
     "nw_logp_from_class_lse": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "nw_row_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nw_class_lse_merge": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
@@ -152,7 +157,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.nw_abi_version() != 2:
+    if lib.nw_abi_version() != 3:
         raise NWLibraryError("libnw_sm100.so ABI version mismatch")
     _lib = _DeviceBoundLib(lib)
     return _lib

@@ -1,0 +1,166 @@
+"""Tensor-core forward + backward of NWHead.forward against a LARGE shared support.
+
+The reference differentiates `NWHead.forward` (nwhead/nw.py:266-289) with plain autograd (train.py:414), whatever
+the support size.  The direct fp32 kernels (nw_direct_backward) cover episodic training and are HBM-bound for a few
+dozen queries; for a big batch against a big support the work is four dense contractions of 2*B*N*d FLOP each, and
+they belong on the tensor cores (closed form: SURVEY.md B.2):
+
+    forward   class log-sum-exp table L (B, C)                      fused forward (nw_forward_class_lse)
+    backward  T(b, c) = g/(P + 1e-12) - sum_c' g P/(P + 1e-12)      (B, C) host-side table, P = softmax_c L
+              W  (B, N) = dL/dscore [/ distance], bf16              nw_backward_coefficients, orientation 0
+              W^t (N, B)                                            nw_backward_coefficients, orientation 1
+              grad_q = W S   - rowsum(W) q                          nw_dense_products (split-K over the supports)
+              grad_s = W^t Q - colsum(W) s                          nw_dense_products
+    (linear scores: grad_q = W S, grad_s = W^t Q; normalised kernels chain through the normalisation.)
+
+Accuracy: scores are recomputed from bf16 operands exactly as in the forward and the coefficients are rounded to
+bf16, so gradients carry ~2^-9 relative rounding per term (tests: <= 2e-2 of the gradient's max-abs against the
+float64 closed form) — the usual bf16 training trade; the direct path stays the default for small problems.
+"""
+import torch
+
+from . import _abi
+from ._abi import check, load, ptr, stream_of
+from .bank import EUCLID_KINDS, NORMALISED_KINDS, SupportBank, logp_from_class_lse
+
+# NWHead.forward takes this path when gradients are needed, the support is shared (2-D) and the problem is at
+# least this big (below it the direct fp32 kernels are within a small factor of their HBM bound)
+MIN_QUERIES = 64
+MIN_PAIRS = 1 << 24
+
+
+def transpose_operand(x: torch.Tensor) -> torch.Tensor:
+    """k-block-major bf16 rows (kb, R, 64) -> the same matrix TRANSPOSED, k-block-major over the rows:
+    (ceil(R / 64), kb * 64, 64), out[r / 64][f][r % 64] = x[f / 64][r][f % 64] (zero rows appended).  A pure
+    permutation of bf16 elements (device-memory plumbing, once per operand)."""
+    kb, r, _ = x.shape
+    rp = (r + 63) // 64 * 64
+    if rp != r:
+        x = torch.nn.functional.pad(x, (0, 0, 0, rp - r))
+    return x.view(kb, rp // 64, 64, 64).permute(1, 0, 3, 2).reshape(rp // 64, kb * 64, 64).contiguous()
+
+
+def backward_table(class_lse: torch.Tensor, grad_logp: torch.Tensor):
+    """(row_lse (B,), T (B, C)) from the class log-sum-exp table and dL/dlogp (see the module docstring)."""
+    row_lse = torch.logsumexp(class_lse, dim=1)
+    p = torch.exp(class_lse - row_lse[:, None])
+    g = grad_logp / (p + 1e-12)
+    return row_lse.contiguous(), (g - (g * p).sum(1, keepdim=True)).contiguous()
+
+
+def coefficients(bank: SupportBank, q_bf16, q_sq, row_lse, table, scale: float, orientation: int):
+    """orientation 0: W (ceil(N/64), B, 64); orientation 1: W^t (ceil(B/64), N, 64) — bf16, zero padded."""
+    lib = load()
+    dev = bank.device
+    b, n = q_bf16.shape[1], len(bank)
+    epi = _abi.EPI_EUCLID if bank.kind in EUCLID_KINDS else _abi.EPI_LINEAR
+    if orientation == 0:
+        out = torch.zeros(((n + 63) // 64, b, 64), dtype=torch.bfloat16, device=dev)
+        check(lib.nw_backward_coefficients(epi, float(scale), 0, ptr(q_bf16), ptr(q_sq), b, ptr(bank.feats_bf16),
+                                           ptr(bank.sqnorm), n, bank.row_elems, ptr(row_lse), None, None,
+                                           ptr(bank.labels), ptr(table), table.stride(0), ptr(out), stream_of(dev)),
+              "nw_backward_coefficients")
+    else:
+        out = torch.zeros(((b + 63) // 64, n, 64), dtype=torch.bfloat16, device=dev)
+        table = table.t().contiguous()  # (C, B): the row's class selects a contiguous run over the queries
+        check(lib.nw_backward_coefficients(epi, float(scale), 1, ptr(bank.feats_bf16), ptr(bank.sqnorm), n,
+                                           ptr(q_bf16), ptr(q_sq), b, bank.row_elems, None, ptr(bank.labels),
+                                           ptr(row_lse), None, ptr(table), table.stride(0), ptr(out), stream_of(dev)),
+              "nw_backward_coefficients")
+    return out
+
+
+def dense_products(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a (kb, n_a, 64), b (kb, n_b, 64) bf16 k-block-major -> a @ b^t (n_a, n_b) fp32 on the tensor cores.
+    Skinny problems are split along K so that every SM has a unit; the partial products are summed here."""
+    lib = load()
+    kb, n_a, _ = a.shape
+    n_b = b.shape[1]
+    assert b.shape[0] == kb and a.dtype == b.dtype == torch.bfloat16
+    dev = a.device
+    plan = _abi.forward_plan(n_a, n_b)
+    units = plan.chunks * plan.q_tiles
+    workers = torch.cuda.get_device_properties(dev).multi_processor_count // (2 if plan.cta_pair else 1)
+    kslices = max(1, min(workers // max(units, 1), kb // 8))
+    per = -(-kb // kslices)
+    kslices = -(-kb // per)  # the library's own rounding: no empty slice
+    ld = (n_b + 3) // 4 * 4
+    out = torch.empty((kslices, n_a, ld), dtype=torch.float32, device=dev)
+    check(lib.nw_dense_products(ptr(a), n_a, ptr(b), n_b, kb * 64, kslices, ptr(out), ld, n_a * ld, stream_of(dev)),
+          "nw_dense_products")
+    res = out[0] if kslices == 1 else out.sum(0)
+    return res[:, :n_b]
+
+
+class NWTensorFunction(torch.autograd.Function):
+    """NWHead.forward(x, sx, sy) for a 2-D support on the tensor cores, forward and backward."""
+
+    @staticmethod
+    def forward(ctx, x, sx, sy, logit_scale, kind, n_classes):
+        scale = float(logit_scale.detach().exp()) if logit_scale is not None else 1.0
+        bank = SupportBank.build(sx, sy, n_classes, kind, "bf16")  # raises like F.one_hot on a bad label
+        q_bf16, q_sq = bank.prepare_queries(x)
+        class_lse = bank.class_lse_prepared(q_bf16, q_sq, scale)
+        ctx.bank, ctx.scale, ctx.kind = bank, scale, kind
+        ctx.has_scale = logit_scale is not None
+        ctx.save_for_backward(x, sx, q_bf16, q_sq, class_lse)
+        return logp_from_class_lse(class_lse)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, sx, q_bf16, q_sq, class_lse = ctx.saved_tensors
+        bank, scale, kind = ctx.bank, ctx.scale, ctx.kind
+        need_q, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_scale = ctx.has_scale and ctx.needs_input_grad[3]
+        d = bank.d
+        euclid = kind in EUCLID_KINDS
+        normalised = kind in NORMALISED_KINDS
+        row_lse, table = backward_table(class_lse, grad_out.float())
+
+        def stored_rows(t_bf16):
+            """the rows the scores were computed from — centred / normalised AND rounded to bf16 — as fp32 (R, d):
+            grad = W S - rowsum(W) q must take q from the same rounded operands as S, or the two terms of a close
+            (query, support) pair do not cancel"""
+            return t_bf16.permute(1, 0, 2).reshape(t_bf16.shape[1], -1)[:, :d].float()
+
+        def through_normalisation(g_hat, raw):
+            """gradient with respect to the normalised row -> gradient with respect to the raw row"""
+            if not normalised:
+                return g_hat
+            norm = raw.norm(dim=1, keepdim=True).clamp_min(1e-12)
+            unit = raw / norm
+            return (g_hat - (g_hat * unit).sum(1, keepdim=True) * unit) / norm
+
+        gq = gs = gscale = None
+        if need_q or need_scale:
+            w = coefficients(bank, q_bf16, q_sq, row_lse, table, scale, 0)
+            g_hat = dense_products(w, transpose_operand(bank.feats_bf16))[:, :d]
+            xq = stored_rows(q_bf16)
+            if euclid:
+                g_hat = g_hat - w.sum(dim=(0, 2), dtype=torch.float32)[:, None] * xq
+            del w
+            if need_scale:  # d score / d logit_scale = score, and sum_j coef * score = q_hat . grad_q_hat
+                gscale = (g_hat * xq).sum()
+            if need_q:
+                gq = through_normalisation(g_hat, x)
+        if need_s:
+            wt = coefficients(bank, q_bf16, q_sq, row_lse, table, scale, 1)
+            g_hat = dense_products(wt, transpose_operand(q_bf16))[:, :d]
+            if euclid:
+                g_hat = g_hat - wt.sum(dim=(0, 2), dtype=torch.float32)[:, None] * stored_rows(bank.feats_bf16)
+            del wt
+            g_sorted = through_normalisation(g_hat, sx if bank.perm is None else sx[bank.perm])
+            if bank.perm is None:
+                gs = g_sorted
+            else:
+                gs = torch.empty_like(g_sorted)
+                gs[bank.perm] = g_sorted
+        return gq, gs, None, gscale, None, None
+
+
+def wants_tensor_path(n_query: int, n_support: int, support_dims: int, mode: str) -> bool:
+    if mode == "direct" or support_dims != 2:
+        return False
+    if mode == "tensor":
+        return True
+    return n_query >= MIN_QUERIES and n_query * n_support >= MIN_PAIRS

@@ -145,13 +145,23 @@ struct Params {
   unsigned long long* clock_probe;  // diagnostics (nw_forward_set_clock_probe) or NULL: per-CTA SM cycles + ns
   const float* row_lse;      // (B) logsumexp_j score(b, j)          [influence]
   const float* p_query;      // (B) softmax mass of the query's class [influence]
-  const int32_t* qlabel;     // (B) query labels                      [influence]
+  const int32_t* qlabel;     // (B) query labels                      [influence]; row labels [coefficients, orientation 1]
+  // ---- split-K (dense products of the tensor-core backward): a unit is (K slice, chunk, query group)
+  int kslices;               // >= 1
+  int kb_per_slice;          // k-blocks per slice (== kblocks when kslices == 1)
+  long long emit_slice_stride;  // floats between the partial outputs of consecutive slices
+  // ---- MODE_EMIT_COEF: backward coefficients as the bf16 A operand of the gradient GEMMs
+  const float* coef_tab;     // orientation 0: T (rows, coef_ld), value = T[row][label of column]
+                             // orientation 1: T^t (classes, coef_ld), value = T^t[label of row][column]
+  long long coef_ld;
+  int coef_orient;
 };
 
 constexpr int MODE_CLASS_LSE = 0;       // online softmax + per-class sums (the NW head)
 constexpr int MODE_EMIT_SCORES = 1;     // dense per-pair output: the similarity scores
 constexpr int MODE_EMIT_INFLUENCE = 2;  // dense per-pair output: support influence
 constexpr int MODE_EMIT_BLOCKBEST = 3;  // best score of every block of 64 support rows (candidate search for top-k)
+constexpr int MODE_EMIT_COEF = 4;       // backward coefficients w(row, col), bf16, k-block-major over the columns
 // (the emit kind is a template parameter: one kernel with a runtime switch and logf inlined 64 times was > 64 KB
 //  of SASS and ran 4x slower on instruction fetch)
 
@@ -435,6 +445,67 @@ __device__ __forceinline__ void emit_chunk(float (&acc)[32], const float* __rest
   __syncwarp();
 }
 
+// MODE_EMIT_COEF — the recompute step of the tensor-core backward (closed form: SURVEY.md B.2).  With
+//   p(b, j) = exp(score(b, j) - lse_b)            the softmax weight of support j for query b
+//   T(b, c) = g(b, c) / (P(b, c) + 1e-12) - sum_c' g(b, c') P(b, c') / (P(b, c') + 1e-12)
+// the gradient of the loss with respect to score(b, j) is p(b, j) T(b, y_j), and
+//   EUCLID (score = -|q - s|):  w = p T / |q - s|   ->  grad_q = W S - rowsum(W) q,   grad_s = W^t Q - colsum(W) s
+//   LINEAR (score = scale q.s): w = p T scale       ->  grad_q = W S,                  grad_s = W^t Q
+// (a zero distance contributes nothing, as torch.cdist's backward).  One thread owns one row of the tile and 32
+// consecutive columns; w is rounded to bf16 and stored k-block-major over the COLUMNS,
+// out[col / 64][row][col % 64], which is exactly the A-operand layout of this kernel: the gradient GEMMs consume it
+// with K = the column axis.  Orientation 0: rows = queries, columns = supports (W, for grad_q).  Orientation 1:
+// rows = supports, columns = queries (W^t, for grad_s): the per-column log-sum-exp arrives through the label slots
+// of the tile metadata (float bits) and the table is indexed [label of the row][column].
+template <int EPI>
+__device__ __forceinline__ void coef_chunk(float (&acc)[32], const float* __restrict__ cadd,
+                                           const int* __restrict__ lab, float qn, float scale, float row_z,
+                                           int row_lab, const Params& p, int row, int col0, int n_valid) {
+  if (row < 0 || n_valid <= 0) return;
+  const bool by_col = p.coef_orient == 0;  // the table value changes with the column's label
+  const float* __restrict__ trow =
+      by_col ? p.coef_tab + (long long)row * p.coef_ld : p.coef_tab + (long long)row_lab * p.coef_ld + col0;
+  const bool uniform = by_col && n_valid >= 32 && lab[0] == lab[31];  // class-sorted bank: one class per chunk, mostly
+  const float t_u = uniform ? __ldg(trow + lab[0]) : 0.0f;
+  uint32_t packed[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float w[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = i + k;
+      const bool valid = c < n_valid;
+      float tb, z;
+      if (by_col) {
+        z = row_z;
+        tb = uniform ? t_u : ((valid && lab[c] >= 0) ? __ldg(trow + lab[c]) : 0.0f);
+      } else {
+        z = __int_as_float(lab[c]);
+        tb = valid ? __ldg(trow + c) : 0.0f;
+      }
+      float v;
+      if (EPI == NW_EPI_EUCLID) {
+        const float d2 = fmaf(-2.0f, acc[c], qn + cadd[c]);
+        const float dist = sqrt_approx(fmaxf(d2, 0.0f));
+        const float pr = ex2_approx((-dist - z) * kLog2e);
+        // a squared distance below the rounding noise of its own terms is a coincident pair: no gradient
+        v = d2 > 1e-6f * (qn + cadd[c]) ? __fdividef(pr * tb, dist) : 0.0f;
+      } else {
+        v = ex2_approx(fmaf(acc[c], scale, -z) * kLog2e) * tb * scale;
+      }
+      w[k] = valid ? v : 0.0f;
+    }
+    const __nv_bfloat162 h = __floats2bfloat162_rn(w[0], w[1]);
+    packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.emit_out) +
+                       ((long long)(col0 >> 6) * p.n_query + row) * 64 + (col0 & 63);
+  uint4* dst4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int v4 = 0; v4 < 4; ++v4)
+    dst4[v4] = make_uint4(packed[v4 * 4], packed[v4 * 4 + 1], packed[v4 * 4 + 2], packed[v4 * 4 + 3]);
+}
+
 // MODE_EMIT_BLOCKBEST: best score of this thread's query row over one 32-column chunk (padding columns excluded).
 template <int EPI>
 __device__ __forceinline__ float chunk_best(const float (&acc)[32], const float* __restrict__ cadd, float qn,
@@ -472,7 +543,8 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const bool leader = cta_rank == 0;
   const int worker = blockIdx.x / NCTA;
   const int n_workers = gridDim.x / NCTA;
-  const int n_units = p.chunks * p.q_groups;
+  const int units_per_slice = p.chunks * p.q_groups;
+  const int n_units = units_per_slice * p.kslices;  // kslices == 1 except for the split-K dense products
   // epilogue sets: they share every tile by columns (a compile-time constant where the epilogue is the bottleneck)
   const int n_sets = QUAD ? QUAD_SETS : (MODE == MODE_CLASS_LSE ? p.sets : 2);
 
@@ -534,8 +606,12 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
       }
       for (int u = worker; u < n_units; u += n_workers) {
-        const int g = u / p.q_groups;
-        const int qg = u - g * p.q_groups;
+        const int ks = u / units_per_slice;
+        const int ur = u - ks * units_per_slice;
+        const int g = ur / p.q_groups;
+        const int qg = ur - g * p.q_groups;
+        const int kb0 = ks * p.kb_per_slice;
+        const int kb1 = min(kb0 + p.kb_per_slice, p.kblocks);
         const int t0 = g * p.tiles_per_chunk;
         const int t1 = min(t0 + p.tiles_per_chunk, p.s_tiles);
         const int q_row0 = (qg * NCTA + int(cta_rank)) * BM;
@@ -550,7 +626,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             bulk_load_1d(smem_u32(tail->mslot[ms].lab), p.labels + t * BN, META_LAB_BYTES, bar);
             ++mc;
           }
-          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const uint32_t s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
@@ -578,7 +654,10 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       constexpr uint32_t idesc = umma_idesc_bf16(BM * NCTA, BN);
       uint32_t it = 0, tc = 0;
       for (int u = worker; u < n_units; u += n_workers) {
-        const int g = u / p.q_groups;
+        const int ks = u / units_per_slice;
+        const int g = (u - ks * units_per_slice) / p.q_groups;
+        const int kb0 = ks * p.kb_per_slice;
+        const int kb1 = min(kb0 + p.kb_per_slice, p.kblocks);
         const int t0 = g * p.tiles_per_chunk;
         const int t1 = min(t0 + p.tiles_per_chunk, p.s_tiles);
         for (int t = t0; t < t1; ++t, ++tc) {
@@ -587,7 +666,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           mbar_wait(smem_u32(&tail->tempty[as]), aph ^ 1u);  // epilogues have drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * BN;
-          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const uint32_t s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(smem_u32(&tail->full[s]), ph);  // TMA bytes (of both CTAs) have landed
@@ -598,8 +677,9 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               // advance 32 B (= 16 bf16) inside the 128-B swizzled row: +2 in the 16-B address field
-              if (NCTA == 2) umma_bf16_ss_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              const uint32_t accumulate = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (NCTA == 2) umma_bf16_ss_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accumulate);
+              else umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accumulate);
             }
             // frees the smem stage (in both CTAs) once these MMAs retire
             if (NCTA == 2) umma_commit_pair(smem_u32(&tail->empty[s]), 3);
@@ -633,8 +713,11 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       probe_t0 = globaltimer_ns();
     }
     for (int u = worker; u < n_units; u += n_workers, ++uc) {
-      const int g = u / p.q_groups;
-      const int qg = u - g * p.q_groups;
+      const int ks = u / units_per_slice;
+      const int ur = u - ks * units_per_slice;
+      const int g = ur / p.q_groups;
+      const int qg = ur - g * p.q_groups;
+      float* const emit_out = p.emit_out + (long long)ks * p.emit_slice_stride;  // this K slice's partial output
       const int t0 = g * p.tiles_per_chunk;
       const int t1 = min(t0 + p.tiles_per_chunk, p.s_tiles);
       const int n0 = t0 * BN;
@@ -667,6 +750,10 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         e_z = __ldg(p.row_lse + row);
         e_p = __ldg(p.p_query + row);
         e_qy = __ldg(p.qlabel + row);
+      }
+      if (MODE == MODE_EMIT_COEF && row_valid) {
+        if (p.coef_orient == 0) e_z = __ldg(p.row_lse + row);
+        else e_qy = __ldg(p.qlabel + row);
       }
 
       // column metadata of a tile: additive term (|s|^2, or 0; +inf / -inf on padding columns) and labels
@@ -742,7 +829,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 tmem_ld_32x32(t_addr + cc * 32, acc);
                 tmem_ld_wait();
                 emit_chunk<EPI, INFL>(acc, meta.cadd + cc * 32, meta.lab + cc * 32, qn, p.scale_log2 * kLn2, e_z, e_p, e_qy,
-                                      stg, lane, p.emit_out, p.emit_ld, row0, p.n_query, j0 + cc * 32, n1 - (j0 + cc * 32),
+                                      stg, lane, emit_out, p.emit_ld, row0, p.n_query, j0 + cc * 32, n1 - (j0 + cc * 32),
                                       p.emit_vec != 0);
               }
               continue;
@@ -751,21 +838,29 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             tmem_ld_32x32(t_addr + c * 32, acc0);
             tmem_ld_32x32(t_addr + (c + 1) * 32, acc1);
             tmem_ld_wait();
+            if (MODE == MODE_EMIT_COEF) {
+              const int rr = row_valid ? row : -1;
+              coef_chunk<EPI>(acc0, meta.cadd + c * 32, meta.lab + c * 32, qn, p.scale_log2 * kLn2, e_z, e_qy, p, rr,
+                              j0 + c * 32, n1 - (j0 + c * 32));
+              coef_chunk<EPI>(acc1, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, qn, p.scale_log2 * kLn2, e_z, e_qy,
+                              p, rr, j0 + (c + 1) * 32, n1 - (j0 + (c + 1) * 32));
+              continue;
+            }
             if (MODE == MODE_EMIT_BLOCKBEST) {
               const float b0 = chunk_best<EPI>(acc0, meta.cadd + c * 32, qn, p.scale_log2 * kLn2, n1 - (j0 + c * 32));
               const float b1 = chunk_best<EPI>(acc1, meta.cadd + (c + 1) * 32, qn, p.scale_log2 * kLn2,
                                                n1 - (j0 + (c + 1) * 32));
               // out[block][query]: 32 consecutive query rows per warp -> one coalesced 128-byte store
-              if (row_valid) p.emit_out[(long long)(t * (BN / 64) + (c >> 1)) * p.emit_ld + row] = fmaxf(b0, b1);
+              if (row_valid) emit_out[(long long)(t * (BN / 64) + (c >> 1)) * p.emit_ld + row] = fmaxf(b0, b1);
               continue;
             }
             const int row0 = (qg * NCTA + int(cta_rank)) * BM + ew * 32;
             float(*stg)[33] = tail->stage[warp - EPI_WARP0];
             emit_chunk<EPI, INFL>(acc0, meta.cadd + c * 32, meta.lab + c * 32, qn, p.scale_log2 * kLn2, e_z, e_p, e_qy,
-                                  stg, lane, p.emit_out, p.emit_ld, row0, p.n_query, j0 + c * 32, n1 - (j0 + c * 32),
+                                  stg, lane, emit_out, p.emit_ld, row0, p.n_query, j0 + c * 32, n1 - (j0 + c * 32),
                                   p.emit_vec != 0);
             emit_chunk<EPI, INFL>(acc1, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, qn, p.scale_log2 * kLn2, e_z,
-                                  e_p, e_qy, stg, lane, p.emit_out, p.emit_ld, row0, p.n_query, j0 + (c + 1) * 32,
+                                  e_p, e_qy, stg, lane, emit_out, p.emit_ld, row0, p.n_query, j0 + (c + 1) * 32,
                                   n1 - (j0 + (c + 1) * 32), p.emit_vec != 0);
             continue;
           }
@@ -1306,6 +1401,12 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.emit_ld = 0;
   p.emit_kind = 0;
   p.emit_vec = 0;
+  p.kslices = 1;
+  p.kb_per_slice = p.kblocks;
+  p.emit_slice_stride = 0;
+  p.coef_tab = nullptr;
+  p.coef_ld = 0;
+  p.coef_orient = 0;
   p.clock_probe = (g_clock_probe && plan.grid <= g_clock_probe_ctas) ? g_clock_probe : nullptr;
   {
     static const int skip = [] {
@@ -1383,14 +1484,25 @@ extern "C" int nw_forward_class_lse_peers(int epilogue, float scale, const void*
                       static_cast<cudaStream_t>(stream_));
 }
 
-extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
-                               const void* bank_bf16, const float* s_sqnorm, const int32_t* labels,
-                               int64_t n_support, int row_elems, int emit_kind, const float* row_lse,
-                               const float* p_query, const int32_t* qlabel, float* out, int64_t ld_out,
-                               void* stream_) {
+// Internal emit kinds beyond include/nw_sm100.h's NW_EMIT_*: the backward coefficients (nw_backward_coefficients).
+constexpr int EMIT_COEF_INTERNAL = 100;
+
+struct EmitExtra {
+  int kslices = 1;                  // split-K (NW_EMIT_SCORES only): partial products, one output per slice
+  long long slice_stride = 0;       // floats between the slices' outputs
+  const float* coef_tab = nullptr;  // EMIT_COEF_INTERNAL
+  long long coef_ld = 0;
+  int coef_orient = 0;
+};
+
+static int emit_impl(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
+                     const void* bank_bf16, const float* s_sqnorm, const int32_t* labels, int64_t n_support,
+                     int row_elems, int emit_kind, const float* row_lse, const float* p_query, const int32_t* qlabel,
+                     float* out, int64_t ld_out, const EmitExtra& ex, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NW_REQUIRE(epilogue == NW_EPI_EUCLID || epilogue == NW_EPI_LINEAR, NW_ERR_INVALID, "unknown epilogue %d", epilogue);
-  NW_REQUIRE(emit_kind == NW_EMIT_SCORES || emit_kind == NW_EMIT_INFLUENCE || emit_kind == NW_EMIT_BLOCK_BEST,
+  NW_REQUIRE(emit_kind == NW_EMIT_SCORES || emit_kind == NW_EMIT_INFLUENCE || emit_kind == NW_EMIT_BLOCK_BEST ||
+                 emit_kind == EMIT_COEF_INTERNAL,
              NW_ERR_INVALID, "unknown emit kind %d", emit_kind);
   NW_REQUIRE(q_bf16 && bank_bf16 && out, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(epilogue != NW_EPI_EUCLID || (q_sqnorm && s_sqnorm), NW_ERR_INVALID,
@@ -1398,8 +1510,10 @@ extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, co
   NW_REQUIRE(emit_kind != NW_EMIT_INFLUENCE || (labels && row_lse && p_query && qlabel), NW_ERR_INVALID,
              "influence needs labels, row_lse, p_query and qlabel");
   NW_REQUIRE(row_elems > 0 && row_elems % k1::BK == 0, NW_ERR_INVALID, "row_elems must be a positive multiple of 64");
-  NW_REQUIRE(emit_kind == NW_EMIT_BLOCK_BEST ? ld_out >= n_query : ld_out >= n_support, NW_ERR_INVALID,
-             "ld_out must be >= n_support (>= n_query for NW_EMIT_BLOCK_BEST)");
+  NW_REQUIRE(emit_kind == EMIT_COEF_INTERNAL || (emit_kind == NW_EMIT_BLOCK_BEST ? ld_out >= n_query : ld_out >= n_support),
+             NW_ERR_INVALID, "ld_out must be >= n_support (>= n_query for NW_EMIT_BLOCK_BEST)");
+  NW_REQUIRE(ex.kslices >= 1 && (ex.kslices == 1 || emit_kind == NW_EMIT_SCORES), NW_ERR_INVALID,
+             "split-K is available for dense products only");
   NW_REQUIRE((reinterpret_cast<uintptr_t>(q_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(bank_bf16) & 15) == 0,
              NW_ERR_INVALID, "bf16 operands must be 16-byte aligned");
   int rc = nw_device_check();
@@ -1438,12 +1552,25 @@ extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, co
   p.row_lse = row_lse;
   p.p_query = p_query;
   p.qlabel = qlabel;
+  // split-K: no slice may be empty (its accumulator would be read without a single MMA)
+  p.kb_per_slice = ceil_div(p.kblocks, ex.kslices);
+  p.kslices = ceil_div(p.kblocks, p.kb_per_slice);
+  p.emit_slice_stride = ex.slice_stride;
+  p.coef_tab = ex.coef_tab;
+  p.coef_ld = ex.coef_ld;
+  p.coef_orient = ex.coef_orient;
+  int grid = plan.grid;
+  if (p.kslices > 1) {  // more units than the plan knew of: size the persistent grid for all of them
+    const long long units = (long long)plan.chunks * plan.q_tiles * p.kslices;
+    const int workers = sm_count() / ncta;
+    grid = int(units < workers ? units : workers) * ncta;
+  }
   const bool euc = epilogue == NW_EPI_EUCLID;
 #define NW_LAUNCH_EMIT(MODE_)                                                                                    \
-  rc = euc ? (ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2, MODE_>(map_q, map_s, p, plan.grid, stream)           \
-                        : k1::launch_forward<NW_EPI_EUCLID, 1, MODE_>(map_q, map_s, p, plan.grid, stream))          \
-           : (ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2, MODE_>(map_q, map_s, p, plan.grid, stream)           \
-                        : k1::launch_forward<NW_EPI_LINEAR, 1, MODE_>(map_q, map_s, p, plan.grid, stream))
+  rc = euc ? (ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2, MODE_>(map_q, map_s, p, grid, stream)           \
+                        : k1::launch_forward<NW_EPI_EUCLID, 1, MODE_>(map_q, map_s, p, grid, stream))          \
+           : (ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2, MODE_>(map_q, map_s, p, grid, stream)           \
+                        : k1::launch_forward<NW_EPI_LINEAR, 1, MODE_>(map_q, map_s, p, grid, stream))
   static const int emit_sets = [] {  // developer knob: 2 = the influence emit runs the 8-warp epilogue as well
     const char* e = getenv("NW_B200_EMIT_SETS");
     return e && *e ? atoi(e) : 4;
@@ -1452,11 +1579,12 @@ extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, co
   // four epilogue sets, at the price of two ring stages (config 5 from features, bf16: 2.29 -> 1.70 ms).  Dense
   // scores keep two sets: four gave +4.5 % with one bf16 pass and -7 % with the three passes of bf16x3.
 #define NW_LAUNCH_EMIT4(MODE_)                                                                                         \
-  rc = euc ? (ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2, MODE_, true>(map_q, map_s, p, plan.grid, stream)           \
-                        : k1::launch_forward<NW_EPI_EUCLID, 1, MODE_, true>(map_q, map_s, p, plan.grid, stream))          \
-           : (ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2, MODE_, true>(map_q, map_s, p, plan.grid, stream)           \
-                        : k1::launch_forward<NW_EPI_LINEAR, 1, MODE_, true>(map_q, map_s, p, plan.grid, stream))
+  rc = euc ? (ncta == 2 ? k1::launch_forward<NW_EPI_EUCLID, 2, MODE_, true>(map_q, map_s, p, grid, stream)           \
+                        : k1::launch_forward<NW_EPI_EUCLID, 1, MODE_, true>(map_q, map_s, p, grid, stream))          \
+           : (ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2, MODE_, true>(map_q, map_s, p, grid, stream)           \
+                        : k1::launch_forward<NW_EPI_LINEAR, 1, MODE_, true>(map_q, map_s, p, grid, stream))
   if (emit_kind == NW_EMIT_SCORES) NW_LAUNCH_EMIT(k1::MODE_EMIT_SCORES);
+  else if (emit_kind == EMIT_COEF_INTERNAL) NW_LAUNCH_EMIT(k1::MODE_EMIT_COEF);
   else if (emit_kind == NW_EMIT_INFLUENCE && emit_sets == 4) {
     p.sets = k1::QUAD_SETS;
     NW_LAUNCH_EMIT4(k1::MODE_EMIT_INFLUENCE);
@@ -1465,6 +1593,60 @@ extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, co
 #undef NW_LAUNCH_EMIT4
 #undef NW_LAUNCH_EMIT
   return rc;
+}
+
+extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
+                               const void* bank_bf16, const float* s_sqnorm, const int32_t* labels,
+                               int64_t n_support, int row_elems, int emit_kind, const float* row_lse,
+                               const float* p_query, const int32_t* qlabel, float* out, int64_t ld_out,
+                               void* stream_) {
+  NW_REQUIRE(emit_kind == NW_EMIT_SCORES || emit_kind == NW_EMIT_INFLUENCE || emit_kind == NW_EMIT_BLOCK_BEST,
+             NW_ERR_INVALID, "unknown emit kind %d", emit_kind);
+  return emit_impl(epilogue, scale, q_bf16, q_sqnorm, n_query, bank_bf16, s_sqnorm, labels, n_support, row_elems,
+                   emit_kind, row_lse, p_query, qlabel, out, ld_out, EmitExtra(), stream_);
+}
+
+// Tensor-core backward, step 1 (recompute): see coef_chunk.  `rows` / `cols` are the two operands of the score
+// GEMM in this kernel's k-block-major bf16 layout; orientation 0: rows = queries, cols = the class-sorted bank;
+// orientation 1: rows = the bank, cols = queries.
+extern "C" int nw_backward_coefficients(int epilogue, float scale, int orientation, const void* rows_bf16,
+                                        const float* rows_sqnorm, int64_t n_rows, const void* cols_bf16,
+                                        const float* cols_sqnorm, int64_t n_cols, int row_elems,
+                                        const float* row_lse, const int32_t* row_labels, const float* col_lse,
+                                        const int32_t* col_labels, const float* table, int64_t table_ld,
+                                        void* out_bf16, void* stream_) {
+  NW_REQUIRE(orientation == 0 || orientation == 1, NW_ERR_INVALID, "orientation must be 0 or 1");
+  NW_REQUIRE(table != nullptr && out_bf16 != nullptr, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n_rows > 0 && n_rows < (int64_t(1) << 31) - 512, NW_ERR_UNSUPPORTED, "n_rows must be in (0, 2^31 - 512)");
+  NW_REQUIRE((reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0, NW_ERR_INVALID, "out_bf16 must be 16-byte aligned");
+  if (orientation == 0)
+    NW_REQUIRE(row_lse && col_labels, NW_ERR_INVALID, "orientation 0 needs row_lse and col_labels");
+  else
+    NW_REQUIRE(col_lse && row_labels, NW_ERR_INVALID, "orientation 1 needs col_lse and row_labels");
+  EmitExtra ex;
+  ex.coef_tab = table;
+  ex.coef_ld = table_ld;
+  ex.coef_orient = orientation;
+  // orientation 1: the per-column log-sum-exp travels through the label slots of the tile metadata (float bits)
+  const int32_t* col_meta = orientation == 0 ? col_labels : reinterpret_cast<const int32_t*>(col_lse);
+  return emit_impl(epilogue, scale, rows_bf16, rows_sqnorm, int(n_rows), cols_bf16, cols_sqnorm, col_meta, n_cols,
+                   row_elems, EMIT_COEF_INTERNAL, row_lse, nullptr, row_labels, reinterpret_cast<float*>(out_bf16),
+                   /*ld_out=*/0, ex, stream_);
+}
+
+// Tensor-core backward, step 2: out[ks][r][c] = sum over K slice ks of a[r][k] * b[c][k]  (both operands bf16,
+// k-block-major), fp32, row-major with leading dimension ld_out.  The slices' partial products are summed by the
+// caller (split-K keeps all SMs busy when (n_a / 256) * (n_b / 256) is smaller than the GPU).
+extern "C" int nw_dense_products(const void* a_bf16, int64_t n_a, const void* b_bf16, int64_t n_b, int k_elems,
+                                 int kslices, float* out, int64_t ld_out, int64_t slice_stride, void* stream_) {
+  NW_REQUIRE(n_a > 0 && n_a < (int64_t(1) << 31) - 512, NW_ERR_UNSUPPORTED, "n_a must be in (0, 2^31 - 512)");
+  NW_REQUIRE(kslices >= 1 && kslices <= 1024, NW_ERR_INVALID, "kslices must be in [1, 1024]");
+  NW_REQUIRE(kslices == 1 || slice_stride >= n_a * ld_out, NW_ERR_INVALID, "slice_stride must cover one output");
+  EmitExtra ex;
+  ex.kslices = kslices;
+  ex.slice_stride = slice_stride;
+  return emit_impl(NW_EPI_LINEAR, 1.0f, a_bf16, nullptr, int(n_a), b_bf16, nullptr, nullptr, n_b, k_elems,
+                   NW_EMIT_SCORES, nullptr, nullptr, nullptr, out, ld_out, ex, stream_);
 }
 
 extern "C" int nw_logp_from_class_lse(const float* class_lse, int n_query, int n_classes, float* logp,

@@ -6,6 +6,8 @@ Two execution paths, both through libnw_sm100 (no PyTorch or CPU fallback):
     switches to the expanded |q|^2+|s|^2-2q.s form above 25 rows.
   * direct fp32 path  (nw_direct_*): exact differences, differentiable, per-query 3-D supports —
     episodic training (`forward`) and tiny supports.
+A differentiable call with a big batch against a big shared support runs forward AND backward on the tensor
+cores (nwhead_b200/backward.py).
 """
 import weakref
 
@@ -14,6 +16,7 @@ import torch.nn as nn
 
 from . import _abi
 from ._abi import KIND, check, load, ptr, stream_of
+from .backward import NWTensorFunction, wants_tensor_path
 from .bank import SupportBank
 from .kernel import get_kernel
 from .support import SupportSetEval, SupportSetTrain
@@ -128,11 +131,16 @@ class _NWDirectFunction(torch.autograd.Function):
 class NWHead(nn.Module):
     BANK_CACHE_SIZE = 2  # banks built from raw (sx, sy) tensors are kept while the tensors stay unmodified
 
-    def __init__(self, kernel, n_classes, precision="auto"):
+    def __init__(self, kernel, n_classes, precision="auto", backward_path="auto"):
         super().__init__()
         self.kernel = kernel
         self.n_classes = n_classes
         self.precision = precision
+        # differentiable calls: 'direct' = exact-difference fp32 kernels, 'tensor' = tcgen05 forward + backward
+        # (bf16 operands, nwhead_b200/backward.py), 'auto' = tensor for big batches against big shared supports
+        if backward_path not in ("auto", "direct", "tensor"):
+            raise ValueError(f"unknown backward_path {backward_path!r}")
+        self.backward_path = backward_path
         self._bank_cache = []
 
     def _bank_for(self, sx, sy, kind):
@@ -203,6 +211,8 @@ class NWHead(nn.Module):
             return x.new_empty((0, self.n_classes))
         if n == 0:
             raise ValueError("NWHead needs at least one support row")
+        if needs_grad and wants_tensor_path(x.shape[0], n, sx.dim(), self.backward_path):
+            return NWTensorFunction.apply(x, sx, sy, logit_scale, kind, self.n_classes)
         if needs_grad or sx.dim() == 3 or n < MM_PATH_MIN_ROWS:
             if needs_grad and x.shape[-1] + self.n_classes > _abi.DIRECT_BACKWARD_MAX_D_PLUS_C:
                 # fail before the forward, not at .backward()

@@ -42,7 +42,7 @@ def test_ctypes_table_matches_header():
 
 def test_pure_host_entry_points(lib):
     lib.nw_row_elems.restype = ctypes.c_int
-    assert lib.nw_abi_version() == 2
+    assert lib.nw_abi_version() == 3
     assert lib.nw_row_elems(2048, 1) == 2048
     assert lib.nw_row_elems(512, 3) == 1536
     assert lib.nw_row_elems(16, 1) == 64

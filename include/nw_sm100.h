@@ -217,13 +217,29 @@ NW_API int nw_forward_emit(int epilogue, float scale, const void* q_bf16, const 
  * rows / cols: the two operands in the fused forward's k-block-major bf16 layout with their squared norms
  * (euclidean).  Orientation 0: rows = queries (row_lse (B) required), cols = class-sorted bank (col_labels int32
  * required).  Orientation 1: rows = bank (row_labels required), cols = queries (col_lse required).
- * out_bf16: (ceil(n_cols / 64), n_rows, 64) bf16, ZEROED by the caller (padding columns are not written):
- * out[j / 64][r][j % 64] = w(r, j). */
+ * out_bf16: (ceil(n_cols / 64), n_rows, 64) bf16, every element written (padding columns as zeros):
+ * out[j / 64][r][j % 64] = w(r, j).
+ * row_sums (n_rows): sum_j of the ROUNDED w(r, j) — rowsum(W) / colsum(W) of the formulas above, summed in a
+ * fixed order (bitwise reproducible).  workspace: nw_backward_coefficients_workspace_elems(n_rows, n_cols) floats. */
+NW_API int64_t nw_backward_coefficients_workspace_elems(int64_t n_rows, int64_t n_cols);
 NW_API int nw_backward_coefficients(int epilogue, float scale, int orientation, const void* rows_bf16,
                              const float* rows_sqnorm, int64_t n_rows, const void* cols_bf16,
                              const float* cols_sqnorm, int64_t n_cols, int row_elems, const float* row_lse,
                              const int32_t* row_labels, const float* col_lse, const int32_t* col_labels,
-                             const float* table, int64_t table_ld, void* out_bf16, void* stream);
+                             const float* table, int64_t table_ld, void* out_bf16, float* row_sums,
+                             float* workspace, int64_t workspace_elems, void* stream);
+
+/* Transposed operand: in (kblocks, n_rows, 64) bf16 k-block-major -> out (ceil(n_rows / 64), kblocks * 64, 64),
+ * out[r / 64][f][r % 64] = in[f / 64][r][f % 64], zero rows appended up to a multiple of 64 (the B operand of
+ * nw_dense_products when the contraction runs over the ROWS: S^t for grad_q, Q^t for grad_s). */
+NW_API int nw_transpose_kblocks(const void* in_bf16, int64_t n_rows, int kblocks, void* out_bf16, void* stream);
+
+/* Last step of a gradient: out[dst(r)][c] = raw[r][c] - row_sums[r] * rows_bf16[c / 64][r][c % 64], c < d, with
+ * dst(r) = perm ? perm[r] : r (bank row -> row of the caller's support tensor).  row_sums == NULL: copy / permute
+ * only (linear scores).  The subtracted rows are the STORED (centred, rounded) operand rows, so the two terms of a
+ * close (query, support) pair cancel. */
+NW_API int nw_backward_finish(const float* raw, int64_t ld_raw, const void* rows_bf16, const float* row_sums,
+                       const int64_t* perm, int64_t n_rows, int d, float* out, int64_t ld_out, void* stream);
 
 /* out[ks][r][c] = sum over the k-blocks of K slice ks of a[r][k] * b[c][k]; a (k_elems/64, n_a, 64) and
  * b (k_elems/64, n_b, 64) bf16 k-block-major, out fp32 row-major (n_a, ld_out >= n_b) per slice, slices

@@ -65,9 +65,13 @@ SIGNATURES = {
                                            c_int64, c_void_p]),
     "nw_forward_emit": (c_int, [c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "nw_backward_coefficients_workspace_elems": (c_int64, [c_int64, c_int64]),
     "nw_backward_coefficients": (c_int, [c_int, c_float, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                          c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                         c_void_p, c_void_p]),
+                                         c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "nw_transpose_kblocks": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "nw_backward_finish": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
+                                   c_int64, c_void_p]),
     "nw_dense_products": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int64,
                                   c_void_p]),
     "nw_logp_from_class_lse": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

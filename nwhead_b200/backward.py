@@ -31,13 +31,20 @@ MIN_PAIRS = 1 << 24
 
 def transpose_operand(x: torch.Tensor) -> torch.Tensor:
     """k-block-major bf16 rows (kb, R, 64) -> the same matrix TRANSPOSED, k-block-major over the rows:
-    (ceil(R / 64), kb * 64, 64), out[r / 64][f][r % 64] = x[f / 64][r][f % 64] (zero rows appended).  A pure
-    permutation of bf16 elements (device-memory plumbing, once per operand)."""
+    (ceil(R / 64), kb * 64, 64), out[r / 64][f][r % 64] = x[f / 64][r][f % 64] (zero rows appended):
+    nw_transpose_kblocks, one pass over the operand at HBM speed."""
     kb, r, _ = x.shape
-    rp = (r + 63) // 64 * 64
-    if rp != r:
-        x = torch.nn.functional.pad(x, (0, 0, 0, rp - r))
-    return x.view(kb, rp // 64, 64, 64).permute(1, 0, 3, 2).reshape(rp // 64, kb * 64, 64).contiguous()
+    out = torch.empty(((r + 63) // 64, kb * 64, 64), dtype=torch.bfloat16, device=x.device)
+    check(load().nw_transpose_kblocks(ptr(x), r, kb, ptr(out), stream_of(x.device)), "nw_transpose_kblocks")
+    return out
+
+
+def bank_transposed(bank: SupportBank) -> torch.Tensor:
+    """S^t of a bank, kept with the bank (a fixed support is transposed once, not once per training step)."""
+    t = getattr(bank, "_transposed", None)
+    if t is None:
+        t = bank._transposed = transpose_operand(bank.feats_bf16)
+    return t
 
 
 def backward_table(class_lse: torch.Tensor, grad_logp: torch.Tensor):
@@ -49,24 +56,34 @@ def backward_table(class_lse: torch.Tensor, grad_logp: torch.Tensor):
 
 
 def coefficients(bank: SupportBank, q_bf16, q_sq, row_lse, table, scale: float, orientation: int):
-    """orientation 0: W (ceil(N/64), B, 64); orientation 1: W^t (ceil(B/64), N, 64) — bf16, zero padded."""
+    """orientation 0: W (ceil(N/64), B, 64) and rowsum(W) (B,); orientation 1: W^t (ceil(B/64), N, 64) and
+    colsum(W) (N,).  bf16, zero padded; the sums are of the rounded values, in a fixed order."""
     lib = load()
     dev = bank.device
     b, n = q_bf16.shape[1], len(bank)
     epi = _abi.EPI_EUCLID if bank.kind in EUCLID_KINDS else _abi.EPI_LINEAR
+    n_rows, n_cols = (b, n) if orientation == 0 else (n, b)
+    out = torch.empty(((n_cols + 63) // 64, n_rows, 64), dtype=torch.bfloat16, device=dev)
+    sums = torch.empty((n_rows,), dtype=torch.float32, device=dev)
+    ws = torch.empty((lib.nw_backward_coefficients_workspace_elems(n_rows, n_cols),), dtype=torch.float32, device=dev)
     if orientation == 0:
-        out = torch.zeros(((n + 63) // 64, b, 64), dtype=torch.bfloat16, device=dev)
-        check(lib.nw_backward_coefficients(epi, float(scale), 0, ptr(q_bf16), ptr(q_sq), b, ptr(bank.feats_bf16),
-                                           ptr(bank.sqnorm), n, bank.row_elems, ptr(row_lse), None, None,
-                                           ptr(bank.labels), ptr(table), table.stride(0), ptr(out), stream_of(dev)),
-              "nw_backward_coefficients")
+        args = (ptr(q_bf16), ptr(q_sq), b, ptr(bank.feats_bf16), ptr(bank.sqnorm), n, bank.row_elems, ptr(row_lse),
+                None, None, ptr(bank.labels))
     else:
-        out = torch.zeros(((b + 63) // 64, n, 64), dtype=torch.bfloat16, device=dev)
         table = table.t().contiguous()  # (C, B): the row's class selects a contiguous run over the queries
-        check(lib.nw_backward_coefficients(epi, float(scale), 1, ptr(bank.feats_bf16), ptr(bank.sqnorm), n,
-                                           ptr(q_bf16), ptr(q_sq), b, bank.row_elems, None, ptr(bank.labels),
-                                           ptr(row_lse), None, ptr(table), table.stride(0), ptr(out), stream_of(dev)),
-              "nw_backward_coefficients")
+        args = (ptr(bank.feats_bf16), ptr(bank.sqnorm), n, ptr(q_bf16), ptr(q_sq), b, bank.row_elems, None,
+                ptr(bank.labels), ptr(row_lse), None)
+    check(lib.nw_backward_coefficients(epi, float(scale), orientation, *args, ptr(table), table.stride(0), ptr(out),
+                                       ptr(sums), ptr(ws), ws.numel(), stream_of(dev)), "nw_backward_coefficients")
+    return out, sums
+
+
+def finish(raw: torch.Tensor, rows_bf16, sums, perm, d: int) -> torch.Tensor:
+    """grad[dst(r)] = raw[r, :d] - sums[r] * stored_row(r)  (nw_backward_finish; sums None: copy / permute)."""
+    n_rows = raw.shape[0]
+    out = torch.empty((n_rows, d), dtype=torch.float32, device=raw.device)
+    check(load().nw_backward_finish(ptr(raw), raw.stride(0), ptr(rows_bf16), ptr(sums), ptr(perm), n_rows, d, ptr(out),
+                                    d, stream_of(raw.device)), "nw_backward_finish")
     return out
 
 
@@ -81,7 +98,11 @@ def dense_products(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     plan = _abi.forward_plan(n_a, n_b)
     units = plan.chunks * plan.q_tiles
     workers = torch.cuda.get_device_properties(dev).multi_processor_count // (2 if plan.cta_pair else 1)
-    kslices = max(1, min(workers // max(units, 1), kb // 8))
+    # split K so that the units fill whole waves of persistent workers: cost = waves x (k-blocks per unit + the
+    # per-unit pipeline fill and epilogue, ~16 k-blocks' worth); B=4096 against config 3 is 128 units on 74 CTA
+    # pairs (two waves, the second 73 % full) unsplit
+    kslices = min(range(1, max(1, min(64, kb // 8)) + 1),
+                  key=lambda ks: -(-units * ks // workers) * (-(-kb // ks) + 16))
     per = -(-kb // kslices)
     kslices = -(-kb // per)  # the library's own rounding: no empty slice
     ld = (n_b + 3) // 4 * 4
@@ -96,9 +117,10 @@ class NWTensorFunction(torch.autograd.Function):
     """NWHead.forward(x, sx, sy) for a 2-D support on the tensor cores, forward and backward."""
 
     @staticmethod
-    def forward(ctx, x, sx, sy, logit_scale, kind, n_classes):
+    def forward(ctx, x, sx, sy, logit_scale, kind, n_classes, bank=None):
         scale = float(logit_scale.detach().exp()) if logit_scale is not None else 1.0
-        bank = SupportBank.build(sx, sy, n_classes, kind, "bf16")  # raises like F.one_hot on a bad label
+        if bank is None:  # (a fixed support arrives with its cached bank)
+            bank = SupportBank.build(sx, sy, n_classes, kind, "bf16")  # raises like F.one_hot on a bad label
         q_bf16, q_sq = bank.prepare_queries(x)
         class_lse = bank.class_lse_prepared(q_bf16, q_sq, scale)
         ctx.bank, ctx.scale, ctx.kind = bank, scale, kind
@@ -117,12 +139,6 @@ class NWTensorFunction(torch.autograd.Function):
         normalised = kind in NORMALISED_KINDS
         row_lse, table = backward_table(class_lse, grad_out.float())
 
-        def stored_rows(t_bf16):
-            """the rows the scores were computed from — centred / normalised AND rounded to bf16 — as fp32 (R, d):
-            grad = W S - rowsum(W) q must take q from the same rounded operands as S, or the two terms of a close
-            (query, support) pair do not cancel"""
-            return t_bf16.permute(1, 0, 2).reshape(t_bf16.shape[1], -1)[:, :d].float()
-
         def through_normalisation(g_hat, raw):
             """gradient with respect to the normalised row -> gradient with respect to the raw row"""
             if not normalised:
@@ -131,31 +147,30 @@ class NWTensorFunction(torch.autograd.Function):
             unit = raw / norm
             return (g_hat - (g_hat * unit).sum(1, keepdim=True) * unit) / norm
 
+        # grad = W S - rowsum(W) q takes q from the STORED operand rows (centred / normalised AND rounded to bf16,
+        # like S): otherwise the two terms of a close (query, support) pair do not cancel
         gq = gs = gscale = None
         if need_q or need_scale:
-            w = coefficients(bank, q_bf16, q_sq, row_lse, table, scale, 0)
-            g_hat = dense_products(w, transpose_operand(bank.feats_bf16))[:, :d]
-            xq = stored_rows(q_bf16)
-            if euclid:
-                g_hat = g_hat - w.sum(dim=(0, 2), dtype=torch.float32)[:, None] * xq
+            w, rowsum = coefficients(bank, q_bf16, q_sq, row_lse, table, scale, 0)
+            raw = dense_products(w, bank_transposed(bank))
             del w
+            g_hat = finish(raw, q_bf16, rowsum if euclid else None, None, d)
             if need_scale:  # d score / d logit_scale = score, and sum_j coef * score = q_hat . grad_q_hat
-                gscale = (g_hat * xq).sum()
+                gscale = (g_hat * q_bf16.permute(1, 0, 2).reshape(x.shape[0], -1)[:, :d].float()).sum()
             if need_q:
                 gq = through_normalisation(g_hat, x)
         if need_s:
-            wt = coefficients(bank, q_bf16, q_sq, row_lse, table, scale, 1)
-            g_hat = dense_products(wt, transpose_operand(q_bf16))[:, :d]
-            if euclid:
-                g_hat = g_hat - wt.sum(dim=(0, 2), dtype=torch.float32)[:, None] * stored_rows(bank.feats_bf16)
+            wt, colsum = coefficients(bank, q_bf16, q_sq, row_lse, table, scale, 1)
+            raw = dense_products(wt, transpose_operand(q_bf16))
             del wt
-            g_sorted = through_normalisation(g_hat, sx if bank.perm is None else sx[bank.perm])
-            if bank.perm is None:
-                gs = g_sorted
-            else:
+            if normalised and bank.perm is not None:
+                g_sorted = through_normalisation(finish(raw, bank.feats_bf16, colsum if euclid else None, None, d),
+                                                 sx[bank.perm])
                 gs = torch.empty_like(g_sorted)
                 gs[bank.perm] = g_sorted
-        return gq, gs, None, gscale, None, None
+            else:  # the support's own row order is restored by the finishing kernel
+                gs = through_normalisation(finish(raw, bank.feats_bf16, colsum if euclid else None, bank.perm, d), sx)
+        return gq, gs, None, gscale, None, None, None
 
 
 def wants_tensor_path(n_query: int, n_support: int, support_dims: int, mode: str) -> bool:

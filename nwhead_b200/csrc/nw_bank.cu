@@ -385,3 +385,105 @@ extern "C" int nw_rounding_residual(const float* rows, int64_t n, int d, int64_t
   NW_CUDA_OK(cudaGetLastError());
   return NW_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Operand plumbing of the tensor-core backward (nw_backward_coefficients / nw_dense_products): HBM-bound.
+// ---------------------------------------------------------------------------------------------
+namespace nw {
+namespace k0 {
+
+// in  (kblocks, n_rows, 64) bf16 k-block-major: element f of row r at in[f / 64][r][f % 64]
+// out (ceil(n_rows / 64), kblocks * 64, 64): the TRANSPOSED matrix in the same layout, out[r / 64][f][r % 64]
+// (rows beyond n_rows are written as zeros).  One block moves one 64 x 64 tile through shared memory: 128-byte
+// row segments on both sides.
+__global__ void transpose_kblocks_kernel(const __nv_bfloat16* __restrict__ in, long long n_rows, int kblocks,
+                                         __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const long long rb = blockIdx.x;  // row block
+  const int kb = blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads, 2 elements per thread and pass
+  for (int i = ty; i < 64; i += 8) {
+    const long long r = rb * 64 + i;
+    __nv_bfloat162 v = __floats2bfloat162_rn(0.0f, 0.0f);
+    if (r < n_rows) v = *reinterpret_cast<const __nv_bfloat162*>(in + ((long long)kb * n_rows + r) * 64 + 2 * tx);
+    tile[i][2 * tx] = v.x;
+    tile[i][2 * tx + 1] = v.y;
+  }
+  __syncthreads();
+  const long long f_rows = (long long)kblocks * 64;
+  for (int i = ty; i < 64; i += 8) {  // output row f = kb * 64 + i holds column i of the tile
+    __nv_bfloat162 v;
+    v.x = tile[2 * tx][i];
+    v.y = tile[2 * tx + 1][i];
+    *reinterpret_cast<__nv_bfloat162*>(out + (rb * f_rows + kb * 64 + i) * 64 + 2 * tx) = v;
+  }
+}
+
+// out[dst(r)][c] = raw[r][c] - sums[r] * rows[c / 64][r][c % 64]   (sums == NULL: a plain copy),
+// dst(r) = perm ? perm[r] : r.  One warp per row, four columns per lane and pass.
+__global__ void backward_finish_kernel(const float* __restrict__ raw, long long ld_raw,
+                                       const __nv_bfloat16* __restrict__ rows, const float* __restrict__ sums,
+                                       const int64_t* __restrict__ perm, long long n_rows, int d,
+                                       float* __restrict__ out, long long ld_out) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const float s = sums ? __ldg(sums + r) : 0.0f;
+  const long long dst = perm ? perm[r] : r;
+  const float* src = raw + r * ld_raw;
+  float* o = out + dst * ld_out;
+  const bool vec = ((ld_raw | ld_out) & 3) == 0 && (d & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (vec) {
+    for (int c = lane * 4; c < d; c += 128) {
+      float4 v = __ldcs(reinterpret_cast<const float4*>(src + c));
+      if (sums) {
+        const uint2 b = *reinterpret_cast<const uint2*>(rows + ((long long)(c >> 6) * n_rows + r) * 64 + (c & 63));
+        const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&b.x);
+        const __nv_bfloat162 b1 = *reinterpret_cast<const __nv_bfloat162*>(&b.y);
+        v.x = fmaf(-s, __low2float(b0), v.x);
+        v.y = fmaf(-s, __high2float(b0), v.y);
+        v.z = fmaf(-s, __low2float(b1), v.z);
+        v.w = fmaf(-s, __high2float(b1), v.w);
+      }
+      __stcs(reinterpret_cast<float4*>(o + c), v);
+    }
+  } else {
+    for (int c = lane; c < d; c += 32) {
+      float v = src[c];
+      if (sums) v = fmaf(-s, __bfloat162float(rows[((long long)(c >> 6) * n_rows + r) * 64 + (c & 63)]), v);
+      o[c] = v;
+    }
+  }
+}
+
+}  // namespace k0
+}  // namespace nw
+
+extern "C" int nw_transpose_kblocks(const void* in_bf16, int64_t n_rows, int kblocks, void* out_bf16, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(in_bf16 && out_bf16, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(n_rows > 0 && kblocks > 0 && kblocks <= 65535, NW_ERR_INVALID, "bad shape n_rows=%lld kblocks=%d",
+             (long long)n_rows, kblocks);
+  const long long row_blocks = ceil_div_ll(n_rows, 64);
+  NW_REQUIRE(row_blocks < (1ll << 31), NW_ERR_UNSUPPORTED, "too many rows");
+  k0::transpose_kblocks_kernel<<<dim3(unsigned(row_blocks), unsigned(kblocks)), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(in_bf16), n_rows, kblocks, static_cast<__nv_bfloat16*>(out_bf16));
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}
+
+extern "C" int nw_backward_finish(const float* raw, int64_t ld_raw, const void* rows_bf16, const float* row_sums,
+                                  const int64_t* perm, int64_t n_rows, int d, float* out, int64_t ld_out,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NW_REQUIRE(raw && out, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(row_sums == nullptr || rows_bf16 != nullptr, NW_ERR_INVALID, "row_sums needs rows_bf16");
+  NW_REQUIRE(n_rows > 0 && d > 0 && ld_raw >= d && ld_out >= d, NW_ERR_INVALID, "bad shape");
+  const long long blocks = ceil_div_ll(n_rows, 8);
+  NW_REQUIRE(blocks < (1ll << 31), NW_ERR_UNSUPPORTED, "too many rows");
+  k0::backward_finish_kernel<<<unsigned(blocks), 256, 0, stream>>>(
+      raw, ld_raw, static_cast<const __nv_bfloat16*>(rows_bf16), row_sums, perm, n_rows, d, out, ld_out);
+  NW_CUDA_OK(cudaGetLastError());
+  return NW_OK;
+}

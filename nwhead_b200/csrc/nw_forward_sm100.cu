@@ -55,6 +55,14 @@ constexpr int QUAD_THREADS = (EPI_WARP0 + 4 * QUAD_SETS) * 32;
 // in registers at a time so that 640 threads fit the register file).
 constexpr int NW_MAX_PEERS = 16;
 
+constexpr int MODE_CLASS_LSE = 0;       // online softmax + per-class sums (the NW head)
+constexpr int MODE_EMIT_SCORES = 1;     // dense per-pair output: the similarity scores
+constexpr int MODE_EMIT_INFLUENCE = 2;  // dense per-pair output: support influence
+constexpr int MODE_EMIT_BLOCKBEST = 3;  // best score of every block of 64 support rows (candidate search for top-k)
+constexpr int MODE_EMIT_COEF = 4;       // backward coefficients w(row, col), bf16, k-block-major over the columns
+// modes whose epilogue goes through the per-warp 32 x 32 transpose buffers (row-major fp32 output)
+constexpr bool mode_transposes(int mode) { return mode != MODE_CLASS_LSE && mode != MODE_EMIT_COEF; }
+
 // NCTA = 1: one CTA computes a 128 x 256 tile (UMMA M=128).
 // NCTA = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x 256 tile (UMMA M=256); each CTA stages
 //           its own 128 query rows and HALF of the support tile, so L2->SM traffic and shared-memory operand
@@ -63,7 +71,7 @@ template <int NCTA, int MODE = 0, bool QUAD = false>
 struct Cfg {
   // the emit modes give ring stages up for the per-warp transpose buffers of their epilogue (8 warps: one stage,
   // the 16 warps of the QUAD variant: two)
-  static constexpr int STAGES = (NCTA == 1 ? 4 : 6) - (MODE == 0 ? 0 : (QUAD ? 2 : 1));
+  static constexpr int STAGES = (NCTA == 1 ? 4 : 6) - (!mode_transposes(MODE) ? 0 : (QUAD ? 2 : 1));
   static constexpr int B_ROWS = BN / NCTA;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -100,7 +108,7 @@ struct SmemTail {
   TileMeta mslot[META_SLOTS];                       // class-LSE: tile metadata delivered by the producer (bulk copies)
   uint64_t mfull[META_SLOTS];
   uint64_t mempty[META_SLOTS];
-  float stage[MODE == 0 ? 1 : (QUAD ? 4 * QUAD_SETS : MAX_EPI_WARPS)][32][33];  // emit modes: per-warp 32x32 transpose buffers
+  float stage[!mode_transposes(MODE) ? 1 : (QUAD ? 4 * QUAD_SETS : MAX_EPI_WARPS)][32][33];  // emit modes: per-warp 32x32 transpose buffers
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
   uint64_t tfull[ACC_STAGES];
@@ -155,13 +163,9 @@ struct Params {
                              // orientation 1: T^t (classes, coef_ld), value = T^t[label of row][column]
   long long coef_ld;
   int coef_orient;
+  float* coef_sums;          // [chunk][epilogue set][row]: sum over the unit's columns of the ROUNDED coefficients
 };
 
-constexpr int MODE_CLASS_LSE = 0;       // online softmax + per-class sums (the NW head)
-constexpr int MODE_EMIT_SCORES = 1;     // dense per-pair output: the similarity scores
-constexpr int MODE_EMIT_INFLUENCE = 2;  // dense per-pair output: support influence
-constexpr int MODE_EMIT_BLOCKBEST = 3;  // best score of every block of 64 support rows (candidate search for top-k)
-constexpr int MODE_EMIT_COEF = 4;       // backward coefficients w(row, col), bf16, k-block-major over the columns
 // (the emit kind is a template parameter: one kernel with a runtime switch and logf inlined 64 times was > 64 KB
 //  of SASS and ran 4x slower on instruction fetch)
 
@@ -457,53 +461,114 @@ __device__ __forceinline__ void emit_chunk(float (&acc)[32], const float* __rest
 // with K = the column axis.  Orientation 0: rows = queries, columns = supports (W, for grad_q).  Orientation 1:
 // rows = supports, columns = queries (W^t, for grad_s): the per-column log-sum-exp arrives through the label slots
 // of the tile metadata (float bits) and the table is indexed [label of the row][column].
+// Eight columns of one row: coefficient values -> four packed bf16 pairs; `sum` accumulates the ROUNDED values.
+// Branch-free (the first version tested validity and table index per element: 48 BSSY/BSYNC pairs in the SASS
+// serialised the rsqrt -> exp2 chains of the 32 columns, and the emit ran at 65 % of the MMA-bound rate).
+template <int EPI, bool FULL>
+__device__ __forceinline__ uint4 coef_group(const float (&acc)[32], const float* __restrict__ cadd, int c0,
+                                            const float (&tb)[8], const float (&zl)[8], float qn, float scale,
+                                            int n_valid, float& sum) {
+  uint32_t pk[4];
+#pragma unroll
+  for (int k2 = 0; k2 < 4; ++k2) {
+    float w[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = 2 * k2 + h, c = c0 + k;
+      float v;
+      if (EPI == NW_EPI_EUCLID) {
+        const float nn = qn + cadd[c];
+        const float d2 = fmaf(-2.0f, acc[c], nn);
+        float inv;  // 1 / distance: one MUFU op serves the distance and the division (NaN / inf for d2 <= 0: discarded)
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(d2));
+        const float pr = ex2_approx(fmaf(d2 * inv, -kLog2e, zl[k]));
+        // a squared distance below the rounding noise of its own terms (~1e-6 (|q|^2 + |s|^2), and |s| ~ |q| for
+        // such a pair) is a coincident pair: no gradient
+        v = d2 > 2e-6f * qn ? (pr * inv) * tb[k] : 0.0f;
+      } else {
+        v = ex2_approx(fmaf(acc[c], scale * kLog2e, zl[k])) * (tb[k] * scale);
+      }
+      w[h] = (FULL || c < n_valid) ? v : 0.0f;
+    }
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(w[0], w[1]);
+    pk[k2] = *reinterpret_cast<const uint32_t*>(&hh);
+    sum += __uint_as_float(pk[k2] << 16) + __uint_as_float(pk[k2] & 0xffff0000u);
+  }
+  return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
 template <int EPI>
-__device__ __forceinline__ void coef_chunk(float (&acc)[32], const float* __restrict__ cadd,
-                                           const int* __restrict__ lab, float qn, float scale, float row_z,
-                                           int row_lab, const Params& p, int row, int col0, int n_valid) {
-  if (row < 0 || n_valid <= 0) return;
+__device__ __forceinline__ float coef_chunk(float (&acc)[32], const float* __restrict__ cadd,
+                                            const int* __restrict__ lab, float qn, float scale, float row_z,
+                                            int row_lab, const Params& p, int row, int col0, int n_valid) {
+  if (row < 0) return 0.0f;
+  uint4* dst4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.emit_out) +
+                                         ((long long)(col0 >> 6) * p.n_query + row) * 64 + (col0 & 63));
+  if (n_valid <= 0) {
+    // beyond the last column: the output's K axis is padded to a multiple of 64 and the padding must read as zero
+    // in the gradient GEMM (the caller need not clear 10 GB for the sake of at most 63 columns)
+    if (col0 < ((p.n_support + 63) & ~63)) {
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) dst4[g8] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    return 0.0f;
+  }
+  float sum = 0.0f;  // of the values as the gradient GEMM will see them (bf16-rounded)
   const bool by_col = p.coef_orient == 0;  // the table value changes with the column's label
   const float* __restrict__ trow =
       by_col ? p.coef_tab + (long long)row * p.coef_ld : p.coef_tab + (long long)row_lab * p.coef_ld + col0;
-  const bool uniform = by_col && n_valid >= 32 && lab[0] == lab[31];  // class-sorted bank: one class per chunk, mostly
-  const float t_u = uniform ? __ldg(trow + lab[0]) : 0.0f;
-  uint32_t packed[16];
+  const float zl_row = -row_z * kLog2e;
+  // all three tests are warp-uniform (tile metadata and column counts are the same for every row of the warp)
+  if (by_col && n_valid >= 32 && lab[0] == lab[31]) {
+    // class-sorted bank: the 32 columns share one class (39 of 40 chunks at 1280 rows per class): one table value
+    const float t_u = __ldg(trow + lab[0]);
+    float tb[8], zl[8];
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    float w[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int c = i + k;
-      const bool valid = c < n_valid;
-      float tb, z;
-      if (by_col) {
-        z = row_z;
-        tb = uniform ? t_u : ((valid && lab[c] >= 0) ? __ldg(trow + lab[c]) : 0.0f);
-      } else {
-        z = __int_as_float(lab[c]);
-        tb = valid ? __ldg(trow + c) : 0.0f;
-      }
-      float v;
-      if (EPI == NW_EPI_EUCLID) {
-        const float d2 = fmaf(-2.0f, acc[c], qn + cadd[c]);
-        const float dist = sqrt_approx(fmaxf(d2, 0.0f));
-        const float pr = ex2_approx((-dist - z) * kLog2e);
-        // a squared distance below the rounding noise of its own terms is a coincident pair: no gradient
-        v = d2 > 1e-6f * (qn + cadd[c]) ? __fdividef(pr * tb, dist) : 0.0f;
-      } else {
-        v = ex2_approx(fmaf(acc[c], scale, -z) * kLog2e) * tb * scale;
-      }
-      w[k] = valid ? v : 0.0f;
+    for (int k = 0; k < 8; ++k) {
+      tb[k] = t_u;
+      zl[k] = zl_row;
     }
-    const __nv_bfloat162 h = __floats2bfloat162_rn(w[0], w[1]);
-    packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-  }
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.emit_out) +
-                       ((long long)(col0 >> 6) * p.n_query + row) * 64 + (col0 & 63);
-  uint4* dst4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-  for (int v4 = 0; v4 < 4; ++v4)
-    dst4[v4] = make_uint4(packed[v4 * 4], packed[v4 * 4 + 1], packed[v4 * 4 + 2], packed[v4 * 4 + 3]);
+    for (int g8 = 0; g8 < 4; ++g8) dst4[g8] = coef_group<EPI, true>(acc, cadd, g8 * 8, tb, zl, qn, scale, 32, sum);
+  } else if (by_col) {
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      float tb[8], zl[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {  // labels of columns beyond the bank are -1: clamped, the value is masked
+        tb[k] = __ldg(trow + max(lab[g8 * 8 + k], 0));
+        zl[k] = zl_row;
+      }
+      dst4[g8] = coef_group<EPI, false>(acc, cadd, g8 * 8, tb, zl, qn, scale, n_valid, sum);
+    }
+  } else if (n_valid >= 32 && (p.coef_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.coef_tab) & 15) == 0) {
+    // rows = supports, a full chunk of query columns: table values and column terms as 16-byte loads
+    const float4* __restrict__ t4 = reinterpret_cast<const float4*>(trow);
+    const int4* __restrict__ l4 = reinterpret_cast<const int4*>(lab);
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      const float4 ta = __ldg(t4 + 2 * g8), tc = __ldg(t4 + 2 * g8 + 1);
+      const int4 la = l4[2 * g8], lc = l4[2 * g8 + 1];
+      const float tb[8] = {ta.x, ta.y, ta.z, ta.w, tc.x, tc.y, tc.z, tc.w};
+      const float zl[8] = {-__int_as_float(la.x) * kLog2e, -__int_as_float(la.y) * kLog2e,
+                           -__int_as_float(la.z) * kLog2e, -__int_as_float(la.w) * kLog2e,
+                           -__int_as_float(lc.x) * kLog2e, -__int_as_float(lc.y) * kLog2e,
+                           -__int_as_float(lc.z) * kLog2e, -__int_as_float(lc.w) * kLog2e};
+      dst4[g8] = coef_group<EPI, true>(acc, cadd, g8 * 8, tb, zl, qn, scale, 32, sum);
+    }
+  } else {
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      float tb[8], zl[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {  // the column's log-sum-exp rides in the label slot (float bits)
+        tb[k] = __ldg(trow + min(g8 * 8 + k, n_valid - 1));
+        zl[k] = -__int_as_float(lab[g8 * 8 + k]) * kLog2e;
+      }
+      dst4[g8] = coef_group<EPI, false>(acc, cadd, g8 * 8, tb, zl, qn, scale, n_valid, sum);
+    }
+  }
+  return sum;
 }
 
 // MODE_EMIT_BLOCKBEST: best score of this thread's query row over one 32-column chunk (padding columns excluded).
@@ -777,6 +842,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       if (!bulk_tile(t0)) load_meta(t0);
 
       float m = neg_inf, l = 0.0f;
+      float coef_rsum = 0.0f;  // MODE_EMIT_COEF: this row's coefficient sum over the unit's columns (this set's share)
       int open_cls = -1;  // two sets: class whose partial this set currently holds (warp-uniform)
       for (int t = t0; t < t1; ++t, ++tc) {
         const uint32_t as = tc & 1u;
@@ -828,6 +894,11 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 float acc[32];
                 tmem_ld_32x32(t_addr + cc * 32, acc);
                 tmem_ld_wait();
+                if (MODE == MODE_EMIT_COEF) {
+                  coef_rsum += coef_chunk<EPI>(acc, meta.cadd + cc * 32, meta.lab + cc * 32, qn, p.scale_log2 * kLn2, e_z,
+                                               e_qy, p, row_valid ? row : -1, j0 + cc * 32, n1 - (j0 + cc * 32));
+                  continue;
+                }
                 emit_chunk<EPI, INFL>(acc, meta.cadd + cc * 32, meta.lab + cc * 32, qn, p.scale_log2 * kLn2, e_z, e_p, e_qy,
                                       stg, lane, emit_out, p.emit_ld, row0, p.n_query, j0 + cc * 32, n1 - (j0 + cc * 32),
                                       p.emit_vec != 0);
@@ -840,10 +911,11 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             tmem_ld_wait();
             if (MODE == MODE_EMIT_COEF) {
               const int rr = row_valid ? row : -1;
-              coef_chunk<EPI>(acc0, meta.cadd + c * 32, meta.lab + c * 32, qn, p.scale_log2 * kLn2, e_z, e_qy, p, rr,
-                              j0 + c * 32, n1 - (j0 + c * 32));
-              coef_chunk<EPI>(acc1, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, qn, p.scale_log2 * kLn2, e_z, e_qy,
-                              p, rr, j0 + (c + 1) * 32, n1 - (j0 + (c + 1) * 32));
+              coef_rsum += coef_chunk<EPI>(acc0, meta.cadd + c * 32, meta.lab + c * 32, qn, p.scale_log2 * kLn2, e_z, e_qy,
+                                           p, rr, j0 + c * 32, n1 - (j0 + c * 32));
+              coef_rsum += coef_chunk<EPI>(acc1, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, qn,
+                                           p.scale_log2 * kLn2, e_z, e_qy, p, rr, j0 + (c + 1) * 32,
+                                           n1 - (j0 + (c + 1) * 32));
               continue;
             }
             if (MODE == MODE_EMIT_BLOCKBEST) {
@@ -946,6 +1018,8 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       // two sets: the unit's last columns may belong to the other set; close what this set still holds
       if (MODE == MODE_CLASS_LSE && n_sets >= 2 && open_cls >= 0) flush(open_cls, m, l);
+      if (MODE == MODE_EMIT_COEF && row_valid && p.coef_sums != nullptr)
+        p.coef_sums[(long long)(g * n_sets + eg) * p.n_query + row] = coef_rsum;
     }
     if (probe) {
       atomicAdd(p.clock_probe + 2 * blockIdx.x, (unsigned long long)(clock64() - probe_c0));
@@ -1407,6 +1481,7 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   p.coef_tab = nullptr;
   p.coef_ld = 0;
   p.coef_orient = 0;
+  p.coef_sums = nullptr;
   p.clock_probe = (g_clock_probe && plan.grid <= g_clock_probe_ctas) ? g_clock_probe : nullptr;
   {
     static const int skip = [] {
@@ -1493,7 +1568,20 @@ struct EmitExtra {
   const float* coef_tab = nullptr;  // EMIT_COEF_INTERNAL
   long long coef_ld = 0;
   int coef_orient = 0;
+  float* coef_ws = nullptr;    // [chunks][COEF_SETS][n_rows] partial row sums
+  float* coef_sums = nullptr;  // (n_rows) their fixed-order total
 };
+
+constexpr int COEF_SETS = k1::QUAD_SETS;  // epilogue sets of the coefficient emit
+
+// sums[r] = sum_i ws[i][r] in fixed order (deterministic: no atomics across the chunks / epilogue sets)
+__global__ void coef_sum_kernel(const float* __restrict__ ws, int parts, int n_rows, float* __restrict__ sums) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  float acc = 0.0f;
+  for (int i = 0; i < parts; ++i) acc += ws[(long long)i * n_rows + r];
+  sums[r] = acc;
+}
 
 static int emit_impl(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
                      const void* bank_bf16, const float* s_sqnorm, const int32_t* labels, int64_t n_support,
@@ -1549,6 +1637,7 @@ static int emit_impl(int epilogue, float scale, const void* q_bf16, const float*
   p.emit_ld = ld_out;
   p.emit_kind = emit_kind;
   p.emit_vec = (ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+  p.clock_probe = (g_clock_probe && plan.grid <= g_clock_probe_ctas) ? g_clock_probe : nullptr;
   p.row_lse = row_lse;
   p.p_query = p_query;
   p.qlabel = qlabel;
@@ -1559,6 +1648,7 @@ static int emit_impl(int epilogue, float scale, const void* q_bf16, const float*
   p.coef_tab = ex.coef_tab;
   p.coef_ld = ex.coef_ld;
   p.coef_orient = ex.coef_orient;
+  p.coef_sums = ex.coef_ws;
   int grid = plan.grid;
   if (p.kslices > 1) {  // more units than the plan knew of: size the persistent grid for all of them
     const long long units = (long long)plan.chunks * plan.q_tiles * p.kslices;
@@ -1584,7 +1674,17 @@ static int emit_impl(int epilogue, float scale, const void* q_bf16, const float*
            : (ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2, MODE_, true>(map_q, map_s, p, grid, stream)           \
                         : k1::launch_forward<NW_EPI_LINEAR, 1, MODE_, true>(map_q, map_s, p, grid, stream))
   if (emit_kind == NW_EMIT_SCORES) NW_LAUNCH_EMIT(k1::MODE_EMIT_SCORES);
-  else if (emit_kind == EMIT_COEF_INTERNAL) NW_LAUNCH_EMIT(k1::MODE_EMIT_COEF);
+  else if (emit_kind == EMIT_COEF_INTERNAL) {
+    // exp, reciprocal square root, table lookup, rounding and 64-byte stores per pair: latency-bound like the
+    // influence transform, so four epilogue sets
+    p.sets = COEF_SETS;
+    NW_LAUNCH_EMIT4(k1::MODE_EMIT_COEF);
+    if (rc == NW_OK && ex.coef_sums != nullptr) {
+      coef_sum_kernel<<<ceil_div(n_query, 256), 256, 0, stream>>>(ex.coef_ws, plan.chunks * COEF_SETS, n_query,
+                                                                  ex.coef_sums);
+      NW_CUDA_OK(cudaGetLastError());
+    }
+  }
   else if (emit_kind == NW_EMIT_INFLUENCE && emit_sets == 4) {
     p.sets = k1::QUAD_SETS;
     NW_LAUNCH_EMIT4(k1::MODE_EMIT_INFLUENCE);
@@ -1606,6 +1706,12 @@ extern "C" int nw_forward_emit(int epilogue, float scale, const void* q_bf16, co
                    emit_kind, row_lse, p_query, qlabel, out, ld_out, EmitExtra(), stream_);
 }
 
+extern "C" int64_t nw_backward_coefficients_workspace_elems(int64_t n_rows, int64_t n_cols) {
+  nw_forward_plan_t plan;
+  if (n_rows <= 0 || n_rows >= (int64_t(1) << 31) - 512 || nw_forward_plan(int(n_rows), n_cols, &plan) != NW_OK) return -1;
+  return int64_t(plan.chunks) * COEF_SETS * n_rows;
+}
+
 // Tensor-core backward, step 1 (recompute): see coef_chunk.  `rows` / `cols` are the two operands of the score
 // GEMM in this kernel's k-block-major bf16 layout; orientation 0: rows = queries, cols = the class-sorted bank;
 // orientation 1: rows = the bank, cols = queries.
@@ -1614,7 +1720,8 @@ extern "C" int nw_backward_coefficients(int epilogue, float scale, int orientati
                                         const float* cols_sqnorm, int64_t n_cols, int row_elems,
                                         const float* row_lse, const int32_t* row_labels, const float* col_lse,
                                         const int32_t* col_labels, const float* table, int64_t table_ld,
-                                        void* out_bf16, void* stream_) {
+                                        void* out_bf16, float* row_sums, float* workspace,
+                                        int64_t workspace_elems, void* stream_) {
   NW_REQUIRE(orientation == 0 || orientation == 1, NW_ERR_INVALID, "orientation must be 0 or 1");
   NW_REQUIRE(table != nullptr && out_bf16 != nullptr, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(n_rows > 0 && n_rows < (int64_t(1) << 31) - 512, NW_ERR_UNSUPPORTED, "n_rows must be in (0, 2^31 - 512)");
@@ -1623,10 +1730,16 @@ extern "C" int nw_backward_coefficients(int epilogue, float scale, int orientati
     NW_REQUIRE(row_lse && col_labels, NW_ERR_INVALID, "orientation 0 needs row_lse and col_labels");
   else
     NW_REQUIRE(col_lse && row_labels, NW_ERR_INVALID, "orientation 1 needs col_lse and row_labels");
+  NW_REQUIRE(row_sums != nullptr && workspace != nullptr, NW_ERR_INVALID, "NULL pointer argument");
+  NW_REQUIRE(workspace_elems >= nw_backward_coefficients_workspace_elems(n_rows, n_cols), NW_ERR_WORKSPACE,
+             "workspace too small: %lld < %lld floats", (long long)workspace_elems,
+             (long long)nw_backward_coefficients_workspace_elems(n_rows, n_cols));
   EmitExtra ex;
   ex.coef_tab = table;
   ex.coef_ld = table_ld;
   ex.coef_orient = orientation;
+  ex.coef_ws = workspace;
+  ex.coef_sums = row_sums;
   // orientation 1: the per-column log-sum-exp travels through the label slots of the tile metadata (float bits)
   const int32_t* col_meta = orientation == 0 ? col_labels : reinterpret_cast<const int32_t*>(col_lse);
   return emit_impl(epilogue, scale, rows_bf16, rows_sqnorm, int(n_rows), cols_bf16, cols_sqnorm, col_meta, n_cols,

@@ -143,20 +143,21 @@ class NWHead(nn.Module):
         self.backward_path = backward_path
         self._bank_cache = []
 
-    def _bank_for(self, sx, sy, kind):
+    def _bank_for(self, sx, sy, kind, precision=None):
         """The reference hands the SAME support tensors to the head on every predict call (nwhead/nw.py:156-160).
         Building the device bank (sort check, centring, bf16 conversion) once per tensor version instead of once
         per call keeps that usage pattern fast; in-place modification bumps `_version` and invalidates the entry."""
         # identity of the live tensor OBJECTS (weak references), not their addresses: a freed support's memory is
         # routinely handed to the next one (knn mode builds a new support per batch)
+        precision = precision or self.precision
         if sx.is_inference() or sy.is_inference():
             # inference-mode tensors have no version counter: nothing to validate a cached bank against
-            return SupportBank.build(sx, sy, self.n_classes, kind, self.precision)
-        key = (sx._version, sy._version, kind, self.precision, self.n_classes)
+            return SupportBank.build(sx, sy, self.n_classes, kind, precision)
+        key = (sx._version, sy._version, kind, precision, self.n_classes)
         for ref_x, ref_y, k, bank in self._bank_cache:
             if ref_x() is sx and ref_y() is sy and k == key:
                 return bank
-        bank = SupportBank.build(sx, sy, self.n_classes, kind, self.precision)
+        bank = SupportBank.build(sx, sy, self.n_classes, kind, precision)
         self._bank_cache = [e for e in self._bank_cache if e[0]() is not None and e[1]() is not None]
         self._bank_cache.append((weakref.ref(sx), weakref.ref(sy), key, bank))
         del self._bank_cache[:-self.BANK_CACHE_SIZE]
@@ -212,7 +213,9 @@ class NWHead(nn.Module):
         if n == 0:
             raise ValueError("NWHead needs at least one support row")
         if needs_grad and wants_tensor_path(x.shape[0], n, sx.dim(), self.backward_path):
-            return NWTensorFunction.apply(x, sx, sy, logit_scale, kind, self.n_classes)
+            # a support that is not being trained keeps its bank (and its transposed copy) across steps
+            bank = None if sx.requires_grad else self._bank_for(sx, sy, kind, "bf16")
+            return NWTensorFunction.apply(x, sx, sy, logit_scale, kind, self.n_classes, bank)
         if needs_grad or sx.dim() == 3 or n < MM_PATH_MIN_ROWS:
             if needs_grad and x.shape[-1] + self.n_classes > _abi.DIRECT_BACKWARD_MAX_D_PLUS_C:
                 # fail before the forward, not at .backward()

@@ -470,6 +470,39 @@ def aux_configs(feats, labels, bank, mu, dev, peaks):
                 "engine, 2 gradient accumulations): host time no head implementation can remove",
         "cpu_baseline": {"wall_us": cpu_us, "cores": cores, "kind": "port",
                          "sample": "the same step through the reference's op sequence on CPU tensors, 200 iterations"}}
+    # ---- large-support training step: forward + backward (grad_q) of B=1024 queries against the whole bank on the
+    # tensor cores (nwhead_b200/backward.py; the reference differentiates NWHead.forward with autograd at any N)
+    try:
+        b_t = 1024
+        qt, qyt = synth_queries(mu, b_t, dev)
+        head_t = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), c, backward_path="tensor")
+
+        def train_step():
+            qq = qt.clone().requires_grad_(True)
+            torch.nn.functional.nll_loss(head_t(qq, feats, labels), qyt).backward()
+            return qq.grad
+
+        ms_t = gpu_ms(train_step, 5, warm=2)
+        flop_t = 3 * 2.0 * b_t * n * d  # forward, score recompute, W @ S
+        nb = 160000
+        hs, hy = feats[:nb].cpu(), labels[:nb].cpu()
+        hq = qt[:1].cpu()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            qq = hq.clone().requires_grad_(True)
+            torch.nn.functional.nll_loss(TP.port_nw_forward(qq, hs, hy, c, "euclidean"), qyt[:1].cpu()).backward()
+        cpu_s = (time.perf_counter() - t0) / 2
+        out["large_support_backward"] = {
+            "workload": f"NWHead forward + backward (grad wrt queries) B={b_t} vs the fixed N={n} d={d} support, tensor-core "
+                        "path (class-LSE forward, coefficient recompute, split-K W @ S)",
+            "ms": ms_t, "tflops": flop_t / ms_t / 1e9, "contractions": 3, "peak_tflops": peaks["burst"],
+            "frac_of_tensor_peak": flop_t / ms_t / 1e9 / peaks["burst"] if peaks["burst"] else None,
+            "cpu_baseline": {"s_per_query_scaled": cpu_s * (n / nb), "cores": cores, "kind": "port",
+                             "sample": f"the reference's op sequence + torch autograd, B=1 query x N={nb} supports "
+                                       f"(1/{n // nb} of the bank), forward+backward, scaled linearly in N"}}
+        del hs, hy, head_t
+    except Exception as e:
+        out["large_support_backward"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return out
 
 

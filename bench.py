@@ -230,7 +230,8 @@ class ClockProbe:
     def __enter__(self):
         self.buf.zero_()
         torch.cuda.synchronize()
-        self.abi.check(self.abi.load().nw_forward_set_clock_probe(self.abi.ptr(self.buf), self.n), "set_clock_probe")
+        if os.environ.get("NW_BENCH_CLOCK_PROBE", "on") != "off":
+            self.abi.check(self.abi.load().nw_forward_set_clock_probe(self.abi.ptr(self.buf), self.n), "set_clock_probe")
         return self
 
     def __exit__(self, *exc):
@@ -557,16 +558,35 @@ def main():
     torch.cuda.synchronize()
     plan = _abi.forward_plan(B, len(bank))
 
-    def step_resident():
+    def event_pairs(n):
+        """Timing events, created AND recorded once before they are needed: the first record of a torch event is
+        what creates the CUDA event, and creating one while the persistent forward kernel occupies every SM blocked
+        the host for 2-80 ms on the second step of every timed region (profiles/r2_bench_warmup_trace.txt)."""
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for a, b in pairs:
+            a.record()
+            b.record()
+        return pairs
+
+    stamps = []  # NW_BENCH_TRACE: host time of the sub-calls of every resident step
+
+    def step_resident(ev=None):
+        t_a = time.perf_counter()
         qb, qs = bank.prepare_queries(q_dev)
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
+        t_b = time.perf_counter()
+        e0, e1 = ev if ev is not None else event_pairs(1)[0]
         e0.record()
         # every rank finalises its own B/R rows of the merged table (the results stay sharded across ranks)
         if sharded.peer is None:
+            t_c = time.perf_counter()
             lse = bank.class_lse_prepared(qb, qs)
+            t_d = time.perf_counter()
             e1.record()
             lse = sharded_merge(lse)[rank * rows:(rank + 1) * rows]
+            if trace_on:
+                out = logp_from_class_lse(lse)
+                stamps.append([(y - x) * 1e3 for x, y in ((t_a, t_b), (t_b, t_c), (t_c, t_d), (t_d, time.perf_counter()))])
+                return out, (e0, e1)
         else:
             table, hdl, ptrs, ch = sharded.peer.next()
             bank.class_lse_prepared(qb, qs, tables=ptrs, rows_per_table=rows)
@@ -614,26 +634,38 @@ def main():
 
     def timed_resident(n_steps):
         """n_steps resident steps between barriers, CUDA events on the launching stream, max over ranks."""
+        events = event_pairs(n_steps)
+        (s0, s1), = event_pairs(1)
+        # Two untimed steps whose results are held together with whatever the caller still holds: the caching
+        # allocator then owns every block the loop below will ask for.  Without them the SECOND step of a region
+        # needed one block more than any step before it, and that cudaMalloc — issued while the persistent forward
+        # kernel occupied every SM — blocked the host for 2-150 ms: one 70 ms "step" in a 20-step window
+        # (profiles/r2_bench_warmup_trace.txt).  Timing events are pre-created for the same reason.
+        held = [step_resident(events[i])[0] for i in range(min(2, n_steps))]
+        del held
+        for _ in range(8):  # back to the operating point after that stall (the GPU idled through it)
+            step_resident(events[0])
         barrier()
-        events = []
         w0 = time.time()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for _ in range(n_steps):
-            out, ev = step_resident()
-            events.append(ev)
+        host_t = []
+        for i in range(n_steps):
+            out, _ = step_resident(events[i])
+            host_t.append(time.perf_counter())
         s1.record()
         barrier()
         win = (w0, time.time())
         total = max_over_ranks(s0.elapsed_time(s1))
         per_step = [a.elapsed_time(b) for a, b in events]
         kern = max_over_ranks(statistics.mean(per_step))
-        trace.append({"steps": n_steps, "window": win, "kernel_ms_per_step": per_step})
+        trace.append({"steps": n_steps, "window": win, "kernel_ms_per_step": per_step,
+                      "host_submit_ms": [(t - host_t[0]) * 1e3 for t in host_t[:64]]})
         return out, total, kern, win
 
+    trace_on = bool(os.environ.get("NW_BENCH_TRACE"))
     trace = []  # per-step kernel times of every timed region (NW_BENCH_TRACE=<file> dumps them with the NVML samples)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get("NW_BENCH_SAMPLER", "on") != "off":  # (developer switch: is the sampler intrusive?)
         sampler.start()
     probe = ClockProbe(_abi, dev, plan.grid)
 
@@ -812,7 +844,7 @@ def main():
         print(json.dumps(line), flush=True)
         if os.environ.get("NW_BENCH_TRACE"):
             with open(os.environ["NW_BENCH_TRACE"], "w") as f:
-                json.dump({"regions": trace, "nvml": [[r[0], r[1], r[2], r[3]] for r in sampler.rows]}, f)
+                json.dump({"regions": trace, "stamps": stamps, "stamp_names": ["prepare_queries", "events", "class_lse_prepared", "record+logp"], "nvml": [[r[0], r[1], r[2], r[3]] for r in sampler.rows]}, f)
         for msg in failed:
             print(f"bench: CHECK FAILED — {msg}", file=sys.stderr, flush=True)
     fail_flag = torch.tensor([1 if failed else 0], device=dev)

@@ -24,7 +24,9 @@
 // (one thread per query row = TMEM lane); the emit modes (dense scores / support influence, no state along
 // the columns) add warps 8-11 as a second epilogue set.
 
+#include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include "nw_common.cuh"
 
@@ -1406,6 +1408,28 @@ static int launch_forward(const CUtensorMap& map_q, const CUtensorMap& map_s, co
 }  // namespace k1
 }  // namespace nw
 
+// Developer probe (NW_B200_TRACE_HOST=1): report host-side stages of the forward call that take longer than 0.3 ms.
+struct HostStageTimer {
+  bool on;
+  timespec t0;
+  HostStageTimer() {
+    static const bool enabled = [] {
+      const char* e = getenv("NW_B200_TRACE_HOST");
+      return e && e[0] == '1';
+    }();
+    on = enabled;
+    if (on) clock_gettime(CLOCK_MONOTONIC, &t0);
+  }
+  void lap(const char* what) {
+    if (!on) return;
+    timespec t1;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+    if (ms > 0.3) fprintf(stderr, "[nw host trace] %s took %.2f ms\n", what, ms);
+    t0 = t1;
+  }
+};
+
 static int forward_impl(int epilogue, float scale, const void* q_bf16, const float* q_sqnorm, int n_query,
                         const void* bank_bf16, const float* s_sqnorm, const int32_t* labels, int64_t n_support,
                         int row_elems, int n_classes, float* const* tables, int n_tables, int rows_per_table,
@@ -1423,8 +1447,10 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   NW_REQUIRE(n_classes > 0, NW_ERR_INVALID, "n_classes must be positive");
   NW_REQUIRE((reinterpret_cast<uintptr_t>(q_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(bank_bf16) & 15) == 0,
              NW_ERR_INVALID, "bf16 operands must be 16-byte aligned");
+  HostStageTimer host_timer;
   int rc = nw_device_check();
   if (rc != NW_OK) return rc;
+  host_timer.lap("nw_device_check");
   nw_forward_plan_t plan;
   rc = nw_forward_plan(n_query, n_support, &plan);
   if (rc != NW_OK) return rc;
@@ -1444,11 +1470,13 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
   if (rc != NW_OK) return rc;
   rc = k1::make_map(&map_s, bank_bf16, uint64_t(n_support), uint64_t(row_elems), k1::BN / ncta);
   if (rc != NW_OK) return rc;
+  host_timer.lap("plan + tensor maps");
 
   k1::fill_kernel<<<sm_count() * 4, 256, 0, stream>>>(tables[0], fill_local ? table_elems : 0, side,
                                                       (long long)plan.side_elems + (sets - 1) * table_elems,
                                                       -INFINITY);
   NW_CUDA_OK(cudaGetLastError());
+  host_timer.lap("fill launch");
 
   k1::Params p;
   p.q_sqnorm = q_sqnorm;
@@ -1526,6 +1554,7 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
                           : k1::launch_forward<NW_EPI_LINEAR, 1>(map_q, map_s, p, plan.grid, stream));
   }
   if (rc != NW_OK) return rc;
+  host_timer.lap("K1 launch");
 
   if (sets > 1) {  // combine the epilogue sets' tables
     k1::lse_merge_sets_kernel<<<sm_count() * 4, 256, 0, stream>>>(tables[0], table1, sets - 1, table_elems);
@@ -1536,6 +1565,7 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
         tl, side, labels, n_query, int(n_support), n_classes, plan.chunks, plan.tiles_per_chunk, plan.s_tiles, sets);
     NW_CUDA_OK(cudaGetLastError());
   }
+  host_timer.lap("merge launches");
   return NW_OK;
 }
 

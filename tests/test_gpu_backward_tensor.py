@@ -110,3 +110,52 @@ def test_zero_distance_contributes_no_gradient(cuda_lib):
     st = torch.from_numpy(s).to(DEV).requires_grad_(True)
     (head(qt, st, torch.from_numpy(y).to(DEV)) * torch.from_numpy(g).to(DEV)).sum().backward()
     assert torch.isfinite(qt.grad).all() and torch.isfinite(st.grad).all()
+
+
+def test_auto_routing_and_label_errors(cuda_lib):
+    """backward_path='auto': a big batch against a big shared support differentiates on the tensor cores, a small
+    problem stays on the direct fp32 kernels; an out-of-range label raises like F.one_hot (nwhead/nw.py:276)."""
+    import nwhead_b200
+
+    C, d = 16, 32
+    head = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), C)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    s = torch.randn(1 << 18, d, generator=g, device=DEV)
+    y = torch.randint(0, C, (1 << 18,), generator=g, device=DEV)
+    q = torch.randn(64, d, generator=g, device=DEV, requires_grad=True)
+    out = head(q, s, y)
+    assert type(out.grad_fn).__name__ == "NWTensorFunctionBackward"
+    out.sum().backward()
+    assert torch.isfinite(q.grad).all()
+    small = head(q[:8], s[:100], y[:100])
+    assert type(small.grad_fn).__name__ != "NWTensorFunctionBackward"
+    # the fixed support's bank (and its transposed copy) is built once and reused
+    assert head(q, s, y).grad_fn is not None and len(head._bank_cache) == 1
+    bad = y.clone()
+    bad[5] = C
+    strict = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), C, backward_path="tensor")
+    with pytest.raises(RuntimeError):
+        strict(q, s, bad)
+    with pytest.raises(ValueError):
+        nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), C, backward_path="nope")
+
+
+def test_tensor_backward_on_tiny_and_ragged_problems(cuda_lib):
+    """Forced tensor path far below its intended sizes: fewer than 8 queries, fewer supports than one tile, one
+    support per class (the identity-class bank of cluster mode)."""
+    import nwhead_b200
+
+    for B, N, d, C in [(3, 40, 20, 5), (1, 7, 8, 7), (9, 300, 70, 300)]:
+        rng = np.random.default_rng(N)
+        q = rng.normal(size=(B, d)).astype(np.float32)
+        s = rng.normal(size=(N, d)).astype(np.float32)
+        y = (np.arange(N) % C).astype(np.int64) if N != C else np.arange(N).astype(np.int64)
+        g = rng.normal(size=(B, C)).astype(np.float32)
+        head = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), C, backward_path="tensor")
+        qt = torch.from_numpy(q).to(DEV).requires_grad_(True)
+        st = torch.from_numpy(s).to(DEV).requires_grad_(True)
+        (head(qt, st, torch.from_numpy(y).to(DEV)) * torch.from_numpy(g).to(DEV)).sum().backward()
+        res = O.nw_backward(q, s, y, C, g, "euclidean")
+        for got, want in ((qt.grad, res[0]), (st.grad, res[1])):
+            err = np.abs(got.cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-30)
+            assert err < GRAD_TOL, (B, N, d, C, err)

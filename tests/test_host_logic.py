@@ -129,3 +129,16 @@ def test_kmeans_first_seed_matches_numpy_choice():
     ref = np.random.RandomState(0)
     ref.choice(5, p=np.ones(5) / 5)
     assert np.array_equal(rs.uniform(size=3), ref.uniform(size=3))
+
+
+def test_tensor_backward_routing():
+    """NWHead's choice between the direct fp32 kernels and the tensor-core forward + backward (host logic)."""
+    from nwhead_b200.backward import MIN_PAIRS, MIN_QUERIES, wants_tensor_path
+
+    assert wants_tensor_path(4096, 1280000, 2, "auto")
+    assert wants_tensor_path(MIN_QUERIES, MIN_PAIRS // MIN_QUERIES, 2, "auto")
+    assert not wants_tensor_path(8, 1280000, 2, "auto")          # few queries: HBM-bound, the direct path reads S once
+    assert not wants_tensor_path(4096, 1000, 2, "auto")          # small support
+    assert not wants_tensor_path(4096, 1280000, 3, "auto")       # per-query supports are not a shared GEMM
+    assert not wants_tensor_path(4096, 1280000, 2, "direct")
+    assert wants_tensor_path(2, 30, 2, "tensor") and not wants_tensor_path(2, 30, 3, "tensor")

@@ -501,9 +501,28 @@ def aux_configs(feats, labels, bank, mu, dev, peaks):
             "cpu_baseline": {"s_per_query_scaled": cpu_s * (n / nb), "cores": cores, "kind": "port",
                              "sample": f"the reference's op sequence + torch autograd, B=1 query x N={nb} supports "
                                        f"(1/{n // nb} of the bank), forward+backward, scaled linearly in N"}}
-        del hs, hy, head_t
+        del hs, hy
+        # config 3 itself as a training step: 4096 queries, gradients for the queries AND all 1.28M support rows
+        q4, qy4 = synth_queries(mu, 4096, dev)
+        feats.requires_grad_(True)
+
+        def train_step_both():
+            qq = q4.clone().requires_grad_(True)
+            feats.grad = None
+            torch.nn.functional.nll_loss(head_t(qq, feats, labels), qy4).backward()
+
+        try:
+            ms_b = gpu_ms(train_step_both, 3, warm=1)
+            out["large_support_backward"]["both_gradients"] = {
+                "workload": f"B=4096 vs N={n}: forward + grad_q + grad_s (the support is rebuilt and transposed every step)",
+                "ms": ms_b, "tflops": 5 * 2.0 * 4096 * n * d / ms_b / 1e9, "contractions": 5}
+        finally:
+            feats.requires_grad_(False)
+            feats.grad = None
+        del head_t
     except Exception as e:
-        out["large_support_backward"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        out.setdefault("large_support_backward", {})["error"] = f"{type(e).__name__}: {e}"[:300]
+    torch.cuda.empty_cache()
     return out
 
 

@@ -73,7 +73,10 @@ template <int NCTA, int MODE = 0, bool QUAD = false>
 struct Cfg {
   // the emit modes give ring stages up for the per-warp transpose buffers of their epilogue (8 warps: one stage,
   // the 16 warps of the QUAD variant: two)
-  static constexpr int STAGES = (NCTA == 1 ? 4 : 6) - (!mode_transposes(MODE) ? 0 : (QUAD ? 2 : 1));
+#ifndef NW_K1_STAGES_PAIR
+#define NW_K1_STAGES_PAIR 6  // developer A/B builds: TMA ring depth of the CTA-pair kernels (32 KB per stage and CTA)
+#endif
+  static constexpr int STAGES = (NCTA == 1 ? 4 : NW_K1_STAGES_PAIR) - (!mode_transposes(MODE) ? 0 : (QUAD ? 2 : 1));
   static constexpr int B_ROWS = BN / NCTA;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;

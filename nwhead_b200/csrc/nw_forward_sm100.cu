@@ -147,6 +147,9 @@ struct Params {
   float scale_log2;  // LINEAR: scale * log2(e)
   int sets;          // epilogue warp sets (1, 2 or 4); class-LSE with several sets: set s stores to lse[s]
   int meta_bulk;     // class-LSE: the producer delivers the metadata of interior tiles (see META_SLOTS)
+  int krot_step;            // query group qg walks the k-blocks of every tile starting at (qg * krot_step) % count:
+                            // the CTA pairs that share a support tile then ask the L2 for DIFFERENT lines at any
+                            // one time (0: all start at k-block 0)
   int stagger_ns;           // developer probe (NW_B200_STAGGER_NS): query group g delays its first load by g * this
   int debug_skip_epilogue;  // developer probe (NW_B200_DEBUG_SKIP_EPI=1): accumulators are released unread -> the
                             // speed of the TMA + MMA mainloop alone (results are garbage)
@@ -696,7 +699,10 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             bulk_load_1d(smem_u32(tail->mslot[ms].lab), p.labels + t * BN, META_LAB_BYTES, bar);
             ++mc;
           }
-          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int nkb = kb1 - kb0;
+          const int rot = (qg * p.krot_step) % nkb;  // (the sum over k does not care where it starts)
+          for (int i = 0; i < nkb; ++i, ++it) {
+            const int kb = kb0 + (i + rot < nkb ? i + rot : i + rot - nkb);
             const uint32_t s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
@@ -1411,6 +1417,21 @@ static int launch_forward(const CUtensorMap& map_q, const CUtensorMap& map_s, co
 }  // namespace k1
 }  // namespace nw
 
+// k-block rotation between the query groups that share a support tile (Params::krot_step).  Developer experiment,
+// OFF unless NW_B200_KROT=1: it was meant to keep 16 CTA pairs from asking the L2 for the same line at the same time
+// (were the bank re-reads from HBM duplicate fetches of lines still in flight?).  Measured on a box that re-reads
+// 13.8 GB per launch: 12.4 GB with the rotation, but 1190 instead of 1204 MHz under the power cap and 269 k instead of
+// 272 k queries/s — simultaneous requests are not the cause, and the L2 serves them more cheaply than spread ones.
+static int k_rotation_step(int q_groups, int kblocks) {
+  static const int enabled = [] {
+    const char* e = getenv("NW_B200_KROT");
+    return e && *e ? atoi(e) : 0;
+  }();
+  if (!enabled || q_groups < 2 || kblocks < 2) return 0;
+  const int step = kblocks / q_groups;
+  return step > 0 ? step : 1;
+}
+
 // Developer probe (NW_B200_TRACE_HOST=1): report host-side stages of the forward call that take longer than 0.3 ms.
 struct HostStageTimer {
   bool on;
@@ -1532,6 +1553,7 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
       return e && *e ? atoi(e) : 0;
     }();
     p.stagger_ns = stagger;
+    p.krot_step = k_rotation_step(plan.q_tiles, p.kblocks);
     static const int bulk_meta = [] {  // developer knob: 0 = every tile's metadata staged by the epilogue sets
       const char* e = getenv("NW_B200_META_BULK");
       return e && *e ? atoi(e) : 1;
@@ -1677,6 +1699,7 @@ static int emit_impl(int epilogue, float scale, const void* q_bf16, const float*
   // split-K: no slice may be empty (its accumulator would be read without a single MMA)
   p.kb_per_slice = ceil_div(p.kblocks, ex.kslices);
   p.kslices = ceil_div(p.kblocks, p.kb_per_slice);
+  p.krot_step = k_rotation_step(plan.q_tiles, p.kb_per_slice);
   p.emit_slice_stride = ex.slice_stride;
   p.coef_tab = ex.coef_tab;
   p.coef_ld = ex.coef_ld;

@@ -229,6 +229,17 @@ NW_API int nw_backward_coefficients(int epilogue, float scale, int orientation, 
                              const float* table, int64_t table_ld, void* out_bf16, float* row_sums,
                              float* workspace, int64_t workspace_elems, void* stream);
 
+/* grad_s of the tensor-core backward in one launch (products + last step):
+ *   out[dst(c)][r] = sum_k a[r][k] * b[c][k] - col_sub[c] * rows_t(r, c),   r < n_out_cols, c < n_b
+ * a = Q^t (k_elems/64, n_a, 64): the features as rows, K = the queries; b = W^t (k_elems/64, n_b, 64): the supports as
+ * rows; rows_t = the transposed bank (ceil(n_b / 64), n_a, 64) with col_sub = colsum(W) (both NULL for linear
+ * scores); dst_rows int32 (n_b): bank row -> row of the caller's support tensor (NULL: identity).  out fp32
+ * (n_b, ld_out >= n_out_cols).  The big operand streams once as the kernel's "bank"; nothing but the gradient is
+ * written. */
+NW_API int nw_dense_products_transposed(const void* a_bf16, int64_t n_a, const void* b_bf16, int64_t n_b, int k_elems,
+                                 const float* col_sub, const void* rows_t_bf16, const int32_t* dst_rows,
+                                 int n_out_cols, float* out, int64_t ld_out, void* stream);
+
 /* Transposed operand: in (kblocks, n_rows, 64) bf16 k-block-major -> out (ceil(n_rows / 64), kblocks * 64, 64),
  * out[r / 64][f][r % 64] = in[f / 64][r][f % 64], zero rows appended up to a multiple of 64 (the B operand of
  * nw_dense_products when the contraction runs over the ROWS: S^t for grad_q, Q^t for grad_s). */

@@ -69,6 +69,8 @@ SIGNATURES = {
     "nw_backward_coefficients": (c_int, [c_int, c_float, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                          c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                          c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "nw_dense_products_transposed": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                             c_int, c_void_p, c_int64, c_void_p]),
     "nw_transpose_kblocks": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "nw_backward_finish": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
                                    c_int64, c_void_p]),

@@ -113,6 +113,28 @@ def dense_products(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return res[:, :n_b]
 
 
+def support_gradient(wt: torch.Tensor, q_bf16: torch.Tensor, bank: SupportBank, colsum) -> torch.Tensor:
+    """grad wrt the stored support rows, (N, d) in the row order of the tensor the bank was built from, in ONE launch
+    (nw_dense_products_transposed): W^t streams once as the kernel's bank operand against Q^t, and the epilogue
+    subtracts colsum(W) * stored row (colsum None: linear scores) and scatters the rows back through the bank's
+    sort permutation."""
+    lib = load()
+    dev = bank.device
+    n, d = len(bank), bank.d
+    qt = transpose_operand(q_bf16)  # (ceil(B/64), row_elems, 64): features as rows, K = the queries
+    assert wt.shape[0] == qt.shape[0] and wt.shape[1] == n
+    dst = None
+    if bank.perm is not None:
+        dst = getattr(bank, "_perm_i32", None)
+        if dst is None:
+            dst = bank._perm_i32 = bank.perm.to(torch.int32)
+    out = torch.empty((n, d), dtype=torch.float32, device=dev)
+    rows_t = bank_transposed(bank) if colsum is not None else None
+    check(lib.nw_dense_products_transposed(ptr(qt), qt.shape[1], ptr(wt), n, qt.shape[0] * 64, ptr(colsum), ptr(rows_t),
+                                           ptr(dst), d, ptr(out), d, stream_of(dev)), "nw_dense_products_transposed")
+    return out
+
+
 class NWTensorFunction(torch.autograd.Function):
     """NWHead.forward(x, sx, sy) for a 2-D support on the tensor cores, forward and backward."""
 
@@ -161,15 +183,8 @@ class NWTensorFunction(torch.autograd.Function):
                 gq = through_normalisation(g_hat, x)
         if need_s:
             wt, colsum = coefficients(bank, q_bf16, q_sq, row_lse, table, scale, 1)
-            raw = dense_products(wt, transpose_operand(q_bf16))
+            gs = through_normalisation(support_gradient(wt, q_bf16, bank, colsum if euclid else None), sx)
             del wt
-            if normalised and bank.perm is not None:
-                g_sorted = through_normalisation(finish(raw, bank.feats_bf16, colsum if euclid else None, None, d),
-                                                 sx[bank.perm])
-                gs = torch.empty_like(g_sorted)
-                gs[bank.perm] = g_sorted
-            else:  # the support's own row order is restored by the finishing kernel
-                gs = through_normalisation(finish(raw, bank.feats_bf16, colsum if euclid else None, bank.perm, d), sx)
         return gq, gs, None, gscale, None, None, None
 
 

@@ -63,7 +63,10 @@ constexpr int MODE_EMIT_INFLUENCE = 2;  // dense per-pair output: support influe
 constexpr int MODE_EMIT_BLOCKBEST = 3;  // best score of every block of 64 support rows (candidate search for top-k)
 constexpr int MODE_EMIT_COEF = 4;       // backward coefficients w(row, col), bf16, k-block-major over the columns
 // modes whose epilogue goes through the per-warp 32 x 32 transpose buffers (row-major fp32 output)
-constexpr bool mode_transposes(int mode) { return mode != MODE_CLASS_LSE && mode != MODE_EMIT_COEF; }
+constexpr int MODE_EMIT_GRADT = 5;      // dense products, corrected and stored TRANSPOSED: the grad_s GEMM of the backward
+constexpr bool mode_transposes(int mode) {
+  return mode != MODE_CLASS_LSE && mode != MODE_EMIT_COEF && mode != MODE_EMIT_GRADT;
+}
 
 // NCTA = 1: one CTA computes a 128 x 256 tile (UMMA M=128).
 // NCTA = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x 256 tile (UMMA M=256); each CTA stages
@@ -172,6 +175,10 @@ struct Params {
   long long coef_ld;
   int coef_orient;
   float* coef_sums;          // [chunk][epilogue set][row]: sum over the unit's columns of the ROUNDED coefficients
+  // ---- MODE_EMIT_GRADT: out[dst(c)][r] = acc(r, c) - sub[c] * gt_rows(r, c), r < gt_valid_rows; sub arrives as the
+  // per-column additive term (s_sqnorm), dst(c) as the column label (labels; NULL: dst(c) = c)
+  const __nv_bfloat16* gt_rows;  // (ceil(n_support / 64), n_query, 64): element (r, c) at [c / 64][r][c % 64], or NULL
+  int gt_valid_rows;
 };
 
 // (the emit kind is a template parameter: one kernel with a runtime switch and logf inlined 64 times was > 64 KB
@@ -579,6 +586,36 @@ __device__ __forceinline__ float coef_chunk(float (&acc)[32], const float* __res
   return sum;
 }
 
+// MODE_EMIT_GRADT — the grad_s products of the tensor-core backward with their last step fused in.  Operand roles are
+// swapped against the forward (rows = features of Q^t, columns = supports, K = queries) so that the big operand, W^t,
+// streams once as the "bank" while Q^t stays in L2; the result is stored transposed, out[dst(c)][r] — 32 consecutive
+// rows per warp, one coalesced 128-byte store per column — minus colsum(W)[c] times the stored support row, read from
+// the transposed bank (64 contiguous bytes per thread and chunk), and in the row order of the caller's support
+// tensor.  (Unfused: products 16.8 ms with W^t re-read 8x from HBM, + a 26 GB finishing pass of 4.3 ms, at config 3.)
+__device__ __forceinline__ void gradt_chunk(const float (&acc)[32], const float* __restrict__ sub,
+                                            const int* __restrict__ dst_row, const Params& p, int row, int col0,
+                                            int n_valid) {
+  if (row < 0 || row >= p.gt_valid_rows || n_valid <= 0) return;
+  const uint4* __restrict__ r4 = reinterpret_cast<const uint4*>(
+      p.gt_rows + ((long long)(col0 >> 6) * p.n_query + row) * 64 + (col0 & 63));
+  float* __restrict__ out_col = p.emit_out + row;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {  // eight columns at a time: one 16-byte load of the stored rows, eight stores
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (p.gt_rows != nullptr) u = __ldg(r4 + v);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = v * 8 + k;
+      const float corr = (k & 1) ? __uint_as_float(w[k >> 1] & 0xffff0000u) : __uint_as_float(w[k >> 1] << 16);
+      if (i < n_valid) {
+        const long long dst = dst_row[i] >= 0 ? dst_row[i] : col0 + i;
+        out_col[dst * p.emit_ld] = fmaf(-sub[i], corr, acc[i]);
+      }
+    }
+  }
+}
+
 // MODE_EMIT_BLOCKBEST: best score of this thread's query row over one 32-column chunk (padding columns excluded).
 template <int EPI>
 __device__ __forceinline__ float chunk_best(const float (&acc)[32], const float* __restrict__ cadd, float qn,
@@ -844,6 +881,7 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           if (i < BN) {
             const int j = j0 + i;
             if (EPI == NW_EPI_EUCLID) pre_cadd[r] = j < n1 ? __ldg(p.s_sqnorm + j) : pos_inf;
+            else if (MODE == MODE_EMIT_GRADT) pre_cadd[r] = (p.s_sqnorm != nullptr && j < n1) ? __ldg(p.s_sqnorm + j) : 0.0f;
             else pre_cadd[r] = j < n1 ? 0.0f : neg_inf;
             pre_lab[r] = (p.labels != nullptr && j < p.n_support) ? __ldg(p.labels + j) : -1;
           }
@@ -905,6 +943,11 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 float acc[32];
                 tmem_ld_32x32(t_addr + cc * 32, acc);
                 tmem_ld_wait();
+                if (MODE == MODE_EMIT_GRADT) {
+                  gradt_chunk(acc, meta.cadd + cc * 32, meta.lab + cc * 32, p, row_valid ? row : -1, j0 + cc * 32,
+                              n1 - (j0 + cc * 32));
+                  continue;
+                }
                 if (MODE == MODE_EMIT_COEF) {
                   coef_rsum += coef_chunk<EPI>(acc, meta.cadd + cc * 32, meta.lab + cc * 32, qn, p.scale_log2 * kLn2, e_z,
                                                e_qy, p, row_valid ? row : -1, j0 + cc * 32, n1 - (j0 + cc * 32));
@@ -920,6 +963,13 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             tmem_ld_32x32(t_addr + c * 32, acc0);
             tmem_ld_32x32(t_addr + (c + 1) * 32, acc1);
             tmem_ld_wait();
+            if (MODE == MODE_EMIT_GRADT) {
+              const int rr = row_valid ? row : -1;
+              gradt_chunk(acc0, meta.cadd + c * 32, meta.lab + c * 32, p, rr, j0 + c * 32, n1 - (j0 + c * 32));
+              gradt_chunk(acc1, meta.cadd + (c + 1) * 32, meta.lab + (c + 1) * 32, p, rr, j0 + (c + 1) * 32,
+                          n1 - (j0 + (c + 1) * 32));
+              continue;
+            }
             if (MODE == MODE_EMIT_COEF) {
               const int rr = row_valid ? row : -1;
               coef_rsum += coef_chunk<EPI>(acc0, meta.cadd + c * 32, meta.lab + c * 32, qn, p.scale_log2 * kLn2, e_z, e_qy,
@@ -1616,6 +1666,7 @@ extern "C" int nw_forward_class_lse_peers(int epilogue, float scale, const void*
 
 // Internal emit kinds beyond include/nw_sm100.h's NW_EMIT_*: the backward coefficients (nw_backward_coefficients).
 constexpr int EMIT_COEF_INTERNAL = 100;
+constexpr int EMIT_GRADT_INTERNAL = 101;
 
 struct EmitExtra {
   int kslices = 1;                  // split-K (NW_EMIT_SCORES only): partial products, one output per slice
@@ -1625,6 +1676,8 @@ struct EmitExtra {
   int coef_orient = 0;
   float* coef_ws = nullptr;    // [chunks][COEF_SETS][n_rows] partial row sums
   float* coef_sums = nullptr;  // (n_rows) their fixed-order total
+  const void* gt_rows = nullptr;  // EMIT_GRADT_INTERNAL
+  int gt_valid_rows = 0;
 };
 
 constexpr int COEF_SETS = k1::QUAD_SETS;  // epilogue sets of the coefficient emit
@@ -1645,7 +1698,7 @@ static int emit_impl(int epilogue, float scale, const void* q_bf16, const float*
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NW_REQUIRE(epilogue == NW_EPI_EUCLID || epilogue == NW_EPI_LINEAR, NW_ERR_INVALID, "unknown epilogue %d", epilogue);
   NW_REQUIRE(emit_kind == NW_EMIT_SCORES || emit_kind == NW_EMIT_INFLUENCE || emit_kind == NW_EMIT_BLOCK_BEST ||
-                 emit_kind == EMIT_COEF_INTERNAL,
+                 emit_kind == EMIT_COEF_INTERNAL || emit_kind == EMIT_GRADT_INTERNAL,
              NW_ERR_INVALID, "unknown emit kind %d", emit_kind);
   NW_REQUIRE(q_bf16 && bank_bf16 && out, NW_ERR_INVALID, "NULL pointer argument");
   NW_REQUIRE(epilogue != NW_EPI_EUCLID || (q_sqnorm && s_sqnorm), NW_ERR_INVALID,
@@ -1653,7 +1706,8 @@ static int emit_impl(int epilogue, float scale, const void* q_bf16, const float*
   NW_REQUIRE(emit_kind != NW_EMIT_INFLUENCE || (labels && row_lse && p_query && qlabel), NW_ERR_INVALID,
              "influence needs labels, row_lse, p_query and qlabel");
   NW_REQUIRE(row_elems > 0 && row_elems % k1::BK == 0, NW_ERR_INVALID, "row_elems must be a positive multiple of 64");
-  NW_REQUIRE(emit_kind == EMIT_COEF_INTERNAL || (emit_kind == NW_EMIT_BLOCK_BEST ? ld_out >= n_query : ld_out >= n_support),
+  NW_REQUIRE(emit_kind == EMIT_COEF_INTERNAL || emit_kind == EMIT_GRADT_INTERNAL ||
+                 (emit_kind == NW_EMIT_BLOCK_BEST ? ld_out >= n_query : ld_out >= n_support),
              NW_ERR_INVALID, "ld_out must be >= n_support (>= n_query for NW_EMIT_BLOCK_BEST)");
   NW_REQUIRE(ex.kslices >= 1 && (ex.kslices == 1 || emit_kind == NW_EMIT_SCORES), NW_ERR_INVALID,
              "split-K is available for dense products only");
@@ -1705,6 +1759,8 @@ static int emit_impl(int epilogue, float scale, const void* q_bf16, const float*
   p.coef_ld = ex.coef_ld;
   p.coef_orient = ex.coef_orient;
   p.coef_sums = ex.coef_ws;
+  p.gt_rows = static_cast<const __nv_bfloat16*>(ex.gt_rows);
+  p.gt_valid_rows = ex.gt_valid_rows;
   int grid = plan.grid;
   if (p.kslices > 1) {  // more units than the plan knew of: size the persistent grid for all of them
     const long long units = (long long)plan.chunks * plan.q_tiles * p.kslices;
@@ -1730,6 +1786,18 @@ static int emit_impl(int epilogue, float scale, const void* q_bf16, const float*
            : (ncta == 2 ? k1::launch_forward<NW_EPI_LINEAR, 2, MODE_, true>(map_q, map_s, p, grid, stream)           \
                         : k1::launch_forward<NW_EPI_LINEAR, 1, MODE_, true>(map_q, map_s, p, grid, stream))
   if (emit_kind == NW_EMIT_SCORES) NW_LAUNCH_EMIT(k1::MODE_EMIT_SCORES);
+  else if (emit_kind == EMIT_GRADT_INTERNAL) {
+    static const int gradt_sets = [] {  // developer knob (same-box A/B): 2 = the 8-warp epilogue
+      const char* e = getenv("NW_B200_GRADT_SETS");
+      return e && *e ? atoi(e) : 4;
+    }();
+    if (gradt_sets == 4) {
+      p.sets = k1::QUAD_SETS;
+      NW_LAUNCH_EMIT4(k1::MODE_EMIT_GRADT);
+    } else {
+      NW_LAUNCH_EMIT(k1::MODE_EMIT_GRADT);
+    }
+  }
   else if (emit_kind == EMIT_COEF_INTERNAL) {
     // exp, reciprocal square root, table lookup, rounding and 64-byte stores per pair: latency-bound like the
     // influence transform, so four epilogue sets
@@ -1801,6 +1869,26 @@ extern "C" int nw_backward_coefficients(int epilogue, float scale, int orientati
   return emit_impl(epilogue, scale, rows_bf16, rows_sqnorm, int(n_rows), cols_bf16, cols_sqnorm, col_meta, n_cols,
                    row_elems, EMIT_COEF_INTERNAL, row_lse, nullptr, row_labels, reinterpret_cast<float*>(out_bf16),
                    /*ld_out=*/0, ex, stream_);
+}
+
+// Tensor-core backward, grad_s in one launch: out[dst(c)][r] = sum_k a[r][k] * b[c][k] - col_sub[c] * rows_t(r, c) for
+// r < n_out_cols (see gradt_chunk).  a: Q^t (n_a >= n_out_cols rows, the features), b: W^t (n_b rows, the supports).
+extern "C" int nw_dense_products_transposed(const void* a_bf16, int64_t n_a, const void* b_bf16, int64_t n_b,
+                                            int k_elems, const float* col_sub, const void* rows_t_bf16,
+                                            const int32_t* dst_rows, int n_out_cols, float* out, int64_t ld_out,
+                                            void* stream_) {
+  NW_REQUIRE(n_a > 0 && n_a < (int64_t(1) << 31) - 512, NW_ERR_UNSUPPORTED, "n_a must be in (0, 2^31 - 512)");
+  NW_REQUIRE(n_out_cols > 0 && n_out_cols <= n_a && ld_out >= n_out_cols, NW_ERR_INVALID,
+             "need 0 < n_out_cols <= n_a and ld_out >= n_out_cols");
+  NW_REQUIRE((col_sub == nullptr) == (rows_t_bf16 == nullptr), NW_ERR_INVALID,
+             "col_sub and rows_t_bf16 go together");
+  NW_REQUIRE(rows_t_bf16 == nullptr || (reinterpret_cast<uintptr_t>(rows_t_bf16) & 15) == 0, NW_ERR_INVALID,
+             "rows_t_bf16 must be 16-byte aligned");
+  EmitExtra ex;
+  ex.gt_rows = rows_t_bf16;
+  ex.gt_valid_rows = n_out_cols;
+  return emit_impl(NW_EPI_LINEAR, 1.0f, a_bf16, nullptr, int(n_a), b_bf16, col_sub, dst_rows, n_b, k_elems,
+                   EMIT_GRADT_INTERNAL, nullptr, nullptr, nullptr, out, ld_out, ex, stream_);
 }
 
 // Tensor-core backward, step 2: out[ks][r][c] = sum over K slice ks of a[r][k] * b[c][k]  (both operands bf16,

@@ -98,6 +98,22 @@ def test_only_the_requested_gradients_are_computed(cuda_lib):
     assert st.grad is None
 
 
+def test_support_gradient_alone(cuda_lib):
+    """Only the support is trained: the coefficients are computed with the operand roles swapped (rows = supports),
+    no W and no grad_q products; unsorted labels, a batch that is not a multiple of 4 (scalar table loads) and one
+    that is (16-byte loads)."""
+    import nwhead_b200
+
+    for B in (70, 200):
+        q, s, y, g = _data(B, 2500, 96, 9, B, False)
+        head = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), 9, backward_path="tensor")
+        qt = torch.from_numpy(q).to(DEV)
+        st = torch.from_numpy(s).to(DEV).requires_grad_(True)
+        (head(qt, st, torch.from_numpy(y).to(DEV)) * torch.from_numpy(g).to(DEV)).sum().backward()
+        want = O.nw_backward(q, s, y, 9, g, "euclidean")[1]
+        assert np.abs(st.grad.cpu().numpy() - want).max() < GRAD_TOL * np.abs(want).max()
+
+
 def test_zero_distance_contributes_no_gradient(cuda_lib):
     """A query that coincides with a support row: torch.cdist's backward yields 0 for that pair (and so does the
     direct path); the bf16 recompute sees d2 <= 0 there and must not produce inf / NaN."""

@@ -91,6 +91,15 @@ def main():
         torch.cuda.synchronize()
         assert torch.isfinite(q8.grad).all() and torch.isfinite(sx.grad).all()
     print("direct forward/backward: ok", flush=True)
+    # tensor-core backward: coefficient emit in both orientations, split-K products, fused transposed grad_s launch
+    head_t = nwhead_b200.NWHead(nwhead_b200.get_kernel("euclidean"), c, backward_path="tensor")
+    for need_q, need_s in ((True, True), (True, False), (False, True)):
+        qa = qt.clone().requires_grad_(need_q)
+        sa = torch.from_numpy(s).to(DEV).requires_grad_(need_s)
+        head_t(qa, sa, torch.from_numpy(y).to(DEV)).sum().backward()
+        torch.cuda.synchronize()
+        assert (not need_q or torch.isfinite(qa.grad).all()) and (not need_s or torch.isfinite(sa.grad).all())
+    print("tensor-core forward/backward: ok", flush=True)
     print("SANITIZE_DRIVER_OK", flush=True)
 
 

@@ -153,6 +153,11 @@ struct Params {
   int krot_step;            // query group qg walks the k-blocks of every tile starting at (qg * krot_step) % count:
                             // the CTA pairs that share a support tile then ask the L2 for DIFFERENT lines at any
                             // one time (0: all start at k-block 0)
+  int* tile_gate;           // [chunk][2] arrival counters, zeroed before the launch, or NULL: the producers of the CTAs
+                            // that share a chunk in a wave start every support tile together (see the producer)
+  int l2_prefetch;          // developer experiment (NW_B200_L2_PREFETCH=<k-blocks ahead>, 0 = off): support boxes are
+                            // prefetched into L2 this far ahead of the ring; > 0: by query group 0 of every chunk
+                            // only, < 0: by every group (distance = -value)
   int stagger_ns;           // developer probe (NW_B200_STAGGER_NS): query group g delays its first load by g * this
   int debug_skip_epilogue;  // developer probe (NW_B200_DEBUG_SKIP_EPI=1): accumulators are released unread -> the
                             // speed of the TMA + MMA mainloop alone (results are garbage)
@@ -725,8 +730,37 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int t0 = g * p.tiles_per_chunk;
         const int t1 = min(t0 + p.tiles_per_chunk, p.s_tiles);
         const int q_row0 = (qg * NCTA + int(cta_rank)) * BM;
+        // CTAs that work on this chunk at the same time (its units that fall into this worker's wave)
+        int gate_ctas = 0;
+        int* gate = nullptr;
+        if (p.tile_gate != nullptr) {
+          const int wave = u / n_workers;
+          const int lo = max(g * p.q_groups, wave * n_workers);
+          const int hi = min(g * p.q_groups + p.q_groups, (wave + 1) * n_workers);
+          gate_ctas = (hi - lo) * NCTA;
+          gate = p.tile_gate + 2 * g + (g * p.q_groups < wave * n_workers ? 1 : 0);
+        }
         for (int t = t0; t < t1; ++t) {
           const int s_row0 = t * BN + int(cta_rank) * C::B_ROWS;
+          if (gate_ctas > NCTA) {
+            // Start the tile together with the other CTAs that read it: a support line is only cheap to share while
+            // the requests for it are in flight together (lines prefetched into L2 3 us early were gone when the
+            // ring asked for them, profiles/r2_k1_ring_depth_vs_dram.txt), and a 6-stage ring lets the workers drift
+            // by a couple of microseconds.  Measured at config 3 on a box that re-read the bank 3.5x: 18.4 -> 6.3 GB
+            // from HBM per launch (the bank once + the chunks cut by a wave boundary), 1.17 -> 1.25 GHz under the
+            // power cap, 263 k -> 278.6 k queries/s.  The producer runs up to a ring ahead of the MMAs, so the wait
+            // costs the tensor pipe ~1 %.  Bounded: a straggler (a CTA that is not resident yet) delays the others
+            // by 6 us once, then the gate is ignored for the rest of the unit; nothing can hang.
+            atomicAdd(gate, 1);
+            const int target = gate_ctas * (t - t0 + 1);
+            const long long c_start = clock64();
+            while (ld_acquire_gpu_s32(gate) < target) {
+              if (clock64() - c_start > 8000) {
+                gate_ctas = 0;
+                break;
+              }
+            }
+          }
           if (bulk_tile(t)) {
             const uint32_t ms = mc % META_SLOTS;
             mbar_wait(smem_u32(&tail->mempty[ms]), ((mc / META_SLOTS) & 1u) ^ 1u);
@@ -738,8 +772,14 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           }
           const int nkb = kb1 - kb0;
           const int rot = (qg * p.krot_step) % nkb;  // (the sum over k does not care where it starts)
+          const int pf = p.l2_prefetch > 0 ? (qg == 0 ? p.l2_prefetch : 0) : -p.l2_prefetch;
           for (int i = 0; i < nkb; ++i, ++it) {
             const int kb = kb0 + (i + rot < nkb ? i + rot : i + rot - nkb);
+            if (pf > 0) {  // the box this worker's ring will ask for `pf` k-blocks from now
+              const int ahead = i + pf;
+              const int tp = t + ahead / nkb;
+              if (tp < t1) tma_prefetch_l2_3d(&map_s, 0, tp * BN + int(cta_rank) * C::B_ROWS, kb0 + ahead % nkb);
+            }
             const uint32_t s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
@@ -1099,10 +1139,13 @@ nw_forward_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void fill_kernel(float* __restrict__ a, long long n, float* __restrict__ b, long long nb, float v) {
+// a[0, n) = v; b[0, nb) = v except b[z0, z1), which is cleared to integer zero (the tile gates inside `side`)
+__global__ void fill_kernel(float* __restrict__ a, long long n, float* __restrict__ b, long long nb, float v,
+                            long long z0, long long z1) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = v;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) b[i] = v;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride)
+    b[i] = (i >= z0 && i < z1) ? 0.0f : v;
 }
 
 __device__ __forceinline__ float logaddexp_f(float a, float b) {
@@ -1430,7 +1473,7 @@ extern "C" int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t
   plan->cta_pair = ncta == 2 ? 1 : 0;
   // chunk-boundary partials: [chunk][query][2 slots][up to 4 epilogue sets]  (+ room for the further sets' tables
   // is added by the caller, see nw_forward_epilogue_sets / forward_impl)
-  plan->side_elems = int64_t(plan->chunks) * n_query * 2 * k1::QUAD_SETS;
+  plan->side_elems = int64_t(plan->chunks) * n_query * 2 * k1::QUAD_SETS + 2 * plan->chunks;  // + the tile gates
   return NW_OK;
 }
 
@@ -1548,7 +1591,8 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
 
   k1::fill_kernel<<<sm_count() * 4, 256, 0, stream>>>(tables[0], fill_local ? table_elems : 0, side,
                                                       (long long)plan.side_elems + (sets - 1) * table_elems,
-                                                      -INFINITY);
+                                                      -INFINITY, (long long)plan.side_elems - 2 * plan.chunks,
+                                                      (long long)plan.side_elems);
   NW_CUDA_OK(cudaGetLastError());
   host_timer.lap("fill launch");
 
@@ -1604,6 +1648,24 @@ static int forward_impl(int epilogue, float scale, const void* q_bf16, const flo
     }();
     p.stagger_ns = stagger;
     p.krot_step = k_rotation_step(plan.q_tiles, p.kblocks);
+    static const int l2_prefetch = [] {
+      const char* e = getenv("NW_B200_L2_PREFETCH");
+      return e && *e ? atoi(e) : 0;
+    }();
+    p.l2_prefetch = l2_prefetch;
+    static const int tile_gate = [] {  // NW_B200_TILE_GATE=0 switches the per-tile producer gate off (A/B runs)
+      const char* e = getenv("NW_B200_TILE_GATE");
+      return e && *e ? atoi(e) : 1;
+    }();
+    // Only where the workers of a chunk stay in step by themselves — long, MMA-bound tiles (d >= 1024) and long units:
+    // with 10 000 classes at d = 512 (uneven class-end work per tile) the gate cost 6 %, with 17-tile units
+    // (N = 160 000) 3 %; at d = 1024 it gains 2 % even off the power cap (profiles/r2_k1_ring_depth_vs_dram.txt).
+    const bool gate_shape = p.kblocks >= 16 && plan.tiles_per_chunk >= 32 && plan.q_tiles >= 2 &&
+                            plan.q_tiles <= plan.grid / ncta;
+    p.tile_gate = (tile_gate != 0 && (gate_shape || tile_gate == 2))
+                      ? reinterpret_cast<int*>(side + plan.side_elems) - 2 * plan.chunks
+                      : nullptr;
+    if (plan.q_tiles < 2 || plan.q_tiles > plan.grid / ncta) p.tile_gate = nullptr;  // (2 = forced: A/B runs)
     static const int bulk_meta = [] {  // developer knob: 0 = every tile's metadata staged by the epilogue sets
       const char* e = getenv("NW_B200_META_BULK");
       return e && *e ? atoi(e) : 1;

@@ -87,6 +87,16 @@ def finish(raw: torch.Tensor, rows_bf16, sums, perm, d: int) -> torch.Tensor:
     return out
 
 
+def choose_kslices(units: int, workers: int, kb: int) -> int:
+    """Split K so that the units fill whole waves of persistent workers: cost = waves x (k-blocks per unit + the
+    per-unit pipeline fill and epilogue, ~16 k-blocks' worth).  B=4096 against config 3 is 128 units on 74 CTA pairs
+    (two waves, the second 73 % full) unsplit.  The result follows the library's own rounding: no empty slice."""
+    kslices = min(range(1, max(1, min(64, kb // 8)) + 1),
+                  key=lambda ks: -(-units * ks // workers) * (-(-kb // ks) + 16))
+    per = -(-kb // kslices)
+    return -(-kb // per)
+
+
 def dense_products(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a (kb, n_a, 64), b (kb, n_b, 64) bf16 k-block-major -> a @ b^t (n_a, n_b) fp32 on the tensor cores.
     Skinny problems are split along K so that every SM has a unit; the partial products are summed here."""
@@ -98,13 +108,7 @@ def dense_products(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     plan = _abi.forward_plan(n_a, n_b)
     units = plan.chunks * plan.q_tiles
     workers = torch.cuda.get_device_properties(dev).multi_processor_count // (2 if plan.cta_pair else 1)
-    # split K so that the units fill whole waves of persistent workers: cost = waves x (k-blocks per unit + the
-    # per-unit pipeline fill and epilogue, ~16 k-blocks' worth); B=4096 against config 3 is 128 units on 74 CTA
-    # pairs (two waves, the second 73 % full) unsplit
-    kslices = min(range(1, max(1, min(64, kb // 8)) + 1),
-                  key=lambda ks: -(-units * ks // workers) * (-(-kb // ks) + 16))
-    per = -(-kb // kslices)
-    kslices = -(-kb // per)  # the library's own rounding: no empty slice
+    kslices = choose_kslices(units, workers, kb)
     ld = (n_b + 3) // 4 * 4
     out = torch.empty((kslices, n_a, ld), dtype=torch.float32, device=dev)
     check(lib.nw_dense_products(ptr(a), n_a, ptr(b), n_b, kb * 64, kslices, ptr(out), ld, n_a * ld, stream_of(dev)),

@@ -142,3 +142,17 @@ def test_tensor_backward_routing():
     assert not wants_tensor_path(4096, 1280000, 3, "auto")       # per-query supports are not a shared GEMM
     assert not wants_tensor_path(4096, 1280000, 2, "direct")
     assert wants_tensor_path(2, 30, 2, "tensor") and not wants_tensor_path(2, 30, 3, "tensor")
+
+
+def test_split_k_choice_fills_waves_and_leaves_no_empty_slice():
+    """nwhead_b200.backward.choose_kslices (host logic of nw_dense_products' split-K)."""
+    from nwhead_b200.backward import choose_kslices
+
+    assert choose_kslices(40000, 74, 64) == 1          # plenty of units: no split
+    assert choose_kslices(1, 74, 3) == 1               # too short to split
+    ks = choose_kslices(128, 74, 20000)                # config 3 grad_q: 128 units on 74 CTA pairs
+    assert 128 * ks % 74 <= 74 and -(-128 * ks // 74) * (-(-20000 // ks) + 16) < 2 * (20000 + 16)
+    for units, kb in [(8, 20000), (32, 20000), (9, 130), (8, 2500), (3, 17)]:
+        ks = choose_kslices(units, 74, kb)
+        per = -(-kb // ks)
+        assert 1 <= ks <= 64 and per * (ks - 1) < kb <= per * ks  # every slice holds at least one k-block

@@ -140,7 +140,7 @@ typedef struct nw_forward_plan_t {
   int tiles_per_chunk; /* support tiles per chunk */
   int grid;            /* persistent CTAs launched */
   int cta_pair;        /* 1: CTA pairs (cluster of 2, tcgen05 cta_group::2, 256x256 tiles); 0: single CTAs */
-  int64_t side_elems;  /* floats of scratch `side` required: chunks * B * 8 */
+  int64_t side_elems;  /* floats of scratch `side` required: chunks * B * 8 + 2 * chunks (the per-tile producer gates) */
 } nw_forward_plan_t;
 
 NW_API int nw_forward_plan(int n_query, int64_t n_support, nw_forward_plan_t* plan_out);
